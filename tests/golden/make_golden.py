@@ -171,7 +171,10 @@ def golden_resnet_tiny():
     ref_sd = net.state_dict()
     sd = synth.fill_state_dict(ref_sd)
     net.load_state_dict(sd)
-    net.eval()
+    net.train()                                  # BN on batch statistics (never eval() on raw stats) ...
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()                             # ... with the three Dropout2d sites disabled
     x = synth.rand("resnet.x", b, 3, hh, ww)
     label = synth.depth_label("resnet.label", b, hh, ww, 0.5, 10.5)
     with torch.no_grad():

@@ -144,7 +144,7 @@ def test_full_network_matches_reference(golden):
     x = synth.rand("resnet.x", b, 3, hh, ww)
     label = synth.depth_label("resnet.label", b, hh, ww, 0.5, 10.5)
     with torch.no_grad():
-        out = O.acan_forward(x, sd, [1, 1, 1, 1], "OR", training=False)
+        out = O.acan_forward(x, sd, [1, 1, 1, 1], "OR", training=True)     # BN on batch statistics, dropout off
     close(out["y"].reshape(-1)[T(g["y_idx"])], T(g["y_val"]), 1e-4)
     close(out["sim_map"].reshape(-1)[T(g["sim_idx"])], T(g["sim_val"]), 1e-4)
     close(O.inference(out["y"], "OR", "soft", 0.72, 10.0, 80), T(g["depth_soft"]), 1e-4)
