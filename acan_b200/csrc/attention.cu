@@ -1,0 +1,622 @@
+// attention.cu -- pixel-to-pixel affinity, row softmax and aggregation on tcgen05 tensor cores.
+//
+// Replaces PixelAttentionBlock_.forward_att (reference sadecoder.py:42-49) and the matmul / permute of
+// SelfAttentionBlock_.forward (sadecoder.py:85-87), with Q = K = F because f_query is f_key (:30):
+//     S = F^T F * dk^-1/2        [N,N] per image
+//     P = softmax_rows(S)        (= sim_map)
+//     O[c,i] = sum_j V[c,j] P[i,j]    written directly in NCHW ([B,dv,N]), no transpose pass
+// and, fused into the same tensor-core pass, the attention loss of losses.py:12-62.
+//
+// Why three tensor-core passes instead of one flash-style kernel: the aggregation accumulator for a
+// 128-query tile is 128 x dv = 128 x 2048 fp32 = 1 MB, four times the 256 KB of TMEM an SM has, so a single
+// kernel would recompute S once per dv slice (>= 5x).  Instead
+//   pass 1  STATS : S tiles -> per-row (max, sum-exp) partials -> combined to (m_i, l_i)       2*N^2*dk  FLOP
+//   pass 2  PROBS : S tiles again -> P = exp2(S*c - m_i)/l_i, final, fp16, written once          2*N^2*dk  FLOP
+//                   (+ optional fp32 sim_map, + optional fused KL against the on-the-fly target)
+//   pass 3  PV    : O^T = V P^T as a plain TMA/UMMA GEMM, accumulators never rescaled           2*N^2*dv  FLOP
+// P (2*N^2 bytes / image, 4 MB at N = 1408) round-trips through the 126 MB L2.  Executed / algorithmic
+// FLOPs = (2*dk + dv) / (dk + dv) = 1.2.  Exact row statistics up front are also what the KL clamp
+//  and the backward pass need.
+//
+// All three passes are one warp-specialised kernel template (gemm_kernel<MODE>):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor.3d, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN<=256, K=16)
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b.x32 -> registers -> global), TMEM double-buffered so the
+//              epilogue of tile t overlaps the MMAs of tile t+1
+// persistent over a static tile schedule, grid = min(#tiles, 148).  Operands are fp16 (11-bit significand:
+// the rounding of TF32, at the bf16 MMA rate) with fp32 accumulation; bf16 operands miss the 1e-3 parity
+// bar on sim_map.
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace acan {
+
+// from kl.cu
+__global__ void nearest_bins_kernel(const float* __restrict__ label, float* __restrict__ bins, int B, int H, int W);
+__global__ void ordered_sum_kernel(const float* __restrict__ vals, int64_t n, float scale, float* __restrict__ out);
+
+namespace {
+
+constexpr int BM = 128;                 // UMMA M (TMEM lanes)
+constexpr int BK = 64;                  // K elements per pipeline stage: 64 fp16 = one 128 B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kMaxBN = 256;
+constexpr int kMinBN = 64;
+constexpr int kTmemCols = 512;          // 2 accumulator buffers x 256 fp32 columns
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024; // operand ring; barriers + alignment slack come on top
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2 };
+
+struct GemmArgs {
+  int batch, m_tiles, n_tiles, k_steps;
+  int m_rows;          // valid rows of A per image (N queries, or dv channels)
+  int n_cols;          // valid rows of B per image (N keys, or N queries)
+  int bn;              // tile width (multiple of 32, <= 256)
+  int stages;
+  uint32_t idesc;
+  float c;             // scale * log2(e)
+  // MODE_STATS
+  float2* part;        // [B, n_tiles, m_rows] (m2, l) partials
+  // MODE_PROBS
+  const float2* stats; // [B, N] final (m2, l)
+  __half* p_out;       // [B, N, N] fp16 or null
+  float* sim_out;      // [B, N, N] fp32 or null
+  const float* logbin; // [B, N] ln(bin) (-inf for bin 0) or null  -> fused KL
+  const float* lnz;    // [B, N] ln(Z_i) of the target affinity (unused when bin_i == 0)
+  float* kl_part;      // [B, n_tiles, N] per-row partial losses
+  // MODE_PV
+  float* o_out;        // [B, m_rows, n_cols] fp32
+};
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t a_bytes = BM * BK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(g.bn) * BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + static_cast<size_t>(g.stages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.batch * g.m_tiles * g.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 128); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % g.n_tiles;
+        const int mt = (tile / g.n_tiles) % g.m_tiles;
+        const int b = tile / (g.n_tiles * g.m_tiles);
+        for (int ks = 0; ks < g.k_steps; ++ks) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&bars->full[stage], stage_bytes);
+          tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, mt * BM, b);
+          tma_load_3d(sa + a_bytes, &tmap_b, &bars->full[stage], ks * BK, nt * g.bn, b);
+          if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+        for (int ks = 0; ks < g.k_steps; ++ks) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_f16(d_tmem, umma_desc_k_sw128(sa + k * UMMA_K * 2), umma_desc_k_sw128(sb + k * UMMA_K * 2), g.idesc,
+                     (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);            // smem slot free once these MMAs have read it
+          if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[acc]);            // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % g.n_tiles;
+      const int mt = (tile / g.n_tiles) % g.m_tiles;
+      const int b = tile / (g.n_tiles * g.m_tiles);
+      const int row = mt * BM + row_in_tile;
+      const bool row_ok = row < g.m_rows;
+      const int col0 = nt * g.bn;
+      const int nvalid = min(g.bn, g.n_cols - col0);   // >= 1 by construction of n_tiles
+      const int chunks = (nvalid + 31) >> 5;
+
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
+
+      if constexpr (MODE == MODE_STATS) {
+        float m = -INFINITY, l = 0.f;                   // m in raw dot-product units
+        for (int ch = 0; ch < chunks; ++ch) {
+          float v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          const int nv = nvalid - ch * 32;
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { if (j >= nv) v[j] = -INFINITY; cm = fmaxf(cm, v[j]); }
+          if (cm > m) { l *= ex2_approx((m - cm) * g.c); m = cm; }
+          const float mc = m * g.c;
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += ex2_approx(fmaf(v[j], g.c, -mc));
+          l += s;
+        }
+        if (row_ok) g.part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = make_float2(m * g.c, l);
+      } else if constexpr (MODE == MODE_PROBS) {
+        float m2 = 0.f, inv_l = 0.f, la_i = 0.f, lnz_i = 0.f, log2_l = 0.f;
+        const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
+        {
+          const float2 st = g.stats[brow];
+          m2 = st.x; inv_l = 1.0f / st.y; log2_l = lg2_approx(st.y);
+        }
+        const bool kl = g.logbin != nullptr;
+        bool kl_row = false;
+        if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; kl_row = row_ok && la_i > -INFINITY; }
+        float kl_acc = 0.f;
+        const float* la_cols = kl ? g.logbin + static_cast<size_t>(b) * g.n_cols + col0 : nullptr;
+        __half* prow = g.p_out ? g.p_out + (brow * g.n_cols + col0) : nullptr;
+        float* srow = g.sim_out ? g.sim_out + (brow * g.n_cols + col0) : nullptr;
+        for (int ch = 0; ch < chunks; ++ch) {
+          float v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          const int nv = nvalid - ch * 32;              // valid columns in this chunk (multiple of 8 since N % 8 == 0)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], g.c, -m2);      // log2 of the un-normalised probability
+          if (kl_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nv) {
+                const float la_j = __ldg(la_cols + ch * 32 + j);
+                const float lnr = -fabsf(la_i - la_j);                       // ln min(a_i/a_j, a_j/a_i); -inf if a_j = 0
+                const float lnw = lnr - lnz_i;                               // ln W_ij
+                const float lnq = (v[j] - log2_l) * kLn2;                    // ln Q_ij, exact from the logits
+                const float w = ex2_approx(lnw * kLog2e);                    // 0 when a_j = 0
+                const float lr = fminf(fmaxf(lnw - lnq, -18.420680744f), 18.420680744f);   // ln clamp(W/Q, 1e-8, 1e8)
+                kl_acc += (w > 0.f) ? w * lr : 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
+          if (row_ok) {
+            if (prow) {
+              uint4* dst = reinterpret_cast<uint4*>(prow + ch * 32);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q * 8 < nv)
+                  dst[q] = make_uint4(pack_half2(v[q * 8 + 0], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                                      pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+            }
+            if (srow) {
+              float4* dst = reinterpret_cast<float4*>(srow + ch * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+          }
+        }
+        if (kl && row_ok) g.kl_part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = kl_acc;
+      } else {  // MODE_PV: rows = value channels, columns = query positions
+        float* orow = g.o_out + ((static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0)) * g.n_cols + col0);
+        for (int ch = 0; ch < chunks; ++ch) {
+          float v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          const int nv = nvalid - ch * 32;
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(orow + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
+        }
+      }
+
+      tc_fence_before();
+      mbar_arrive(&bars->tmem_empty[acc]);              // 128 arrivals release the accumulator buffer
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ small kernels
+
+// F fp32 [B, dk, N]  ->  Fh fp16 [B, N, dk]   (position-major rows: the K-major operand of S = F^T F)
+__global__ void __launch_bounds__(256) pack_feat_kernel(const float* __restrict__ f, __half* __restrict__ fh, int dk, int N) {
+  __shared__ float tile[64][65];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const float* src = f + static_cast<size_t>(b) * dk * N;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int c = i >> 6, n = i & 63;
+    tile[c][n] = (n0 + n < N) ? src[static_cast<size_t>(c0 + c) * N + n0 + n] : 0.f;
+  }
+  __syncthreads();
+  __half* dst = fh + static_cast<size_t>(b) * N * dk;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    const int n = i >> 5, c2 = (i & 31) * 2;
+    if (n0 + n < N) {
+      // clamp to the fp16 range: post-BN/ReLU activations never get there, +-inf would poison the softmax
+      const float a = fminf(fmaxf(tile[c2][n], -65504.f), 65504.f), bq = fminf(fmaxf(tile[c2 + 1][n], -65504.f), 65504.f);
+      *reinterpret_cast<__half2*>(dst + static_cast<size_t>(n0 + n) * dk + c0 + c2) = __floats2half2_rn(a, bq);
+    }
+  }
+}
+
+// V fp32 [B, dv, N] -> Vh fp16, same layout (keys contiguous: the K-major A operand of O^T = V P^T)
+__global__ void __launch_bounds__(256) pack_value_kernel(const float4* __restrict__ v, uint4* __restrict__ vh, int64_t n8) {
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float4 a = ldg_stream(v + 2 * i), b = ldg_stream(v + 2 * i + 1);
+    auto cl = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
+    vh[i] = make_uint4(pack_half2(cl(a.x), cl(a.y)), pack_half2(cl(a.z), cl(a.w)), pack_half2(cl(b.x), cl(b.y)), pack_half2(cl(b.z), cl(b.w)));
+  }
+}
+
+// (m2, l) partials over key tiles -> final row statistics
+__global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int n_tiles, int N, int B) {
+  const int64_t total = static_cast<int64_t>(B) * N;
+  for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
+    const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
+    const float2* p = part + static_cast<size_t>(b) * n_tiles * N + i;
+    float m = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) m = fmaxf(m, p[static_cast<size_t>(t) * N].x);
+    float l = 0.f;
+    for (int t = 0; t < n_tiles; ++t) { const float2 v = p[static_cast<size_t>(t) * N]; l += v.y * ex2_approx(v.x - m); }
+    stats[q] = make_float2(m, l);
+  }
+}
+
+// per row: ln(bin) and ln(Z_i), Z_i = sum_j min(a_i/a_j, a_j/a_i)   (target-affinity normaliser, losses.py:40-46)
+__global__ void __launch_bounds__(256) gt_norm_kernel(const float* __restrict__ bins, float* __restrict__ logbin, float* __restrict__ lnz, int N) {
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const int b = static_cast<int>(row / N);
+  const float* a = bins + static_cast<size_t>(b) * N;
+  const float ai = a[row - static_cast<int64_t>(b) * N];
+  float z = 0.f;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    const float aj = a[j], lo = fminf(ai, aj), hi = fmaxf(ai, aj);
+    z += lo > 0.f ? lo / hi : 0.f;
+  }
+  z = warp_sum(z);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = z;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    logbin[row] = ai > 0.f ? logf(ai) : -INFINITY;
+    lnz[row] = t > 0.f ? logf(t) : 0.f;
+  }
+}
+
+// selected rows of sim_map on CUDA cores (3 rows per image for the TensorBoard figure, vis_utils.py:107-121)
+__global__ void __launch_bounds__(256) sim_rows_kernel(const __half* __restrict__ fh, const float2* __restrict__ stats,
+                                                        const int* __restrict__ rows, float* __restrict__ out,
+                                                        int n_rows, int N, int dk, float c) {
+  extern __shared__ float qrow[];
+  const int b = blockIdx.y, r = blockIdx.x, i = rows[r];
+  const __half* base = fh + static_cast<size_t>(b) * N * dk;
+  for (int k = threadIdx.x; k < dk; k += 256) qrow[k] = __half2float(base[static_cast<size_t>(i) * dk + k]);
+  __syncthreads();
+  const float2 st = stats[static_cast<size_t>(b) * N + i];
+  const int lane = threadIdx.x & 31;
+  for (int j = threadIdx.x >> 5; j < N; j += 8) {
+    const __half* kj = base + static_cast<size_t>(j) * dk;
+    float acc = 0.f;
+    for (int k = lane * 2; k < dk; k += 64) {
+      const float2 kv = __half22float2(*reinterpret_cast<const __half2*>(kj + k));
+      acc += kv.x * qrow[k] + kv.y * qrow[k + 1];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[(static_cast<size_t>(b) * n_rows + r) * N + j] = ex2_approx(fmaf(acc, c, -st.x)) / st.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 tensor [batch][rows][inner] (inner contiguous), box = {64, box_rows, 1}, 128 B swizzle, OOB -> 0
+int make_tmap(CUtensorMap* m, const void* base, int inner, int rows, int batch, size_t row_pitch_bytes, size_t batch_pitch_bytes, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch_bytes), static_cast<cuuint64_t>(batch_pitch_bytes)};
+  cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%d rows=%d batch=%d box_rows=%d)", (int)r, inner, rows, batch, box_rows);
+  return 0;
+}
+
+// tile width: minimise (waves over 148 SMs) x (per-tile cost ~ bn + fixed overhead)
+int choose_bn(int n_cols, int other_tiles) {
+  int best = kMinBN;
+  double best_cost = 1e30;
+  for (int bn = kMinBN; bn <= kMaxBN; bn += 32) {
+    const int nt = (n_cols + bn - 1) / bn;
+    const long tiles = static_cast<long>(nt) * other_tiles;
+    const long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+struct Workspace {
+  __half* fh;      // [B, N, dk]
+  __half* vh;      // [B, dv, N]
+  __half* p;       // [B, N, N]
+  float2* part;    // [B, ceil(N/kMinBN), N]
+  float2* stats;   // [B, N]   (copy of row_stats, used by acan_attn_rows / loss_fused)
+  float* bins;     // [B, N]
+  float* logbin;   // [B, N]
+  float* lnz;      // [B, N]
+  float* kl_part;  // [B, ceil(N/kMinBN), N]
+  size_t bytes;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+Workspace carve(void* base, int B, int N, int dk, int dv) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return reinterpret_cast<uint8_t*>(base) + o; };
+  const size_t nt_max = (N + kMinBN - 1) / kMinBN;
+  w.fh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * dk * 2));
+  w.vh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * dv * N * 2));
+  w.p = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * N * 2));
+  w.part = reinterpret_cast<float2*>(take(static_cast<size_t>(B) * nt_max * N * 8));
+  w.stats = reinterpret_cast<float2*>(take(static_cast<size_t>(B) * N * 8));
+  w.bins = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.logbin = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.lnz = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.kl_part = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
+  w.bytes = off;
+  return w;
+}
+
+template <int MODE>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream_t st) {
+  const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + static_cast<size_t>(g.bn) * BK * 2;
+  int stages = static_cast<int>(kSmemBudget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  g.stages = stages;
+  const size_t smem = stages * stage_bytes + sizeof(PipeBarriers) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ACAN_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = g.batch * g.m_tiles * g.n_tiles;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  gemm_kernel<MODE><<<grid, kGemmThreads, smem, st>>>(ta, tb, g);
+  return launch_status("acan gemm_kernel");
+}
+
+int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
+  if (B <= 0 || N < 8 || (N % 8) != 0) return fail(ACAN_ERR_BAD_ARG, "%s: need B > 0 and N a positive multiple of 8 (B=%d N=%d)", who, B, N);
+  if (dk <= 0 || (dk % 64) != 0) return fail(ACAN_ERR_BAD_ARG, "%s: dk=%d must be a positive multiple of 64", who, dk);
+  if (dv < 0 || (dv % 128) != 0) return fail(ACAN_ERR_BAD_ARG, "%s: dv=%d must be a multiple of 128", who, dv);
+  if (static_cast<int64_t>(B) * N > 0x7fffffffLL / 2) return fail(ACAN_ERR_BAD_ARG, "%s: B*N too large", who);
+  return 0;
+}
+
+// passes 1+2 over S = Fh Fh^T: statistics, then probabilities / sim_map / fused KL
+int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map, bool kl, int B, int N, int dk, float scale, cudaStream_t st,
+                 bool need_stats, int* key_tiles) {
+  const int m_tiles = (N + BM - 1) / BM;
+  const int bn = choose_bn(N, B * m_tiles);
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, w.fh, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
+  if (int e = make_tmap(&tb, w.fh, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn)) return e;
+  GemmArgs g;
+  std::memset(&g, 0, sizeof(g));
+  g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = dk / BK;
+  g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn); g.c = scale * kLog2e;
+  if (need_stats) {
+    g.part = w.part;
+    if (int e = launch_gemm<MODE_STATS>(ta, tb, g, st)) return e;
+    combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, g.n_tiles, N, B);
+    if (int e = launch_status("combine_stats_kernel")) return e;
+  }
+  if (want_p || sim_map || kl) {
+    g.stats = stats;
+    g.p_out = want_p ? w.p : nullptr;
+    g.sim_out = sim_map;
+    g.logbin = kl ? w.logbin : nullptr;
+    g.lnz = w.lnz;
+    g.kl_part = w.kl_part;
+    if (int e = launch_gemm<MODE_PROBS>(ta, tb, g, st)) return e;
+  }
+  *key_tiles = g.n_tiles;   // callers need it to reduce kl_part
+  return 0;
+}
+
+int prepare_target(const Workspace& w, const float* dis_label, int B, int H, int Wd, cudaStream_t st) {
+  const int N = (H / 8) * (Wd / 8);
+  nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, w.bins, B, H, Wd);
+  if (int e = launch_status("nearest_bins_kernel")) return e;
+  gt_norm_kernel<<<B * N, 256, 0, st>>>(w.bins, w.logbin, w.lnz, N);
+  return launch_status("gt_norm_kernel");
+}
+
+}  // namespace
+}  // namespace acan
+
+using namespace acan;
+
+extern "C" size_t acan_attn_workspace_bytes(int B, int N, int dk, int dv) {
+  if (B <= 0 || N <= 0 || dk <= 0 || dv < 0) return 0;
+  return carve(nullptr, B, N, dk, dv).bytes;
+}
+
+static int attn_forward_impl(const float* feat, const float* value, float* ctx, float* sim_map, float* row_stats,
+                             const float* dis_label, int H, int Wd, float* loss_out,
+                             void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(feat && row_stats && workspace, "acan_attn_fwd: null pointer");
+  ACAN_CHECK_ARG((value == nullptr) == (ctx == nullptr), "acan_attn_fwd: value and ctx must be given together");
+  if (int e = check_attn_shape("acan_attn_fwd", B, N, dk, value ? dv : 0)) return e;
+  ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N), "acan_attn_fwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "acan_attn_fwd: workspace must be 1024-byte aligned");
+  const Workspace w = carve(workspace, B, N, dk, dv);
+  if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_fwd: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+  if (int e = acan_device_check()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* stats = reinterpret_cast<float2*>(row_stats);
+
+  pack_feat_kernel<<<dim3((N + 63) / 64, dk / 64, B), 256, 0, st>>>(feat, w.fh, dk, N);
+  if (int e = launch_status("pack_feat_kernel")) return e;
+  if (value) {
+    const int64_t n8 = static_cast<int64_t>(B) * dv * N / 8;
+    int64_t blocks = (n8 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    pack_value_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(value), reinterpret_cast<uint4*>(w.vh), n8);
+    if (int e = launch_status("pack_value_kernel")) return e;
+  }
+  if (dis_label)
+    if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
+
+  int nt = 0;
+  if (int e = run_affinity(w, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
+  if (dis_label) {
+    ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
+    if (int e = launch_status("ordered_sum_kernel")) return e;
+  }
+  if (value) {
+    // pass 3: O^T[dv, Nq] = V[dv, Nk] * P[Nq, Nk]^T
+    const int m_tiles = dv / BM;
+    const int bn = choose_bn(N, B * m_tiles);
+    CUtensorMap ta, tb;
+    if (int e = make_tmap(&ta, w.vh, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, BM)) return e;
+    if (int e = make_tmap(&tb, w.p, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, bn)) return e;
+    GemmArgs g;
+    std::memset(&g, 0, sizeof(g));
+    g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
+    g.m_rows = dv; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn); g.c = 0.f;
+    g.o_out = ctx;
+    if (int e = launch_gemm<MODE_PV>(ta, tb, g, st)) return e;
+  }
+  return 0;
+}
+
+extern "C" int acan_attn_fwd(const float* feat, const float* value, float* ctx, float* sim_map, float* row_stats,
+                             void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, void* stream) {
+  return attn_forward_impl(feat, value, ctx, sim_map, row_stats, nullptr, 0, 0, nullptr, workspace, workspace_bytes, B, N, dk, dv, scale, stream);
+}
+
+extern "C" int acan_attn_fwd_loss(const float* feat, const float* value, float* ctx, float* sim_map, float* row_stats,
+                                  const float* dis_label, int H, int W, float* loss_out,
+                                  void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(dis_label && loss_out, "acan_attn_fwd_loss: null label / loss pointer");
+  return attn_forward_impl(feat, value, ctx, sim_map, row_stats, dis_label, H, W, loss_out, workspace, workspace_bytes, B, N, dk, dv, scale, stream);
+}
+
+extern "C" int acan_attn_rows(const void* workspace, const int* row_idx_dev, int n_rows, float* rows_out,
+                              int B, int N, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(workspace && row_idx_dev && rows_out && n_rows > 0, "acan_attn_rows: bad argument");
+  if (int e = check_attn_shape("acan_attn_rows", B, N, dk, dv)) return e;
+  const Workspace w = carve(const_cast<void*>(workspace), B, N, dk, dv);
+  sim_rows_kernel<<<dim3(n_rows, B), 256, dk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(w.fh, w.stats, row_idx_dev, rows_out, n_rows, N, dk,
+                                                                                                  scale * kLog2e);
+  return launch_status("sim_rows_kernel");
+}
+
+extern "C" int acan_attention_loss_fused(void* workspace, const float* dis_label, float* loss_out,
+                                         int B, int H, int W, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(workspace && dis_label && loss_out && H >= 8 && W >= 8, "acan_attention_loss_fused: bad argument");
+  const int N = (H / 8) * (W / 8);
+  if (int e = check_attn_shape("acan_attention_loss_fused", B, N, dk, dv)) return e;
+  const Workspace w = carve(workspace, B, N, dk, dv);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = prepare_target(w, dis_label, B, H, W, st)) return e;
+  int nt = 0;
+  if (int e = run_affinity(w, w.stats, false, nullptr, true, B, N, dk, scale, st, false, &nt)) return e;
+  ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
+  return launch_status("ordered_sum_kernel");
+}

@@ -1,0 +1,275 @@
+// head.cu -- ordinal / cross-entropy depth-bin head as single-pass HBM-streaming kernels.
+//
+// Replaces BaseClassificationModel_.decode_ord / soft|hard_ordinal_regression /
+// soft|hard_cross_entropy / inference (reference model.py:40-99) and continuous2discrete
+// (model.py:19-23).  The reference runs ~5 ATen passes for decode_ord (incl. a full-size exp(y)
+// temporary) and ~10 more for the inference; here every variant reads its input exactly once:
+//   prob   -> depth : (K+1)*HW*4  bytes / image   (324*HW at K = 80)
+//   logits -> depth : (2K+1)*HW*4 bytes / image   (644*HW), decode_ord fused, prob never stored
+//   logits -> prob  : 3K*HW*4     bytes / image   (960*HW)
+// Layout [B, C, HW]: a thread owns 4 consecutive pixels (one 16 B load per channel), a warp a
+// 512 B contiguous run per channel, and walks the C channels with the loads unrolled 8 deep so
+// ~8 x 16 B per thread are in flight.  Grid = a multiple of the 148 SMs, grid-stride over quads.
+//
+// Bit-exactness of the hard indices: p > 0.5 is evaluated literally as e1/(e0+e1) > 0.5f with
+// full-precision expf and IEEE division (no fast-math), arg-max keeps the first maximum and treats
+// NaN as the maximum, as torch.argmax does.
+#include "common.cuh"
+#include <cmath>
+
+namespace acan {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBlocksPerSM = 8;
+
+struct BinScale {      // d(k) = exp(k / (K-1) * c1 + c0), evaluated in fp32 like the reference's tensor expression
+  float inv_km1_den;   // K - 1 as float (division, not multiplication by a reciprocal, to round as torch does)
+  float c1;            // (float) log(d_max / d_min)
+  float c0;            // (float) log(d_min)
+};
+
+__device__ __forceinline__ float bin_to_depth(float k, const BinScale& s) {
+  return expf(k / s.inv_km1_den * s.c1 + s.c0);
+}
+
+__device__ __forceinline__ float ord_prob(float y0, float y1) {
+  const float e0 = expf(y0), e1 = expf(y1);
+  return e1 / (e0 + e1);
+}
+
+// ---------------------------------------------------------------- decode_ord fwd / bwd (vector path)
+__global__ void __launch_bounds__(kThreads) decode_ord_fwd_kernel(const float4* __restrict__ y, float4* __restrict__ p,
+                                                                   int K, int64_t hw4, int64_t total) {
+  // total = B*K*hw4 quads; quad q -> (bk = q / hw4, x = q % hw4); logits rows 2*bk and 2*bk+1
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t bk = q / hw4, x = q - bk * hw4;
+    const float4 a = ldg_stream(y + (2 * bk) * hw4 + x);
+    const float4 b = ldg_stream(y + (2 * bk + 1) * hw4 + x);
+    float4 r;
+    r.x = ord_prob(a.x, b.x); r.y = ord_prob(a.y, b.y); r.z = ord_prob(a.z, b.z); r.w = ord_prob(a.w, b.w);
+    p[q] = r;   // prob is re-read by the loss / inference right after: leave it cacheable
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) decode_ord_fwd_scalar(const float* __restrict__ y, float* __restrict__ p,
+                                                                   int64_t hw, int64_t total) {
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t bk = q / hw, x = q - bk * hw;
+    p[q] = ord_prob(y[(2 * bk) * hw + x], y[(2 * bk + 1) * hw + x]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) decode_ord_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g,
+                                                                   float* __restrict__ gy, int64_t hw, int64_t total) {
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t bk = q / hw, x = q - bk * hw;
+    const float pv = p[q];
+    const float d = g[q] * pv * (1.0f - pv);
+    gy[(2 * bk) * hw + x] = -d;
+    gy[(2 * bk + 1) * hw + x] = d;
+  }
+}
+
+// ---------------------------------------------------------------- inference
+// per-pixel accumulator for each head kind; feed() is called once per bin in increasing k.
+template <int KIND> struct Acc;
+
+template <> struct Acc<ACAN_HEAD_OR_SOFT> {
+  float s = 0.f;
+  __device__ __forceinline__ void feed(float p, int) { s += p; }
+  __device__ __forceinline__ float finish(const BinScale& bs, int& idx) const {
+    const float i = floorf(s), f = s - i;
+    const float d0 = bin_to_depth(i, bs), d1 = bin_to_depth(i + 1.f, bs), d2 = bin_to_depth(i + 2.f, bs);
+    idx = (int)i;
+    return (d0 + d1) / 2.f * (1.f - f) + (d1 + d2) / 2.f * f;
+  }
+};
+template <> struct Acc<ACAN_HEAD_OR_HARD> {
+  int n = 0;
+  __device__ __forceinline__ void feed(float p, int) { n += (p > 0.5f) ? 1 : 0; }
+  __device__ __forceinline__ float finish(const BinScale& bs, int& idx) const {
+    idx = n;
+    return (bin_to_depth((float)n, bs) + bin_to_depth((float)n + 1.f, bs)) / 2.f;
+  }
+};
+template <> struct Acc<ACAN_HEAD_CE_HARD> {
+  float best = 0.f; int arg = -1;
+  __device__ __forceinline__ void feed(float v, int k) {
+    // first maximum wins; NaN is the maximum and sticks (torch.argmax semantics)
+    if (arg < 0 || v > best || (v != v && best == best)) { best = v; arg = k; }
+  }
+  __device__ __forceinline__ float finish(const BinScale& bs, int& idx) const {
+    idx = arg;
+    return bin_to_depth((float)arg, bs);
+  }
+};
+template <> struct Acc<ACAN_HEAD_CE_SOFT> {   // online softmax expectation of the log-depth bin centres
+  float m = -INFINITY, z = 0.f, a = 0.f; int arg = 0;
+  float wk = 0.f;
+  __device__ __forceinline__ void feed_w(float v, int k, float w) {
+    if (v > m) { const float c = expf(m - v); z *= c; a *= c; m = v; arg = k; }
+    const float e = expf(v - m);
+    z += e; a += e * w;
+  }
+  __device__ __forceinline__ float finish(const BinScale&, int& idx) const {
+    idx = arg;
+    return expf(a / z);
+  }
+};
+
+template <int KIND, bool FROM_LOGITS>
+__global__ void __launch_bounds__(kThreads) head_kernel(const float4* __restrict__ in, float4* __restrict__ depth,
+                                                        int4* __restrict__ index, int K, int64_t hw4, int64_t total, BinScale bs) {
+  constexpr int U = 8;
+  const int C = FROM_LOGITS ? 2 * K : K;
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t b = q / hw4, x = q - b * hw4;
+    const float4* src = in + b * (int64_t)C * hw4 + x;
+    Acc<KIND> acc[4];
+    for (int c0 = 0; c0 < C; c0 += U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c0 + u < C) v[u] = ldg_stream(src + (int64_t)(c0 + u) * hw4);
+      if constexpr (FROM_LOGITS) {
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+          if (c0 + u < C) {
+            const int k = (c0 + u) >> 1;
+            acc[0].feed(ord_prob(v[u].x, v[u + 1].x), k);
+            acc[1].feed(ord_prob(v[u].y, v[u + 1].y), k);
+            acc[2].feed(ord_prob(v[u].z, v[u + 1].z), k);
+            acc[3].feed(ord_prob(v[u].w, v[u + 1].w), k);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (c0 + u < C) {
+            const int k = c0 + u;
+            if constexpr (KIND == ACAN_HEAD_CE_SOFT) {
+              // weight_k = k * log(dmax/dmin) / (K-1) + log(dmin)   (model.py:54-55, fp32 tensor expression)
+              const float w = (float)k * bs.c1 / bs.inv_km1_den + bs.c0;
+              acc[0].feed_w(v[u].x, k, w); acc[1].feed_w(v[u].y, k, w);
+              acc[2].feed_w(v[u].z, k, w); acc[3].feed_w(v[u].w, k, w);
+            } else {
+              acc[0].feed(v[u].x, k); acc[1].feed(v[u].y, k); acc[2].feed(v[u].z, k); acc[3].feed(v[u].w, k);
+            }
+          }
+        }
+      }
+    }
+    float4 d; int4 i;
+    d.x = acc[0].finish(bs, i.x); d.y = acc[1].finish(bs, i.y); d.z = acc[2].finish(bs, i.z); d.w = acc[3].finish(bs, i.w);
+    depth[q] = d;
+    if (index != nullptr) index[q] = i;
+  }
+}
+
+// scalar twin for HW % 4 != 0 (never the case for the stride-8 network, kept for the ABI's generality)
+template <int KIND, bool FROM_LOGITS>
+__global__ void __launch_bounds__(kThreads) head_kernel_scalar(const float* __restrict__ in, float* __restrict__ depth,
+                                                               int* __restrict__ index, int K, int64_t hw, int64_t total, BinScale bs) {
+  const int C = FROM_LOGITS ? 2 * K : K;
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t b = q / hw, x = q - b * hw;
+    const float* src = in + b * (int64_t)C * hw + x;
+    Acc<KIND> acc;
+    for (int k = 0; k < K; ++k) {
+      if constexpr (FROM_LOGITS) {
+        acc.feed(ord_prob(src[(int64_t)(2 * k) * hw], src[(int64_t)(2 * k + 1) * hw]), k);
+      } else if constexpr (KIND == ACAN_HEAD_CE_SOFT) {
+        acc.feed_w(src[(int64_t)k * hw], k, (float)k * bs.c1 / bs.inv_km1_den + bs.c0);
+      } else {
+        acc.feed(src[(int64_t)k * hw], k);
+      }
+    }
+    int i;
+    depth[q] = acc.finish(bs, i);
+    if (index != nullptr) index[q] = i;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) c2d_kernel(const float* __restrict__ d, float* __restrict__ k, int64_t n,
+                                                        float dmin, float dmax, float inv_log_range, float km1) {
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < n; q += (int64_t)gridDim.x * kThreads) {
+    const float v = d[q];
+    // torch: round(log(depth / d_min) / np.log(d_max/d_min) * (n_c - 1)); rintf = round-half-even like torch.round
+    const float r = rintf(logf(v / dmin) / inv_log_range * km1);
+    k[q] = (v > dmin && v < dmax) ? r : 0.f;
+  }
+}
+
+inline int grid_for(int64_t work_items) {
+  const int64_t want = (work_items + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)kNumSMs * kBlocksPerSM;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <int KIND, bool FL>
+int launch_head(const float* in, float* depth, int32_t* index, int B, int K, int64_t HW, BinScale bs, cudaStream_t st) {
+  if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(depth) % 16 == 0) &&
+      (index == nullptr || reinterpret_cast<uintptr_t>(index) % 16 == 0)) {
+    const int64_t hw4 = HW / 4, total = (int64_t)B * hw4;
+    head_kernel<KIND, FL><<<grid_for(total), kThreads, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(depth),
+                                                                reinterpret_cast<int4*>(index), K, hw4, total, bs);
+  } else {
+    const int64_t total = (int64_t)B * HW;
+    head_kernel_scalar<KIND, FL><<<grid_for(total), kThreads, 0, st>>>(in, depth, index, K, HW, total, bs);
+  }
+  return launch_status("acan_head_fwd");
+}
+
+}  // namespace
+}  // namespace acan
+
+using namespace acan;
+
+extern "C" int acan_decode_ord_fwd(const float* logits, float* prob, int B, int K, int64_t HW, void* stream) {
+  ACAN_CHECK_ARG(logits && prob, "acan_decode_ord_fwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 0 && HW > 0, "acan_decode_ord_fwd: B=%d K=%d HW=%lld must be positive", B, K, (long long)HW);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0 && reinterpret_cast<uintptr_t>(prob) % 16 == 0) {
+    const int64_t hw4 = HW / 4, total = (int64_t)B * K * hw4;
+    decode_ord_fwd_kernel<<<grid_for(total), kThreads, 0, st>>>(reinterpret_cast<const float4*>(logits), reinterpret_cast<float4*>(prob), K, hw4, total);
+  } else {
+    const int64_t total = (int64_t)B * K * HW;
+    decode_ord_fwd_scalar<<<grid_for(total), kThreads, 0, st>>>(logits, prob, HW, total);
+  }
+  return launch_status("acan_decode_ord_fwd");
+}
+
+extern "C" int acan_decode_ord_bwd(const float* prob, const float* grad_prob, float* grad_logits, int B, int K, int64_t HW, void* stream) {
+  ACAN_CHECK_ARG(prob && grad_prob && grad_logits, "acan_decode_ord_bwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 0 && HW > 0, "acan_decode_ord_bwd: sizes must be positive");
+  const int64_t total = (int64_t)B * K * HW;
+  decode_ord_bwd_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(prob, grad_prob, grad_logits, HW, total);
+  return launch_status("acan_decode_ord_bwd");
+}
+
+extern "C" int acan_head_fwd(const float* in, float* depth, int32_t* index, int B, int K, int64_t HW,
+                             double d_min, double d_max, int kind, int from_logits, void* stream) {
+  ACAN_CHECK_ARG(in && depth, "acan_head_fwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 1 && HW > 0, "acan_head_fwd: B=%d K=%d HW=%lld invalid", B, K, (long long)HW);
+  ACAN_CHECK_ARG(d_min > 0 && d_max > d_min, "acan_head_fwd: need 0 < d_min < d_max");
+  ACAN_CHECK_ARG(kind >= 0 && kind <= 3, "acan_head_fwd: kind %d unknown", kind);
+  ACAN_CHECK_ARG(!(from_logits && kind >= ACAN_HEAD_CE_SOFT), "acan_head_fwd: from_logits applies to the OR kinds only");
+  BinScale bs{(float)(K - 1), (float)std::log(d_max / d_min), (float)std::log(d_min)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (kind * 2 + (from_logits ? 1 : 0)) {
+    case ACAN_HEAD_OR_SOFT * 2 + 0: return launch_head<ACAN_HEAD_OR_SOFT, false>(in, depth, index, B, K, HW, bs, st);
+    case ACAN_HEAD_OR_SOFT * 2 + 1: return launch_head<ACAN_HEAD_OR_SOFT, true>(in, depth, index, B, K, HW, bs, st);
+    case ACAN_HEAD_OR_HARD * 2 + 0: return launch_head<ACAN_HEAD_OR_HARD, false>(in, depth, index, B, K, HW, bs, st);
+    case ACAN_HEAD_OR_HARD * 2 + 1: return launch_head<ACAN_HEAD_OR_HARD, true>(in, depth, index, B, K, HW, bs, st);
+    case ACAN_HEAD_CE_SOFT * 2 + 0: return launch_head<ACAN_HEAD_CE_SOFT, false>(in, depth, index, B, K, HW, bs, st);
+    default:                        return launch_head<ACAN_HEAD_CE_HARD, false>(in, depth, index, B, K, HW, bs, st);
+  }
+}
+
+extern "C" int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream) {
+  ACAN_CHECK_ARG(depth && bins && n > 0 && K > 1 && d_min > 0 && d_max > d_min, "acan_continuous2discrete: bad argument");
+  c2d_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(depth, bins, n, (float)d_min, (float)d_max,
+                                                                              (float)std::log(d_max / d_min), (float)(K - 1));
+  return launch_status("acan_continuous2discrete");
+}

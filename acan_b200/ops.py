@@ -1,0 +1,187 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw device pointers and the
+current CUDA stream to ``libacan_b200.so``.  No autograd here (see ``functions.py``), no fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+HEAD_KINDS = {("OR", "soft"): 0, ("OR", "hard"): 1, ("CE", "soft"): 2, ("CE", "hard"): 3}
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.AcanLibraryError(f"{name} must be a CUDA tensor: acan_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------ head
+
+def decode_ord(logits: torch.Tensor) -> torch.Tensor:
+    """[B,2K,H,W] -> [B,K,H,W]   (model.py:40-45)"""
+    y = _cuda_f32(logits, "logits")
+    b, c2, h, w = y.shape
+    out = torch.empty((b, c2 // 2, h, w), device=y.device, dtype=torch.float32)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().acan_decode_ord_fwd(y.data_ptr(), out.data_ptr(), b, c2 // 2, h * w, _lib.current_stream()), "acan_decode_ord_fwd")
+    return out
+
+
+def decode_ord_backward(prob: torch.Tensor, grad_prob: torch.Tensor) -> torch.Tensor:
+    p = _cuda_f32(prob, "prob")
+    g = _cuda_f32(grad_prob, "grad_prob")
+    b, k, h, w = p.shape
+    out = torch.empty((b, 2 * k, h, w), device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.load().acan_decode_ord_bwd(p.data_ptr(), g.data_ptr(), out.data_ptr(), b, k, h * w, _lib.current_stream()), "acan_decode_ord_bwd")
+    return out
+
+
+def head_inference(x: torch.Tensor, classifier: str, mode: str, d_min: float, d_max: float, n_c: int,
+                   from_logits: bool = False, want_index: bool = False):
+    """depth [B,1,H,W] (and optionally the int32 bin index) from probabilities / scores / pair logits (model.py:47-99)."""
+    kind = HEAD_KINDS[("OR" if classifier == "OR" else "CE", "soft" if mode == "soft" else "hard")]
+    t = _cuda_f32(x, "head input")
+    b, c, h, w = t.shape
+    want_c = 2 * n_c if (from_logits and classifier == "OR") else n_c
+    if c != want_c:
+        raise _lib.AcanLibraryError(f"head input has {c} channels, expected {want_c}")
+    depth = torch.empty((b, 1, h, w), device=t.device, dtype=torch.float32)
+    index = torch.empty((b, 1, h, w), device=t.device, dtype=torch.int32) if want_index else None
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().acan_head_fwd(t.data_ptr(), depth.data_ptr(), _lib.ptr(index), b, n_c, h * w, float(d_min), float(d_max),
+                                             kind, int(bool(from_logits)), _lib.current_stream()), "acan_head_fwd")
+    return (depth, index) if want_index else depth
+
+
+def continuous2discrete(depth: torch.Tensor, d_min: float, d_max: float, n_c: int) -> torch.Tensor:
+    d = _cuda_f32(depth, "depth")
+    out = torch.empty_like(d)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.load().acan_continuous2discrete(d.data_ptr(), out.data_ptr(), d.numel(), float(d_min), float(d_max), n_c, _lib.current_stream()),
+                   "acan_continuous2discrete")
+    return out
+
+
+# ------------------------------------------------------------------------------------ pooling branch
+
+def pool_branch(x: torch.Tensor, w1, b1, w2, b2, keep_mask: Optional[torch.Tensor] = None):
+    """(mean [B,C], hidden [B,H1], g [B,H2])   (sadecoder.py:97-106)"""
+    xx = _cuda_f32(x, "x")
+    b, c = xx.shape[:2]
+    n = xx.numel() // (b * c)
+    w1, b1, w2, b2 = (_cuda_f32(t, "pool weight") for t in (w1, b1, w2, b2))
+    h1, h2 = w1.shape[0], w2.shape[0]
+    mean = torch.empty((b, c), device=xx.device, dtype=torch.float32)
+    hid = torch.empty((b, h1), device=xx.device, dtype=torch.float32)
+    g = torch.empty((b, h2), device=xx.device, dtype=torch.float32)
+    km = _cuda_f32(keep_mask, "keep_mask") if keep_mask is not None else None
+    with torch.cuda.device(xx.device):
+        _lib.check(_lib.load().acan_pool_branch_fwd(xx.data_ptr(), _lib.ptr(km), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                                    mean.data_ptr(), hid.data_ptr(), g.data_ptr(), b, c, n, h1, h2, _lib.current_stream()),
+                   "acan_pool_branch_fwd")
+    return mean, hid, g
+
+
+# ------------------------------------------------------------------------------------ attention
+
+class AttnWorkspace:
+    """Scratch for the attention passes; keeps the fp16 operand pack + row statistics of the last forward so
+    selected sim_map rows / the fused loss can be produced later without re-packing."""
+
+    def __init__(self, b: int, n: int, dk: int, dv: int, device):
+        self.shape = (b, n, dk, dv)
+        self.bytes = int(_lib.load().acan_attn_workspace_bytes(b, n, dk, dv))
+        # torch's caching allocator returns >= 512 B aligned blocks; over-allocate and align to 1024 ourselves
+        self._buf = torch.empty(self.bytes + 1024, device=device, dtype=torch.uint8)
+        base = self._buf.data_ptr()
+        self.ptr = (base + 1023) // 1024 * 1024
+        self.scale = None
+
+
+def attention_forward(feat: torch.Tensor, value: Optional[torch.Tensor], want_sim_map: bool = False,
+                      dis_label: Optional[torch.Tensor] = None, ws: Optional[AttnWorkspace] = None):
+    """Returns dict(ctx [B,dv,h,w] | None, sim_map [B,N,N] | None, row_stats [B,N,2], loss 0-dim | None, ws)."""
+    f = _cuda_f32(feat, "feat")
+    b, dk, h, w = f.shape
+    n = h * w
+    v = _cuda_f32(value, "value") if value is not None else None
+    dv = v.shape[1] if v is not None else 0
+    if ws is None or ws.shape != (b, n, dk, dv) or ws._buf.device != f.device:
+        ws = AttnWorkspace(b, n, dk, dv, f.device)
+    scale = float(dk) ** -0.5
+    ws.scale = scale
+    ctx = torch.empty((b, dv, h, w), device=f.device, dtype=torch.float32) if v is not None else None
+    sim = torch.empty((b, n, n), device=f.device, dtype=torch.float32) if want_sim_map else None
+    stats = torch.empty((b, n, 2), device=f.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(f.device):
+        st = _lib.current_stream()
+        if dis_label is None:
+            loss = None
+            _lib.check(lib.acan_attn_fwd(f.data_ptr(), _lib.ptr(v), _lib.ptr(ctx), _lib.ptr(sim), stats.data_ptr(), ws.ptr, ws.bytes,
+                                         b, n, dk, dv, scale, st), "acan_attn_fwd")
+        else:
+            lab = _cuda_f32(dis_label, "dis_label")
+            hh, ww = lab.shape[-2:]
+            loss = torch.empty((), device=f.device, dtype=torch.float32)
+            _lib.check(lib.acan_attn_fwd_loss(f.data_ptr(), _lib.ptr(v), _lib.ptr(ctx), _lib.ptr(sim), stats.data_ptr(), lab.data_ptr(), hh, ww,
+                                              loss.data_ptr(), ws.ptr, ws.bytes, b, n, dk, dv, scale, st), "acan_attn_fwd_loss")
+    return {"ctx": ctx, "sim_map": sim, "row_stats": stats, "loss": loss, "ws": ws}
+
+
+def attention_rows(ws: AttnWorkspace, rows: torch.Tensor) -> torch.Tensor:
+    """sim_map[:, rows, :] -> [B, len(rows), N] from the operand pack of the last forward (vis_utils.py:107-121)."""
+    b, n, dk, dv = ws.shape
+    idx = rows.to(device=ws._buf.device, dtype=torch.int32).contiguous()
+    out = torch.empty((b, idx.numel(), n), device=ws._buf.device, dtype=torch.float32)
+    with torch.cuda.device(ws._buf.device):
+        _lib.check(_lib.load().acan_attn_rows(ws.ptr, idx.data_ptr(), idx.numel(), out.data_ptr(), b, n, dk, dv, ws.scale, _lib.current_stream()),
+                   "acan_attn_rows")
+    return out
+
+
+def attention_loss_fused(ws: AttnWorkspace, dis_label: torch.Tensor) -> torch.Tensor:
+    b, n, dk, dv = ws.shape
+    lab = _cuda_f32(dis_label, "dis_label")
+    hh, ww = lab.shape[-2:]
+    loss = torch.empty((), device=lab.device, dtype=torch.float32)
+    with torch.cuda.device(lab.device):
+        _lib.check(_lib.load().acan_attention_loss_fused(ws.ptr, lab.data_ptr(), loss.data_ptr(), b, hh, ww, dk, dv, ws.scale, _lib.current_stream()),
+                   "acan_attention_loss_fused")
+    return loss
+
+
+# ------------------------------------------------------------------------------------ attention loss (materialised)
+
+def attention_loss(sim_map: torch.Tensor, dis_label: torch.Tensor, want_grad: bool = False, grad_scale: float = 1.0):
+    q = _cuda_f32(sim_map, "sim_map")
+    lab = _cuda_f32(dis_label, "dis_label")
+    b, n, _ = q.shape
+    hh, ww = lab.shape[-2:]
+    if (hh // 8) * (ww // 8) != n:
+        raise _lib.AcanLibraryError(f"label {tuple(lab.shape)} does not match sim_map {tuple(q.shape)}")
+    loss = torch.empty((), device=q.device, dtype=torch.float32)
+    ws = torch.empty(2 * b * n, device=q.device, dtype=torch.float32)
+    grad = torch.empty_like(q) if want_grad else None
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().acan_attention_loss(q.data_ptr(), lab.data_ptr(), loss.data_ptr(), ws.data_ptr(), _lib.ptr(grad), float(grad_scale),
+                                                   b, hh, ww, _lib.current_stream()), "acan_attention_loss")
+    return (loss, grad) if want_grad else loss
+
+
+def gt_sim_map(dis_label: torch.Tensor) -> torch.Tensor:
+    lab = _cuda_f32(dis_label, "dis_label")
+    b = lab.shape[0]
+    hh, ww = lab.shape[-2:]
+    n = (hh // 8) * (ww // 8)
+    gt = torch.empty((b, n, n), device=lab.device, dtype=torch.float32)
+    ws = torch.empty(b * n, device=lab.device, dtype=torch.float32)
+    with torch.cuda.device(lab.device):
+        _lib.check(_lib.load().acan_gt_sim_map(lab.data_ptr(), gt.data_ptr(), ws.data_ptr(), b, hh, ww, _lib.current_stream()), "acan_gt_sim_map")
+    return gt

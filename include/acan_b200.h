@@ -1,0 +1,141 @@
+/* acan_b200.h -- C ABI of libacan_b200.so: sm_100a kernels for the ACAN hot path
+ * (context aggregation module, attention loss, ordinal / cross-entropy depth head).
+ *
+ * The reference (miraiaroha/ACAN) has no FFI layer: its hot path is nn.Module code over ATen.
+ * Each entry point below names the reference function it replaces (path:line under
+ * /root/reference/code/models).  The Python drop-in modules in acan_b200/ bind these with
+ * ctypes; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are dense,
+ *     row-major ("NCHW" with H*W flattened to N / HW); floats are IEEE fp32 unless stated;
+ *   - return value: 0 on success, otherwise a cudaError_t value or one of ACAN_ERR_*;
+ *     acan_last_error() returns a static/thread-local message for the last non-zero return;
+ *   - nothing allocates, frees or synchronises: outputs and workspaces are caller-owned,
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*), inputs must stay alive
+ *     until the stream reaches the end of the call;
+ *   - sizes are validated before any launch; a failing call launches nothing.
+ */
+#ifndef ACAN_B200_H
+#define ACAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACAN_ABI_VERSION 1
+
+#define ACAN_ERR_BAD_ARG     10001   /* null pointer, non-positive size, unsupported shape */
+#define ACAN_ERR_WORKSPACE   10002   /* workspace smaller than *_workspace_bytes() */
+#define ACAN_ERR_DRIVER      10003   /* cuTensorMapEncodeTiled unavailable / failed */
+#define ACAN_ERR_ARCH        10004   /* device is not compute capability 10.x */
+
+/* head `kind` (model.py:47-78) */
+#define ACAN_HEAD_OR_SOFT 0   /* soft_ordinal_regression  model.py:69-78 */
+#define ACAN_HEAD_OR_HARD 1   /* hard_ordinal_regression  model.py:61-67 */
+#define ACAN_HEAD_CE_SOFT 2   /* soft_cross_entropy       model.py:52-59 */
+#define ACAN_HEAD_CE_HARD 3   /* hard_cross_entropy       model.py:47-50 */
+
+int         acan_abi_version(void);
+const char* acan_last_error(void);
+/* 0 if the current device can run the library (sm_100), else ACAN_ERR_ARCH / a cudaError_t. */
+int         acan_device_check(void);
+
+/* ---------------------------------------------------------------- depth head ---------- */
+
+/* BaseClassificationModel_.decode_ord (model.py:40-45):
+ *   prob[b,k,p] = exp(y[b,2k+1,p]) / (exp(y[b,2k,p]) + exp(y[b,2k+1,p])),  unstabilised like the reference.
+ *   logits [B,2K,HW] -> prob [B,K,HW]. */
+int acan_decode_ord_fwd(const float* logits, float* prob, int B, int K, int64_t HW, void* stream);
+
+/* autograd of decode_ord: grad_logits[b,2k+1,p] = g*p*(1-p), grad_logits[b,2k,p] = -g*p*(1-p). */
+int acan_decode_ord_bwd(const float* prob, const float* grad_prob, float* grad_logits,
+                        int B, int K, int64_t HW, void* stream);
+
+/* BaseClassificationModel_.inference and the four functions it dispatches to (model.py:47-99).
+ *   in        OR kinds: prob [B,K,HW] (from_logits = 0) or pair logits [B,2K,HW] (from_logits = 1,
+ *             decode_ord fused, the [B,K,HW] tensor never exists);  CE kinds: scores [B,K,HW].
+ *   depth     [B,1,HW] metres.
+ *   index     optional (may be NULL) int32 [B,1,HW]: the hard bin index (count of p > 0.5 for OR_HARD,
+ *             first arg-max for CE_HARD, floor(sum p) for OR_SOFT, arg-max for CE_SOFT). */
+int acan_head_fwd(const float* in, float* depth, int32_t* index, int B, int K, int64_t HW,
+                  double d_min, double d_max, int kind, int from_logits, void* stream);
+
+/* continuous2discrete (model.py:19-23, torch-0.4 semantics): metres -> bin index as float, 0 outside (d_min,d_max). */
+int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream);
+
+/* ---------------------------------------------------------------- pooling branch ------ */
+
+/* SADecoder.image_context (sadecoder.py:97-106): global mean over the N positions, optional
+ * Dropout2d keep-mask, Linear(C->H1)+ReLU, Linear(H1->H2)+ReLU.  The trailing bilinear "upsample"
+ * of the 1x1 map is a broadcast and is never materialised.
+ *   x [B,C,N] fp32;  keep_mask NULL or [B,C] in {0,1} (kept channels are scaled by 2);
+ *   w1 [H1,C], b1 [H1], w2 [H2,H1], b2 [H2];
+ *   mean_out [B,C] (post-mask, saved for backward), hidden_out [B,H1] (post-ReLU), g_out [B,H2]. */
+int acan_pool_branch_fwd(const float* x, const float* keep_mask,
+                         const float* w1, const float* b1, const float* w2, const float* b2,
+                         float* mean_out, float* hidden_out, float* g_out,
+                         int B, int C, int N, int H1, int H2, void* stream);
+
+/* ---------------------------------------------------------------- attention ----------- */
+
+/* Bytes of scratch the attention entry points need for (B, N, dk, dv).  The workspace must be 1024-byte
+ * aligned.  After acan_attn_fwd it holds the fp16 operand pack of F and the row statistics, which
+ * acan_attn_rows and acan_attention_loss_fused reuse (pass the same B, N, dk, dv). */
+size_t acan_attn_workspace_bytes(int B, int N, int dk, int dv);
+
+/* PixelAttentionBlock_.forward_att + SelfAttentionBlock_.forward (sadecoder.py:42-49, 80-90), Q = K = F:
+ *   S = F^T F * scale;  P = softmax_rows(S);  O[b,c,i] = sum_j P[b,i,j] V[b,c,j].
+ *   feat   F [B,dk,N] fp32 (f_key output, NCHW)
+ *   value  V [B,dv,N] fp32 (f_value output, NCHW); NULL (with ctx NULL) computes the affinity only
+ *   ctx    O [B,dv,N] fp32 (NCHW, what .permute(0,2,1).contiguous().view() yields in the reference)
+ *   sim_map    NULL, or [B,N,N] fp32: the full affinity, materialised only on request
+ *   row_stats  [B,N,2] fp32: (m_i, l_i) with P_ij = exp2(S_ij*scale*log2e - m_i) / l_i  (kept for loss / backward)
+ * tcgen05 path: operands are rounded to fp16 (11-bit significand, the rounding of TF32), accumulation fp32.
+ * Requires dk % 64 == 0, dv % 128 == 0, N % 8 == 0. */
+int acan_attn_fwd(const float* feat, const float* value, float* ctx, float* sim_map, float* row_stats,
+                  void* workspace, size_t workspace_bytes,
+                  int B, int N, int dk, int dv, float scale, void* stream);
+
+/* Same, with the attention loss (losses.py:54-62) fused into the probability pass: sim_map is compared
+ * tile by tile, on chip, against the target affinity generated on the fly from dis_label [B,1,H,W]
+ * (bin indices, model.py:260,270; (H/8)*(W/8) == N).  loss_out: 1 float (device). */
+int acan_attn_fwd_loss(const float* feat, const float* value, float* ctx, float* sim_map, float* row_stats,
+                       const float* dis_label, int H, int W, float* loss_out,
+                       void* workspace, size_t workspace_bytes,
+                       int B, int N, int dk, int dv, float scale, void* stream);
+
+/* Selected rows of sim_map (vis_utils.py:107-121 reads rows N/4, N/2, 3N/4 only):
+ *   rows_out [B, n_rows, N] fp32 for row indices row_idx[0..n_rows) (int32, device).
+ * Needs the workspace left by a preceding acan_attn_fwd with the same (B, N, dk, dv). */
+int acan_attn_rows(const void* workspace, const int* row_idx, int n_rows, float* rows_out,
+                   int B, int N, int dk, int dv, float scale, void* stream);
+
+/* ---------------------------------------------------------------- attention loss ------ */
+
+/* AttentionLoss2d.forward (losses.py:54-62) on a materialised sim_map:
+ *   bins[b,n] = dis_label[b,0,8*(n / w), 8*(n % w)]   (nearest downsample, losses.py:50)
+ *   W = gt affinity (losses.py:40-46);  loss = mean_{b,i} sum_j W log(clamp(W/Q, 1e-8, 1e8)).
+ *   sim_map [B,N,N] fp32, dis_label [B,1,H,W] fp32 bin indices (model.py:260,270), h = H/8, w = W/8, N = h*w.
+ *   loss_out: 1 float (device).  ws: [2*B*N] floats of scratch (row losses, stride-8 bins).
+ *   grad_sim: NULL, or [B,N,N] receiving grad_scale * dLoss/dsim_map = -grad_scale * W/Q / (B*N) inside the
+ *             clamp window, 0 outside it (where the reference yields 0, or NaN when Q == 0 exactly). */
+int acan_attention_loss(const float* sim_map, const float* dis_label, float* loss_out, float* ws,
+                        float* grad_sim, float grad_scale, int B, int H, int W, void* stream);
+
+/* AttentionLoss2d.get_gt_sim_map (losses.py:48-52): gt [B,N,N] fp32 from dis_label [B,1,H,W]; bins_ws: [B*N] floats. */
+int acan_gt_sim_map(const float* dis_label, float* gt, float* bins_ws, int B, int H, int W, void* stream);
+
+/* Fused, streamed form on its own: the loss straight from the fp16 operand pack and row statistics an
+ * acan_attn_fwd call left in `workspace` -- sim_map is recomputed tile by tile on the tensor cores and
+ * never touches HBM.  Same value as acan_attention_loss(sim_map) up to fp16-operand rounding of S. */
+int acan_attention_loss_fused(void* workspace, const float* dis_label, float* loss_out,
+                              int B, int H, int W, int dk, int dv, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACAN_B200_H */
