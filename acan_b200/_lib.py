@@ -24,6 +24,9 @@ SIGNATURES = {
     "acan_abi_version": (c_int, []),
     "acan_last_error": (c_char_p, []),
     "acan_device_check": (c_int, []),
+    "acan_launch_count": (ctypes.c_longlong, []),
+    "acan_profile_begin": (c_int, [c_int]),
+    "acan_profile_end": (c_int, [c_void_p, c_void_p]),
     "acan_decode_ord_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "acan_decode_ord_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "acan_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_double, c_double, c_int, c_int, c_void_p]),

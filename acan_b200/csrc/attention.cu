@@ -499,6 +499,7 @@ int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map,
   g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = dk / BK;
   g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn); g.c = scale * kLog2e;
   if (need_stats) {
+    ProfScope ps(PROF_STATS, st);
     g.part = w.part;
     if (int e = launch_gemm<MODE_STATS>(ta, tb, g, st)) return e;
     combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, g.n_tiles, N, B);
@@ -511,6 +512,7 @@ int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map,
     g.logbin = kl ? w.logbin : nullptr;
     g.lnz = w.lnz;
     g.kl_part = w.kl_part;
+    ProfScope ps(PROF_PROBS, st);
     if (int e = launch_gemm<MODE_PROBS>(ta, tb, g, st)) return e;
   }
   *key_tiles = g.n_tiles;   // callers need it to reduce kl_part
@@ -549,14 +551,17 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float2* stats = reinterpret_cast<float2*>(row_stats);
 
-  pack_feat_kernel<<<dim3((N + 63) / 64, dk / 64, B), 256, 0, st>>>(feat, w.fh, dk, N);
-  if (int e = launch_status("pack_feat_kernel")) return e;
-  if (value) {
-    const int64_t n8 = static_cast<int64_t>(B) * dv * N / 8;
-    int64_t blocks = (n8 + 255) / 256;
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    pack_value_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(value), reinterpret_cast<uint4*>(w.vh), n8);
-    if (int e = launch_status("pack_value_kernel")) return e;
+  {
+    ProfScope ps(PROF_PACK, st);
+    pack_feat_kernel<<<dim3((N + 63) / 64, dk / 64, B), 256, 0, st>>>(feat, w.fh, dk, N);
+    if (int e = launch_status("pack_feat_kernel")) return e;
+    if (value) {
+      const int64_t n8 = static_cast<int64_t>(B) * dv * N / 8;
+      int64_t blocks = (n8 + 255) / 256;
+      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      pack_value_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(value), reinterpret_cast<uint4*>(w.vh), n8);
+      if (int e = launch_status("pack_value_kernel")) return e;
+    }
   }
   if (dis_label)
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
@@ -580,6 +585,7 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
     g.m_rows = dv; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn); g.c = 0.f;
     g.o_out = ctx;
+    ProfScope ps(PROF_PV, st);
     if (int e = launch_gemm<MODE_PV>(ta, tb, g, st)) return e;
   }
   return 0;

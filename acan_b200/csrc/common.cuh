@@ -22,11 +22,22 @@ int  fail(int code, const char* fmt, ...);
   do { cudaError_t e__ = (expr);                                              \
        if (e__ != cudaSuccess) return ::acan::fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__)); } while (0)
 
+void note_launch();                       // counts kernels launched by this library (acan_launch_count)
 inline int launch_status(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, "%s launch: %s", what, cudaGetErrorString(e));
+  note_launch();
   return 0;
 }
+
+// optional CUDA-event brackets around kernel groups (acan_profile_begin / acan_profile_end)
+enum ProfKind { PROF_PACK = 0, PROF_STATS = 1, PROF_PROBS = 2, PROF_PV = 3, PROF_HEAD = 4, PROF_POOL = 5, PROF_KL = 6, PROF_KINDS = 7 };
+void prof_mark(int kind, bool begin, cudaStream_t st);
+struct ProfScope {
+  int kind; cudaStream_t st;
+  ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_mark(kind, true, st); }
+  ~ProfScope() { prof_mark(kind, false, st); }
+};
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 

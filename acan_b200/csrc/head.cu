@@ -257,6 +257,7 @@ extern "C" int acan_head_fwd(const float* in, float* depth, int32_t* index, int 
   ACAN_CHECK_ARG(!(from_logits && kind >= ACAN_HEAD_CE_SOFT), "acan_head_fwd: from_logits applies to the OR kinds only");
   BinScale bs{(float)(K - 1), (float)std::log(d_max / d_min), (float)std::log(d_min)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PROF_HEAD, st);
   switch (kind * 2 + (from_logits ? 1 : 0)) {
     case ACAN_HEAD_OR_SOFT * 2 + 0: return launch_head<ACAN_HEAD_OR_SOFT, false>(in, depth, index, B, K, HW, bs, st);
     case ACAN_HEAD_OR_SOFT * 2 + 1: return launch_head<ACAN_HEAD_OR_SOFT, true>(in, depth, index, B, K, HW, bs, st);

@@ -115,6 +115,7 @@ extern "C" int acan_attention_loss(const float* sim_map, const float* dis_label,
   if (int e = check_hw("acan_attention_loss", B, H, W)) return e;
   const int N = (H / 8) * (W / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PROF_KL, st);
   float* row_loss = ws;
   float* bins = ws + (int64_t)B * N;
   nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, bins, B, H, W);

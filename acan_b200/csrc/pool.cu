@@ -83,6 +83,7 @@ extern "C" int acan_pool_branch_fwd(const float* x, const float* keep_mask, cons
   ACAN_CHECK_ARG(x && w1 && b1 && w2 && b2 && mean_out && hidden_out && g_out, "acan_pool_branch_fwd: null pointer");
   ACAN_CHECK_ARG(B > 0 && C > 0 && N > 0 && H1 > 0 && H2 > 0, "acan_pool_branch_fwd: sizes must be positive");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PROF_POOL, st);
   const int64_t rows = (int64_t)B * C;
   int64_t blocks = (rows + kWarps - 1) / kWarps;
   const int64_t cap = (int64_t)kNumSMs * 8;

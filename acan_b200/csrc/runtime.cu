@@ -18,7 +18,66 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static long long g_launches = 0;
+void note_launch() { ++g_launches; }
+
+// ---- event profiling: begin/end marks per kind, resolved at acan_profile_end
+struct ProfPair { cudaEvent_t a, b; int kind; };
+static bool g_prof_on = false;
+static ProfPair* g_pairs = nullptr;
+static int g_pairs_cap = 0, g_pairs_n = 0;
+static int g_open[PROF_KINDS];
+
+void prof_mark(int kind, bool begin, cudaStream_t st) {
+  if (!g_prof_on) return;
+  if (begin) {
+    if (g_pairs_n >= g_pairs_cap) { g_open[kind] = -1; return; }
+    ProfPair& p = g_pairs[g_pairs_n];
+    p.kind = kind;
+    cudaEventRecord(p.a, st);
+    g_open[kind] = g_pairs_n++;
+  } else if (g_open[kind] >= 0) {
+    cudaEventRecord(g_pairs[g_open[kind]].b, st);
+    g_open[kind] = -1;
+  }
+}
 }  // namespace acan
+
+extern "C" long long acan_launch_count(void) { return acan::g_launches; }
+
+extern "C" int acan_profile_begin(int max_marks) {
+  using namespace acan;
+  if (max_marks <= 0) return fail(ACAN_ERR_BAD_ARG, "acan_profile_begin: max_marks must be positive");
+  if (g_pairs_cap < max_marks) {
+    ProfPair* np = new ProfPair[max_marks];
+    for (int i = 0; i < g_pairs_cap; ++i) np[i] = g_pairs[i];
+    for (int i = g_pairs_cap; i < max_marks; ++i) { ACAN_CUDA(cudaEventCreate(&np[i].a)); ACAN_CUDA(cudaEventCreate(&np[i].b)); np[i].kind = 0; }
+    delete[] g_pairs;
+    g_pairs = np;
+    g_pairs_cap = max_marks;
+  }
+  g_pairs_n = 0;
+  for (int k = 0; k < PROF_KINDS; ++k) g_open[k] = -1;
+  g_prof_on = true;
+  return 0;
+}
+
+extern "C" int acan_profile_end(float* ms_by_kind, int* count_by_kind) {
+  using namespace acan;
+  ACAN_CHECK_ARG(ms_by_kind && count_by_kind, "acan_profile_end: null pointer");
+  g_prof_on = false;
+  for (int k = 0; k < PROF_KINDS; ++k) { ms_by_kind[k] = 0.f; count_by_kind[k] = 0; }
+  for (int i = 0; i < g_pairs_n; ++i) {
+    ACAN_CUDA(cudaEventSynchronize(g_pairs[i].b));
+    float ms = 0.f;
+    ACAN_CUDA(cudaEventElapsedTime(&ms, g_pairs[i].a, g_pairs[i].b));
+    ms_by_kind[g_pairs[i].kind] += ms;
+    count_by_kind[g_pairs[i].kind] += 1;
+  }
+  g_pairs_n = 0;
+  return 0;
+}
 
 extern "C" int acan_abi_version(void) { return ACAN_ABI_VERSION; }
 extern "C" const char* acan_last_error(void) { return acan::g_err; }

@@ -1,0 +1,139 @@
+"""torch.autograd.Function wrappers around the sm_100a kernels.
+
+Forward passes are the hand-written kernels of ``csrc/`` (through the C ABI).  Backward:
+  * decode_ord        -- CUDA kernel (``acan_decode_ord_bwd``)
+  * attention loss    -- CUDA kernel (gradient w.r.t. sim_map comes out of ``acan_attention_loss``)
+  * attention core    -- round 1: sim_map is re-materialised by the tcgen05 kernels and the three gradient
+                         GEMMs (dV, dP, dF) are cuBLAS calls through torch.matmul; the tcgen05 backward is the
+                         next row (DESIGN.md §"what comes next").  No CPU path anywhere.
+The reference has no custom Function: gradients follow what autograd derives for
+sadecoder.py:42-49,80-90 and losses.py:18-33, including Q and K sharing F (dF gets both sides of dS).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class DecodeOrd(torch.autograd.Function):
+    """BaseClassificationModel_.decode_ord (model.py:40-45)."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        prob = ops.decode_ord(logits)
+        ctx.save_for_backward(prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, grad_prob):
+        (prob,) = ctx.saved_tensors
+        return ops.decode_ord_backward(prob, grad_prob.contiguous())
+
+
+class PoolBranch(torch.autograd.Function):
+    """SADecoder.image_context without the broadcast (sadecoder.py:97-106) -> g [B,H2]."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, keep_mask):
+        mean, hid, g = ops.pool_branch(x, w1, b1, w2, b2, keep_mask)
+        ctx.save_for_backward(mean, hid, g, w1, w2, keep_mask if keep_mask is not None else torch.empty(0, device=x.device))
+        ctx.x_shape = x.shape
+        return g
+
+    @staticmethod
+    def backward(ctx, grad_g):
+        mean, hid, g, w1, w2, keep = ctx.saved_tensors
+        b, c = mean.shape
+        n = 1
+        for d in ctx.x_shape[2:]:
+            n *= d
+        dz2 = grad_g * (g > 0).to(grad_g.dtype)              # [B,H2]
+        gw2 = dz2.t() @ hid
+        gb2 = dz2.sum(0)
+        dz1 = (dz2 @ w2) * (hid > 0).to(grad_g.dtype)        # [B,H1]
+        gw1 = dz1.t() @ mean
+        gb1 = dz1.sum(0)
+        dmean = dz1 @ w1                                     # [B,C]
+        if keep.numel():
+            dmean = dmean * keep * 2.0
+        gx = (dmean / n).view(b, c, *([1] * (len(ctx.x_shape) - 2))).expand(ctx.x_shape)
+        return gx, gw1, gb1, gw2, gb2, None
+
+
+def _softmax_backward(p: torch.Tensor, dp: torch.Tensor) -> torch.Tensor:
+    return p * (dp - (dp * p).sum(-1, keepdim=True))
+
+
+class Attention(torch.autograd.Function):
+    """ctx = aggregate(softmax(F^T F / sqrt(dk)), V) and, optionally, the fused attention loss.
+
+    forward(feat [B,dk,h,w], value [B,dv,h,w], dis_label [B,1,H,W] | None, holder)
+      -> (context [B,dv,h,w], loss 0-dim (0 when no label))
+    ``holder`` is a python object that receives ``.ws`` (operand pack / statistics) for lazy sim_map access.
+    """
+
+    @staticmethod
+    def forward(ctx, feat, value, dis_label, holder):
+        out = ops.attention_forward(feat, value, want_sim_map=False, dis_label=dis_label, ws=getattr(holder, "ws", None))
+        holder.ws = out["ws"]
+        holder.row_stats = out["row_stats"]
+        holder.gen = getattr(holder, "gen", 0) + 1
+        ctx.save_for_backward(feat, value, dis_label if dis_label is not None else torch.empty(0, device=feat.device))
+        loss = out["loss"] if out["loss"] is not None else torch.zeros((), device=feat.device)
+        return out["ctx"], loss
+
+    @staticmethod
+    def backward(ctx, grad_ctx, grad_loss):
+        feat, value, dis_label = ctx.saved_tensors
+        b, dk, h, w = feat.shape
+        n = h * w
+        dv = value.shape[1]
+        sim = ops.attention_forward(feat, None, want_sim_map=True)["sim_map"]          # tcgen05 re-materialisation
+        go = grad_ctx.reshape(b, dv, n).float()
+        v = value.reshape(b, dv, n).float()
+        f = feat.reshape(b, dk, n).float()
+        g_value = torch.matmul(go, sim)                                                # dV[c,j] = sum_i dO[c,i] P[i,j]
+        dp = torch.matmul(go.transpose(1, 2), v)                                       # dP[i,j] = sum_c dO[c,i] V[c,j]
+        if dis_label.numel():
+            _, gq = ops.attention_loss(sim, dis_label, want_grad=True)                 # CUDA: dL/dQ with the clamp window
+            dp = dp + gq * grad_loss
+        ds = _softmax_backward(sim, dp)
+        g_feat = torch.matmul(f, ds + ds.transpose(1, 2)) * (dk ** -0.5)               # Q and K are both F
+        return g_feat.view_as(feat), g_value.view_as(value), None, None
+
+
+class SimMap(torch.autograd.Function):
+    """sim_map [B,N,N] materialised on request (forward_att, sadecoder.py:42-49)."""
+
+    @staticmethod
+    def forward(ctx, feat):
+        ctx.save_for_backward(feat)
+        sim = ops.attention_forward(feat, None, want_sim_map=True)["sim_map"]
+        ctx.sim = sim
+        return sim
+
+    @staticmethod
+    def backward(ctx, grad_sim):
+        (feat,) = ctx.saved_tensors
+        b, dk = feat.shape[:2]
+        f = feat.reshape(b, dk, -1).float()
+        ds = _softmax_backward(ctx.sim, grad_sim)
+        return (torch.matmul(f, ds + ds.transpose(1, 2)) * (dk ** -0.5)).view_as(feat)
+
+
+class AttentionLossMaterialised(torch.autograd.Function):
+    """AttentionLoss2d.forward on a real sim_map tensor (losses.py:54-62): one streaming kernel for loss and gradient."""
+
+    @staticmethod
+    def forward(ctx, sim_map, dis_label):
+        loss, grad = ops.attention_loss(sim_map, dis_label, want_grad=True)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None

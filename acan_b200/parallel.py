@@ -1,0 +1,106 @@
+"""Batch sharding + gradient all-reduce: the only multi-GPU machinery the path needs.
+
+One process per GPU, weights replicated, every image an independent unit: inference needs no collective;
+training averages gradients with NCCL all-reduce over NVLink, bucketed in reverse parameter order and
+launched from post-accumulate-grad hooks so the transfers overlap the rest of the backward pass.
+The reference has no distributed code on its live path; nothing here replaces reference code.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: Optional[str] = None) -> tuple:
+    """(rank, world_size, local_rank) from the torchrun environment; no-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> tuple:
+    """contiguous shard [lo, hi) of n_items for `rank`; the first n_items % world ranks get one extra item."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    lo, hi = shard_bounds(t.shape[0], rank, world)
+    return t[lo:hi]
+
+
+class GradAllReducer:
+    """Mean of the gradients over ranks, in buckets of ~bucket_mb MB, overlapped with backward.
+
+    usage:  reducer = GradAllReducer(net.parameters());  loss.backward();  reducer.finish();  optimizer.step()
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 32.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, cur_bytes, limit = [], 0, bucket_mb * (1 << 20)
+        for p in reversed(self.params):                      # gradients become ready roughly in reverse order
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= limit:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [len(b) for b in self.buckets]
+        self._work = []
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _launch(self, bi: int) -> None:
+        ps = [p for p in self.buckets[bi] if p.grad is not None]
+        if not ps:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._work.append((work, flat, ps))
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def finish(self) -> None:
+        """wait for the buckets in flight, launch any bucket whose hooks never all fired (unused parameters),
+        write the averaged gradients back."""
+        if self.world > 1:
+            for bi, left in enumerate(self._pending):
+                if left > 0:
+                    self._launch(bi)
+            for work, flat, ps in self._work:
+                work.wait()
+                flat.div_(self.world)
+                off = 0
+                for p in ps:
+                    n = p.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
+        self._work = []
+        self._pending = [len(b) for b in self.buckets]
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

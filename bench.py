@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: ACAN NYU-shape images/sec on N B200s, CAM attention TFLOP/s vs peak.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+Workload = BASELINE.json configs[1]: full ACAN forward (dilated ResNet-101 backbone + context aggregation module +
+ordinal soft inference), NYU-shaped 256x352 synthetic batch of 16 images per GPU (weak scaling, no data-path
+collective: every image is an independent unit).  One step = net(images) -> net.inference(y), the
+reference's eval call pattern (depthest_trainer.py:184-185), with the drop-in modules of acan_b200/.
+
+  value    images/s with the batch already resident in HBM (CUDA events, max over ranks).
+  e2e      the same call with HOST buffers: pinned images -> H2D, forward, inference, depth -> D2H, every step.
+  roofline the dominant hand-written kernel (aggregation pass O^T = V P^T on tcgen05), its CUDA-event time measured
+           live in this run via the library's event hooks, against MEASURED_PEAKS.json; `attention_core` and `head`
+           give the same arithmetic for the whole fused CAM core and the depth head.
+  cpu_baseline  the oracle port of the reference forward on the host cores, bounded sample (rank 0, N = 1).
+--impl reference times that CPU path alone (the reference is PyTorch-on-CPU code; the oracle is its restatement).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+H, W, BATCH = 256, 352, 16
+DMIN, DMAX, K = 0.72, 10.0, 80
+LAYERS101 = [3, 4, 23, 3]
+WORKLOAD = "configs[1]: full ACAN fwd (ResNet-101 + CAM + OR soft inference), NYU 256x352, batch 16 per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops"], "tensor_sustained": d.get("bf16_tflops_sustained"), "src": "measured"}
+    return {"hbm": 6650.0, "tensor": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_net(device):
+    from acan_b200.network import ResNet
+    torch.manual_seed(2019)
+    net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=0, layers=LAYERS101)
+    net = net.to(device).to(memory_format=torch.channels_last)
+    # BN calibration (never eval() on raw running statistics): one train()-mode pass with momentum 1
+    # puts the batch statistics of a synthetic batch into the running buffers, then eval().
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    net.train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        net(torch.rand(BATCH, 3, H, W, device=device).contiguous(memory_format=torch.channels_last))
+    for m in bns:
+        m.momentum = 0.1
+    return net.eval()
+
+
+def step_device(net, images):
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        return net.inference(net(images))
+
+
+def cpu_reference_forward(sd_cpu, n_iter, warm, threads):
+    """oracle port of the reference forward (ResNet-101 + CAM + decode_ord + soft OR) on the host cores, B = 1."""
+    from oracle import acan_oracle as O
+    torch.set_num_threads(threads)
+    x = torch.rand(1, 3, H, W)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + n_iter):
+            t0 = time.perf_counter()
+            out = O.acan_forward(x, sd_cpu, LAYERS101, "OR", training=False)
+            depth = O.inference(out["y"], "OR", "soft", DMIN, DMAX, K)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    return times, depth
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    from acan_b200.network import ResNet
+    torch.manual_seed(2019)
+    net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=0, layers=LAYERS101)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    threads = os.cpu_count() or 1
+    times, _ = cpu_reference_forward(sd, args.steps, args.warmup, threads)
+    tot = sum(times)
+    val = len(times) / tot
+    sample = f"B=1 image per step x {len(times)} steps, fp32, torch CPU ops, eval-mode BN"
+    print(json.dumps({
+        "impl": "reference", "metric": "ACAN NYU-shape forward images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from acan_b200 import _lib
+    from acan_b200.parallel import init_distributed
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    init_distributed("nccl" if world > 1 else None)
+    lib = _lib.load()
+    _lib.check(lib.acan_device_check(), "acan_device_check")
+    torch.backends.cudnn.benchmark = True                 # as depthest_main.py:65
+
+    net = build_net(device)
+    n_rot = 8                                             # 8 distinct input batches = 138 MB > 126 MB L2
+    host = [torch.rand(BATCH, 3, H, W).contiguous(memory_format=torch.channels_last).pin_memory() for _ in range(n_rot)]
+    dev_in = [h.to(device, non_blocking=True) for h in host]
+    depth_host = torch.empty(BATCH, 1, H, W).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(net, dev_in[i % n_rot])
+    barrier()
+    launches0 = lib.acan_launch_count()
+    _lib.check(lib.acan_profile_begin(args.steps * 16 + 64), "acan_profile_begin")
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        depth = step_device(net, dev_in[i % n_rot])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    ms = (ctypes.c_float * 7)()
+    cnt = (ctypes.c_int * 7)()
+    _lib.check(lib.acan_profile_end(ms, cnt), "acan_profile_end")
+    launches = lib.acan_launch_count() - launches0
+
+    # ---- end to end: host buffers in, host depth out, every step ---------------------------------------------
+    def step_e2e(i):
+        x = host[i % n_rot].to(device, non_blocking=True)
+        d = step_device(net, x)
+        depth_host.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+
+    t = torch.tensor([elapsed, e2e_elapsed], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed, e2e_elapsed = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    n = (H // 8) * (W // 8)
+    per_launch = lambda k: (ms[k] / max(cnt[k], 1)) * 1e-3          # noqa: E731  seconds per bracket
+    pv_flops = BATCH * 2.0 * n * n * 2048                           # a4: 2*N^2*dv per image
+    core_flops = BATCH * 5120.0 * n * n                             # a2+a4: 2*N^2*(dk+dv) per image
+    t_pv = per_launch(3)
+    t_core = per_launch(0) + per_launch(1) + per_launch(2) + per_launch(3)
+    head_bytes = BATCH * 324.0 * H * W                              # prob -> depth: (K+1)*HW*4 per image
+    t_head = per_launch(4)
+    roof = {"bound": "tensor", "kernel": "gemm_kernel<MODE_PV> (aggregation O^T = V P^T, tcgen05)", "achieved": pv_flops / t_pv / 1e12,
+            "peak": pk["tensor"], "unit": "TFLOP/s", "frac": pv_flops / t_pv / 1e12 / pk["tensor"], "traffic": None,
+            "peak_source": pk["src"] + " (bf16 burst)", "launch_us": t_pv * 1e6, "launches_timed": cnt[3]}
+    extra = {
+        "attention_core": {"bound": "tensor", "what": "operand pack + stats + probability + aggregation passes, algorithmic 5120*N^2 FLOP/img",
+                           "achieved": core_flops / t_core / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": core_flops / t_core / 1e12 / pk["tensor"],
+                           "us": {"pack": per_launch(0) * 1e6, "stats": per_launch(1) * 1e6, "probs": per_launch(2) * 1e6, "pv": t_pv * 1e6}},
+        "head": {"bound": "hbm", "what": "OR soft inference prob -> depth, 324*HW B/img", "achieved": head_bytes / t_head / 1e9 if t_head > 0 else None,
+                 "peak": pk["hbm"], "unit": "GB/s", "frac": head_bytes / t_head / 1e9 / pk["hbm"] if t_head > 0 else None, "launch_us": t_head * 1e6},
+        "pool_branch_us": per_launch(5) * 1e6,
+    }
+    out = {
+        "metric": "ACAN NYU-shape forward images/sec", "value": world * BATCH * args.steps / elapsed, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (batch-sharded replicas, no collective in inference)",
+                   "precision": "bf16 autocast cuDNN convs; attention core fp16 operands / fp32 accumulate; head fp32",
+                   "l2": f"{n_rot} rotating input batches (138 MB) + ~190 MB of bf16 weights per step exceed the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": world * BATCH * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
+                "d2h_bytes_per_step": BATCH * H * W * 4, "ms_per_step": e2e_elapsed / args.steps * 1e3},
+        "gpu_launches": int(launches), "roofline": roof, **extra,
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        threads = os.cpu_count() or 1
+        times, d_cpu = cpu_reference_forward(sd, 6, 1, threads)
+        out["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "images/s", "cores": threads, "kind": "port",
+                               "sample": f"B=1 image x {len(times)} forwards of the same network (oracle port, fp32 torch CPU ops), {sum(times):.1f} s"}
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,17 @@ const char* acan_last_error(void);
 /* 0 if the current device can run the library (sm_100), else ACAN_ERR_ARCH / a cudaError_t. */
 int         acan_device_check(void);
 
+/* Kernels launched by this library since it was loaded (bench.py's gpu_launches). */
+long long   acan_launch_count(void);
+
+/* Measurement hooks: between acan_profile_begin and acan_profile_end every kernel group is bracketed by a pair of
+ * CUDA events recorded on the caller's stream.  acan_profile_end waits for them and returns, per group,
+ * the summed device time in ms and the number of brackets.  Groups (ACAN_PROF_*): 0 operand pack, 1 affinity
+ * statistics pass, 2 probability pass, 3 aggregation (P.V) pass, 4 head, 5 pooling branch, 6 materialised KL. */
+#define ACAN_PROF_KINDS 7
+int acan_profile_begin(int max_marks);
+int acan_profile_end(float* ms_by_kind_host, int* count_by_kind_host);
+
 /* ---------------------------------------------------------------- depth head ---------- */
 
 /* BaseClassificationModel_.decode_ord (model.py:40-45):

@@ -1,0 +1,57 @@
+"""world_size-2 gloo test of the multi-GPU host logic (batch sharding + bucketed gradient all-reduce)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from acan_b200.parallel import GradAllReducer, init_distributed, shard_batch
+    r, w, _ = init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(7)                                     # same weights and same global batch on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 1))
+    x, y = torch.randn(8, 6), torch.randn(8, 1)
+    reducer = GradAllReducer(net.parameters(), bucket_mb=0.0005)   # tiny buckets -> several in flight
+    assert len(reducer.buckets) >= 2
+    xs, ys = shard_batch(x, rank, world), shard_batch(y, rank, world)
+    loss = torch.nn.functional.mse_loss(net(xs), ys)
+    loss.backward()
+    reducer.finish()
+    got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    # expectation: mean over ranks of the per-shard gradients == gradient of the mean of per-shard losses
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 1))
+    ref.load_state_dict(net.state_dict())
+    tot = sum(torch.nn.functional.mse_loss(ref(shard_batch(x, q, world)), shard_batch(y, q, world)) for q in range(world)) / world
+    tot.backward()
+    want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    out[rank] = float((got - want).abs().max())
+    # second step reuses the reducer
+    net.zero_grad()
+    torch.nn.functional.mse_loss(net(xs), ys).backward()
+    reducer.finish()
+    got2 = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    out[rank + world] = float((got2 - want).abs().max())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_allreduce_world2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == 2 * world
+    assert all(v < 1e-6 for v in out.values()), dict(out)

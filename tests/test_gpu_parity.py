@@ -1,0 +1,324 @@
+"""GPU parity tests (-m gpu): the sm_100a kernels, called through the C ABI / drop-in modules, against
+  (1) the golden vectors generated from the reference itself (tests/golden/*.npz),
+  (2) the CPU oracle (oracle/acan_oracle.py) on the same seeded inputs, and
+  (3) size-independent properties at the BASELINE.json sizes.
+Tolerances: float outputs <= 1e-3 max-norm relative (north star); hard bin indices bit-exact; the attention core
+computes with fp16 operands (11-bit significand) and fp32 accumulation -- the 1e-3 bar is checked against the
+fp32/fp64 oracle, i.e. it includes that rounding.  /root/reference is never read here.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import acan_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda"
+TOL = 1e-3
+NYU = (0.72, 10.0, 80)
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32_library_ops():
+    """cuDNN / cuBLAS calls around the kernels run true fp32 in these tests (the reference's GPU default lets cuDNN
+    use TF32, ~1e-3 noise on its own); the fp16-operand rounding of the tcgen05 path stays in."""
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def close(a, b, tol=TOL):
+    e = synth.rel_err(a, b)
+    assert e <= tol, f"max-norm relative error {e:.3e} > {tol}"
+
+
+# ------------------------------------------------------------------------------------ head
+
+@pytest.mark.parametrize("tag", ["nyu", "kitti"])
+def test_head_against_reference_golden(golden, tag):
+    from acan_b200 import ops
+    g = golden("head_" + tag)
+    dmin, dmax, K = g["params"]
+    K = int(K)
+    y, prob, score, sat = (T(g[k]).to(DEV) for k in ("y", "prob", "score", "sat"))
+    close(ops.decode_ord(y), T(g["prob"]), 1e-6)
+    d, idx = ops.head_inference(prob, "OR", "hard", dmin, dmax, K, want_index=True)
+    assert torch.equal(idx.cpu(), T(g["or_hard_idx"]))                       # bit-exact bin index
+    close(d, T(g["or_hard"]), 1e-6)
+    close(ops.head_inference(prob, "OR", "soft", dmin, dmax, K), T(g["or_soft"]), 1e-5)
+    close(ops.head_inference(sat, "OR", "soft", dmin, dmax, K), T(g["or_soft_sat"]), 1e-5)   # s = K needs bins K+1, K+2
+    close(ops.head_inference(sat, "OR", "hard", dmin, dmax, K), T(g["or_hard_sat"]), 1e-6)
+    d, idx = ops.head_inference(score, "CE", "hard", dmin, dmax, K, want_index=True)
+    assert torch.equal(idx.cpu(), T(g["ce_hard_idx"]))                       # first maximum wins on the planted tie
+    close(d, T(g["ce_hard"]), 1e-6)
+    close(ops.head_inference(score, "CE", "soft", dmin, dmax, K), T(g["ce_soft"]), 1e-5)
+    # decode_ord fused into the head
+    d, idx = ops.head_inference(y, "OR", "hard", dmin, dmax, K, from_logits=True, want_index=True)
+    assert torch.equal(idx.cpu(), T(g["or_hard_idx"]))
+    close(ops.head_inference(y, "OR", "soft", dmin, dmax, K, from_logits=True), T(g["or_soft"]), 1e-5)
+    assert torch.equal(ops.continuous2discrete(T(g["label"]).to(DEV), dmin, dmax, K).cpu(), T(g["c2d"]))
+
+
+def test_head_edge_cases():
+    from acan_b200 import ops
+    dmin, dmax, K = NYU
+    tie = torch.zeros(1, 2 * K, 4, 4, device=DEV)                            # y0 == y1 -> p = 0.5 exactly -> not counted
+    _, idx = ops.head_inference(tie, "OR", "hard", dmin, dmax, K, from_logits=True, want_index=True)
+    assert int(idx.max()) == 0
+    ones = torch.ones(1, K, 4, 4, device=DEV)
+    d, idx = ops.head_inference(ones, "OR", "hard", dmin, dmax, K, want_index=True)
+    assert int(idx.min()) == K
+    close(d, O.hard_ordinal_regression(ones.cpu(), dmin, dmax, K), 1e-6)
+    nanmax = torch.randn(1, K, 4, 4, device=DEV)
+    nanmax[0, 17, 1, 1] = float("nan")                                        # torch.argmax treats NaN as the maximum
+    _, idx = ops.head_inference(nanmax, "CE", "hard", dmin, dmax, K, want_index=True)
+    assert torch.equal(idx.cpu().long(), torch.argmax(nanmax.cpu(), 1, keepdim=True))
+    odd = 3 * torch.randn(2, 2 * K, 5, 7, device=DEV)                         # HW % 4 != 0 -> scalar twin
+    close(ops.decode_ord(odd), O.decode_ord(odd.cpu()), 1e-6)
+    close(ops.head_inference(odd, "OR", "soft", dmin, dmax, K, from_logits=True),
+          O.soft_ordinal_regression(O.decode_ord(odd.cpu()), dmin, dmax, K), 1e-5)
+
+
+@pytest.mark.parametrize("B,H,W,params", [(16, 256, 352, NYU), (32, 160, 512, (1.98, 80.0, 80))])
+def test_head_full_size_properties(B, H, W, params):
+    """BASELINE.json C2 / C3 shapes: fused == two-step bit for bit; indices in range; depth inside the bin range;
+    hard index == count recomputed by torch on the same probabilities."""
+    from acan_b200 import ops
+    dmin, dmax, K = params
+    torch.manual_seed(synth.SEED)
+    y = 3 * torch.randn(B, 2 * K, H, W, device=DEV)
+    prob = ops.decode_ord(y)
+    for mode in ("soft", "hard"):
+        d1, i1 = ops.head_inference(prob, "OR", mode, dmin, dmax, K, want_index=True)
+        d2, i2 = ops.head_inference(y, "OR", mode, dmin, dmax, K, from_logits=True, want_index=True)
+        assert torch.equal(d1, d2) and torch.equal(i1, i2)
+        assert int(i1.min()) >= 0 and int(i1.max()) <= K
+        assert float(d1.min()) >= dmin * 0.999 and math.isfinite(float(d1.max()))
+    _, ih = ops.head_inference(prob, "OR", "hard", dmin, dmax, K, want_index=True)
+    assert torch.equal(ih.long(), (prob > 0.5).sum(1, keepdim=True))
+    score = y[:, :K].contiguous()
+    _, ic = ops.head_inference(score, "CE", "hard", dmin, dmax, K, want_index=True)
+    assert torch.equal(ic.long(), torch.argmax(score, 1, keepdim=True))
+    sub = slice(0, 2)
+    close(ops.head_inference(score[sub], "CE", "soft", dmin, dmax, K), O.soft_cross_entropy(score[sub].cpu(), dmin, dmax, K), 1e-5)
+    close(d1[sub], O.hard_ordinal_regression(prob[sub].cpu(), dmin, dmax, K), 1e-6)
+
+
+def test_decode_ord_backward_matches_autograd():
+    from acan_b200 import functions as fn
+    y = (2 * torch.randn(2, 160, 8, 12, device=DEV)).requires_grad_(True)
+    g = torch.randn(2, 80, 8, 12, device=DEV)
+    fn.DecodeOrd.apply(y).backward(g)
+    yc = y.detach().cpu().double().requires_grad_(True)
+    O.decode_ord(yc).backward(g.cpu().double())
+    close(y.grad, yc.grad, 1e-5)
+
+
+# ------------------------------------------------------------------------------------ pooling branch
+
+def test_pool_branch_against_oracle():
+    from acan_b200 import ops
+    g = {}
+    sd = synth.fill_state_dict({"linear1.weight": torch.empty(512, 2048), "linear1.bias": torch.empty(512),
+                                "linear2.weight": torch.empty(512, 512), "linear2.bias": torch.empty(512)})
+    for b, h, w in ((2, 4, 6), (3, 28, 38)):
+        x = synth.feature_map("pool.x", b, 2048, h, w)
+        keep = (synth.rand("pool.keep", b, 2048) > 0.5).float()
+        for km in (None, keep):
+            _, _, got = ops.pool_branch(x.to(DEV), *(sd[k].to(DEV) for k in ("linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias")),
+                                        None if km is None else km.to(DEV))
+            close(got, O.image_context(x.double(), {k: v.double() for k, v in sd.items()}, "", None if km is None else km.double()), 1e-5)
+
+
+# ------------------------------------------------------------------------------------ attention loss
+
+def test_attention_loss_against_reference_golden(golden):
+    from acan_b200 import ops
+    g = golden("attention_loss")
+    close(ops.gt_sim_map(T(g["toy_label"]).to(DEV)), T(g["toy_gt"]), 1e-6)      # KAT: a = [3, 6, 0, 12]
+    for tag in ("a", "b"):
+        sim, dis = T(g[tag + "_sim"]).to(DEV), T(g[tag + "_dis"]).to(DEV)
+        loss, grad = ops.attention_loss(sim, dis, want_grad=True)
+        assert abs(float(loss) - float(g[tag + "_loss"])) <= 1e-5 * abs(float(g[tag + "_loss"]))
+        close(grad, T(g[tag + "_grad"]), 1e-5)
+        close(ops.gt_sim_map(dis), T(g[tag + "_gt"]), 1e-6)
+    sim, dis = T(g["c_sim"]).to(DEV), T(g["c_dis"]).to(DEV)                      # clamp window: Q = 0 and Q = 1e-12 under P > 0
+    loss, grad = ops.attention_loss(sim, dis, want_grad=True)
+    assert abs(float(loss) - float(g["c_loss"])) <= 1e-5 * abs(float(g["c_loss"]))
+    want = T(g["c_grad"])
+    live = ~torch.isnan(want)                                                    # reference autograd: NaN where Q == 0 exactly; kernel: 0
+    close(grad.cpu()[live], want[live], 1e-5)
+    assert float(grad.cpu()[~live].abs().max()) == 0.0 and float(grad[0, 5, 7]) == 0.0
+
+
+# ------------------------------------------------------------------------------------ attention core
+
+def _attention_case(b, h, w, dk=512, dv=2048, label=False, tag="attn"):
+    from acan_b200 import ops
+    n = h * w
+    f = synth.feature_map(f"{tag}.f.{b}.{n}", b, dk, h, w)
+    v = synth.feature_map(f"{tag}.v.{b}.{n}", b, dv, h, w)
+    dis = None
+    if label:
+        dis = O.continuous2discrete(synth.depth_label(f"{tag}.lab.{b}.{n}", b, h * 8, w * 8, 0.5, 10.5), *NYU)
+    out = ops.attention_forward(f.to(DEV), v.to(DEV), want_sim_map=True, dis_label=None if dis is None else dis.to(DEV))
+    sim = O.affinity(f.double())
+    ctx = O.aggregate(sim, v.double())
+    close(out["sim_map"], sim)
+    close(out["ctx"], ctx)
+    assert synth.rel_l2(out["ctx"], ctx) <= 5e-4
+    close(out["sim_map"].sum(-1), torch.ones(b, n), 1e-5)
+    st = out["row_stats"].double().cpu()
+    lse = (st[..., 0] + torch.log2(st[..., 1])) * math.log(2.0)
+    close(lse, torch.logsumexp(torch.matmul(f.double().reshape(b, dk, n).transpose(1, 2), f.double().reshape(b, dk, n)) * dk ** -0.5, -1), 1e-4)
+    rows = torch.tensor([n // 4, n // 2, 3 * n // 4])
+    close(ops.attention_rows(out["ws"], rows), sim[:, rows])
+    if label:
+        want = float(O.attention_loss(sim, dis.double()))
+        assert abs(float(out["loss"]) - want) <= TOL * abs(want)                                   # fused into the probability pass
+        assert abs(float(ops.attention_loss_fused(out["ws"], dis.to(DEV))) - want) <= TOL * abs(want)   # fused, stand-alone
+        assert abs(float(ops.attention_loss(out["sim_map"], dis.to(DEV))) - want) <= TOL * abs(want)    # materialised
+    return out
+
+
+@pytest.mark.parametrize("b,h,w,dk,dv", [(1, 8, 16, 64, 128), (2, 4, 6, 512, 2048), (1, 1, 8, 512, 128), (3, 5, 8, 128, 256)])
+def test_attention_small_and_ragged(b, h, w, dk, dv):
+    _attention_case(b, h, w, dk, dv, label=(h * 8 >= 8 and w * 8 >= 8))
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 28, 38), (1, 20, 80), (2, 32, 44), (2, 20, 64)])
+def test_attention_reference_shapes(b, h, w):
+    """N = 1064 / 1600 (reference defaults, not multiples of 128), 1408 / 1280 (BASELINE.json shapes)."""
+    _attention_case(b, h, w, label=True)
+
+
+def test_attention_full_size_properties():
+    """C2 size (B=16, N=1408): rows of P sum to 1, ctx is a convex combination of V columns, linear in V,
+    and equals a cuBLAS fp32 product with the kernel's own sim_map."""
+    from acan_b200 import ops
+    torch.manual_seed(synth.SEED)
+    b, h, w = 16, 32, 44
+    f = torch.relu(torch.randn(b, 512, h, w, device=DEV))
+    v = torch.relu(torch.randn(b, 2048, h, w, device=DEV))
+    out = ops.attention_forward(f, v, want_sim_map=True)
+    sim, ctx = out["sim_map"], out["ctx"].reshape(b, 2048, -1)
+    close(sim.sum(-1), torch.ones(b, h * w), 1e-5)
+    assert float(sim.min()) >= 0.0
+    vv = v.reshape(b, 2048, -1)
+    assert bool((ctx <= vv.max(-1, keepdim=True).values * (1 + 2e-3) + 1e-6).all()) and bool((ctx >= -1e-6).all())
+    close(ctx, torch.matmul(vv, sim.transpose(1, 2)))
+    out2 = ops.attention_forward(f, 2.0 * v)
+    close(out2["ctx"].reshape(b, 2048, -1), 2.0 * ctx, 1e-6)                       # exactly linear in V (power-of-two scale)
+    perm = torch.randperm(b, device=DEV)
+    out3 = ops.attention_forward(f[perm].contiguous(), v[perm].contiguous())
+    assert torch.equal(out3["ctx"], out["ctx"][perm])                             # images are independent units
+
+
+def test_attention_backward_against_oracle_autograd():
+    from acan_b200 import functions as fn
+    from acan_b200.modules import _Holder
+    b, h, w, dk, dv = 2, 4, 6, 128, 256
+    f = synth.feature_map("bw.f", b, dk, h, w)
+    v = synth.feature_map("bw.v", b, dv, h, w)
+    dis = O.continuous2discrete(synth.depth_label("bw.lab", b, h * 8, w * 8, 0.5, 10.5), *NYU)
+    go = synth.randn("bw.go", b, dv, h, w)
+    fd, vd = f.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    ctx, loss = fn.Attention.apply(fd, vd, dis.to(DEV), _Holder())
+    ((ctx * go.to(DEV)).sum() + 0.7 * loss).backward()
+    fc, vc = f.double().requires_grad_(True), v.double().requires_grad_(True)
+    sim = O.affinity(fc)
+    ((O.aggregate(sim, vc) * go.double()).sum() + 0.7 * O.attention_loss(sim, dis.double())).backward()
+    close(fd.grad, fc.grad, 2e-3)
+    close(vd.grad, vc.grad, 2e-3)
+
+
+# ------------------------------------------------------------------------------------ modules against the reference goldens
+
+def _load_synth(module, keys, shapes):
+    sd = synth.fill_state_dict({k: torch.empty(eval(s)) for k, s in zip(keys, shapes)})
+    module.load_state_dict(sd)
+    return sd
+
+
+@pytest.mark.parametrize("name", ["sadecoder_24", "sadecoder_1064"])
+def test_sadecoder_module_against_reference_golden(golden, name):
+    from acan_b200.modules import LazySimMap, SADecoder
+    g = golden(name)
+    hh, ww, b = (int(v) for v in g["hw"])
+    dec = SADecoder(height=hh, width=ww)
+    _load_synth(dec, g["keys"], g["shapes"])
+    dec = dec.to(DEV).eval()
+    x = synth.feature_map(name + ".x", b, 2048, hh // 8, ww // 8).to(DEV)
+    with torch.no_grad():
+        out, sim = dec(x)
+    assert isinstance(sim, LazySimMap) and tuple(sim.shape) == (b, (hh // 8) * (ww // 8), (hh // 8) * (ww // 8))
+    close(out.reshape(-1)[T(g["out_idx"]).to(DEV)], T(g["out_val"]))
+    n = sim.shape[1]
+    pts = [n // 4, n // 2, 3 * n // 4]
+    vis = sim.cpu()[:b][:, pts]                                                   # the vis_utils.py:107-121 access pattern
+    dense = sim.materialize()
+    close(dense.reshape(-1)[T(g["sim_idx"]).to(DEV)], T(g["sim_val"]))
+    close(vis, dense[:, pts].cpu(), 1e-5)
+    close(dense.sum(-1), T(g["sim_rowsum"]), 1e-5)
+    assert dec.get_sim_map() is sim
+
+
+def test_full_network_against_reference_golden(golden):
+    """tiny ResNet ([1,1,1,1] blocks) + CAM + OR head, BN on batch statistics, dropout off -- forward dict, both
+    inference modes and the beta = 1 loss through LossFunc, against the reference's own outputs."""
+    from acan_b200.network import ResNet, OrdinalRegression2d
+    from acan_b200.modules import AttentionLoss2d
+    g = golden("resnet_tiny")
+    hh, ww, b = (int(v) for v in g["hw"])
+    net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=1.0, layers=[1, 1, 1, 1])
+    _load_synth(net, g["keys"], g["shapes"])
+    net = net.to(DEV).train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()
+    x = synth.rand("resnet.x", b, 3, hh, ww).to(DEV)
+    label = synth.depth_label("resnet.label", b, hh, ww, 0.5, 10.5).to(DEV)
+    out = net(x)
+    close(out["y"].reshape(-1)[T(g["y_idx"]).to(DEV)], T(g["y_val"]))
+    close(net.inference(out), T(g["depth_soft"]))
+    net.inferenceType = "hard"
+    hard = net.inference(out).cpu()
+    assert (hard - T(g["depth_hard"])).abs().gt(1e-4).float().mean() < 2e-3          # a p ~ 0.5 bin may flip under conv rounding
+    crit = net.LossFunc(*NYU, AppearanceLoss=OrdinalRegression2d(ignore_index=0), AttentionLoss=AttentionLoss2d(scale=1), alpha=0.0, beta=1.0)
+    l1, _, l3, tot = crit(out, label, 1)
+    assert abs(float(l3) - float(g["loss3"])) <= TOL * abs(float(g["loss3"]))
+    assert abs(float(l1) - float(g["loss1"])) <= TOL * abs(float(g["loss1"]))
+    assert abs(float(tot) - float(g["total"])) <= TOL * abs(float(g["total"]))
+    tot.backward()                                                                  # the training step runs end to end
+    gk = net.decoder.saconv.f_key.conv.weight.grad
+    assert gk is not None and torch.isfinite(gk).all() and float(gk.abs().max()) > 0
+    net.inferenceType = "soft"
+    with torch.no_grad():
+        close(net.predict_depth(x), net.inference(net(x)), 1e-5)                    # fused eval shortcut == two-step
+
+
+def test_training_step_gradients_against_oracle():
+    """SelfAttentionBlock-level fwd+bwd with the attention loss: parameter gradients vs autograd through the oracle."""
+    from acan_b200.modules import AttentionLoss2d, SelfAttentionBlock_
+    blk = SelfAttentionBlock_(64, 64, 128)
+    sd = synth.fill_state_dict(blk.state_dict())
+    blk.load_state_dict(sd)
+    blk = blk.to(DEV).train()
+    b, h, w = 2, 4, 6
+    x = synth.feature_map("ts.x", b, 64, h, w)
+    dis = O.continuous2discrete(synth.depth_label("ts.lab", b, h * 8, w * 8, 0.5, 10.5), *NYU)
+    go = synth.randn("ts.go", b, 128, h, w)
+    ctx, sim = blk(x.to(DEV))
+    loss = (ctx * go.to(DEV)).sum() + AttentionLoss2d()(sim, dis.to(DEV))
+    loss.backward()
+    sdd = {k: v.double().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    c2, s2, _ = O.self_attention_block(x.double(), sdd, "", training=True)
+    ((c2 * go.double()).sum() + O.attention_loss(s2, dis.double())).backward()
+    for name, p in blk.named_parameters():
+        close(p.grad, sdd[name].grad, 5e-3)
