@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace acan {
 
@@ -52,11 +53,14 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2 };
 
+constexpr int kOutChunkBytes = 128 * 128;   // epilogue staging: 128 rows x 128 B (one SWIZZLE_128B TMA-store box)
+constexpr int kOutBuffers = 2;
+
 struct GemmArgs {
-  int batch, m_tiles, n_tiles, k_steps;
+  int batch, m_tiles, n_tiles, k_steps;   // m_tiles counts tiles of 128*CG rows
   int m_rows;          // valid rows of A per image (N queries, or dv channels)
   int n_cols;          // valid rows of B per image (N keys, or N queries)
-  int bn;              // tile width (multiple of 32, <= 256)
+  int bn;              // tile width (multiple of 32, of 64 when P is stored; <= 256)
   int stages;
   uint32_t idesc;
   float c;             // scale * log2(e)
@@ -64,13 +68,11 @@ struct GemmArgs {
   float2* part;        // [B, n_tiles, m_rows] (m2, l) partials
   // MODE_PROBS
   const float2* stats; // [B, N] final (m2, l)
-  __half* p_out;       // [B, N, N] fp16 or null
-  float* sim_out;      // [B, N, N] fp32 or null
+  int store_p;         // P (fp16) goes out through tmap_out
+  float* sim_out;      // [B, N, N] fp32 or null (rare path: plain vector stores)
   const float* logbin; // [B, N] ln(bin) (-inf for bin 0) or null  -> fused KL
   const float* lnz;    // [B, N] ln(Z_i) of the target affinity (unused when bin_i == 0)
   float* kl_part;      // [B, n_tiles, N] per-row partial losses
-  // MODE_PV
-  float* o_out;        // [B, m_rows, n_cols] fp32
 };
 
 struct __align__(8) PipeBarriers {
@@ -86,62 +88,86 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int MODE>
+// 16-byte chunk j (0..7) of row r (0..127) inside a 128 B-per-row SWIZZLE_128B staging buffer
+__device__ __forceinline__ uint4* staged_chunk(uint8_t* buf, int r, int j) {
+  return reinterpret_cast<uint4*>(buf + r * 128 + ((j ^ (r & 7)) << 4));
+}
+
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
+// each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues M = 256 MMAs that read both
+// shared memories and write both TMEMs, so the L2 -> SM operand traffic per FLOP drops by (128+BN)/(128+BN/2).
+template <int MODE, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t a_bytes = BM * BK * 2;
-  const uint32_t b_bytes = static_cast<uint32_t>(g.bn) * BK * 2;
+  const uint32_t b_rows = static_cast<uint32_t>(g.bn) / CG;          // rows of the B tile this CTA stages
+  const uint32_t b_bytes = b_rows * BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + static_cast<size_t>(g.stages) * stage_bytes);
+  uint8_t* out_stage = smem + static_cast<size_t>(g.stages) * stage_bytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(out_stage + kOutBuffers * kOutChunkBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int total_tiles = g.batch * g.m_tiles * g.n_tiles;
+  const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (MODE != MODE_STATS) tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < g.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 128); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 128 * CG); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(&bars->tmem_base, kTmemCols);
+    if (CG == 2) tmem_alloc_2sm(&bars->tmem_base, kTmemCols); else tmem_alloc(&bars->tmem_base, kTmemCols);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();      // barrier inits + TMEM address visible (pair-wide)
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (one thread per CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int nt = tile % g.n_tiles;
         const int mt = (tile / g.n_tiles) % g.m_tiles;
         const int b = tile / (g.n_tiles * g.m_tiles);
+        const int a_row = (mt * CG + static_cast<int>(cta_rank)) * BM;
+        const int b_row = nt * g.bn + static_cast<int>(cta_rank * b_rows);
         for (int ks = 0; ks < g.k_steps; ++ks) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          mbar_expect_tx(&bars->full[stage], stage_bytes);
-          tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, mt * BM, b);
-          tma_load_3d(sa + a_bytes, &tmap_b, &bars->full[stage], ks * BK, nt * g.bn, b);
+          if (CG == 1) {
+            mbar_expect_tx(&bars->full[stage], stage_bytes);
+            tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, a_row, b);
+            tma_load_3d(sa + a_bytes, &tmap_b, &bars->full[stage], ks * BK, b_row, b);
+          } else {
+            // both CTAs' bytes complete on the LEADER's barrier; the leader arms it for the pair's total
+            if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], stage_bytes * 2);
+            const uint32_t leader_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+            tma_load_3d_2sm(sa, &tmap_a, leader_bar, ks * BK, a_row, b);
+            tma_load_3d_2sm(sa + a_bytes, &tmap_b, leader_bar, ks * BK, b_row, b);
+          }
           if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread; leader CTA of a pair)
+    if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kMaxBN;
@@ -152,13 +178,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_f16(d_tmem, umma_desc_k_sw128(sa + k * UMMA_K * 2), umma_desc_k_sw128(sb + k * UMMA_K * 2), g.idesc,
-                     (ks | k) != 0 ? 1u : 0u);
+            const uint64_t da = umma_desc_k_sw128(sa + k * UMMA_K * 2), db = umma_desc_k_sw128(sb + k * UMMA_K * 2);
+            if (CG == 1) umma_f16(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
+            else         umma_f16_2sm(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->empty[stage]);            // smem slot free once these MMAs have read it
+          // smem slot free (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 1) umma_commit(&bars->empty[stage]); else umma_commit_2sm(&bars->empty[stage], 3);
           if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tmem_full[acc]);            // accumulator complete -> epilogue
+        if (CG == 1) umma_commit(&bars->tmem_full[acc]); else umma_commit_2sm(&bars->tmem_full[acc], 3);   // -> epilogue(s)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -167,12 +195,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const bool store_leader = (threadIdx.x == 64);      // warp 2, lane 0 issues the TMA stores
+    uint32_t acc = 0, acc_phase = 0, out_buf = 0;
+    const uint32_t leader_empty0 = (CG == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0) : 0u;
+    const uint32_t leader_empty1 = (CG == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[1]), 0) : 0u;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int nt = tile % g.n_tiles;
       const int mt = (tile / g.n_tiles) % g.m_tiles;
       const int b = tile / (g.n_tiles * g.m_tiles);
-      const int row = mt * BM + row_in_tile;
+      const int row0 = (mt * CG + static_cast<int>(cta_rank)) * BM;
+      const int row = row0 + row_in_tile;
       const bool row_ok = row < g.m_rows;
       const int col0 = nt * g.bn;
       const int nvalid = min(g.bn, g.n_cols - col0);   // >= 1 by construction of n_tiles
@@ -212,77 +244,104 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; kl_row = row_ok && la_i > -INFINITY; }
         float kl_acc = 0.f;
         const float* la_cols = kl ? g.logbin + static_cast<size_t>(b) * g.n_cols + col0 : nullptr;
-        __half* prow = g.p_out ? g.p_out + (brow * g.n_cols + col0) : nullptr;
         float* srow = g.sim_out ? g.sim_out + (brow * g.n_cols + col0) : nullptr;
-        for (int ch = 0; ch < chunks; ++ch) {
-          float v[32];
-          tmem_ld_32x32(taddr + ch * 32, v);
-          tmem_ld_wait();
-          const int nv = nvalid - ch * 32;              // valid columns in this chunk (multiple of 8 since N % 8 == 0)
+        // 64 columns (= 128 B of fp16) per staged TMA store
+        for (int ch = 0; ch < chunks; ch += 2) {
+          uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
+          if (g.store_p) {
+            if (store_leader) tma_store_wait_read<kOutBuffers - 1>();   // the store that last used `buf` has drained it
+            named_bar_sync(1, 128);
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], g.c, -m2);      // log2 of the un-normalised probability
-          if (kl_row) {
+          for (int half = 0; half < 2; ++half) {
+            const int chh = ch + half;
+            if (chh < chunks) {
+              float v[32];
+              tmem_ld_32x32(taddr + chh * 32, v);
+              tmem_ld_wait();
+              const int nv = nvalid - chh * 32;         // valid columns in this chunk (multiple of 8 since N % 8 == 0)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nv) {
-                const float la_j = __ldg(la_cols + ch * 32 + j);
-                const float lnr = -fabsf(la_i - la_j);                       // ln min(a_i/a_j, a_j/a_i); -inf if a_j = 0
-                const float lnw = lnr - lnz_i;                               // ln W_ij
-                const float lnq = (v[j] - log2_l) * kLn2;                    // ln Q_ij, exact from the logits
-                const float w = ex2_approx(lnw * kLog2e);                    // 0 when a_j = 0
-                const float lr = fminf(fmaxf(lnw - lnq, -18.420680744f), 18.420680744f);   // ln clamp(W/Q, 1e-8, 1e8)
-                kl_acc += (w > 0.f) ? w * lr : 0.f;
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], g.c, -m2);      // log2 of the un-normalised probability
+              if (kl_row) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < nv) {
+                    const float la_j = __ldg(la_cols + chh * 32 + j);
+                    const float lnr = -fabsf(la_i - la_j);                       // ln min(a_i/a_j, a_j/a_i); -inf if a_j = 0
+                    const float lnw = lnr - lnz_i;                               // ln W_ij
+                    const float lnq = (v[j] - log2_l) * kLn2;                    // ln Q_ij, exact from the logits
+                    const float w = ex2_approx(lnw * kLog2e);                    // 0 when a_j = 0
+                    const float lr = fminf(fmaxf(lnw - lnq, -18.420680744f), 18.420680744f);   // ln clamp(W/Q, 1e-8, 1e8)
+                    kl_acc += (w > 0.f) ? w * lr : 0.f;
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
+              if (g.store_p) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *staged_chunk(buf, row_in_tile, half * 4 + q) =
+                      make_uint4(pack_half2(v[q * 8 + 0], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                                 pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+              }
+              if (srow && row_ok) {
+                float4* dst = reinterpret_cast<float4*>(srow + chh * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
               }
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
-          if (row_ok) {
-            if (prow) {
-              uint4* dst = reinterpret_cast<uint4*>(prow + ch * 32);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (q * 8 < nv)
-                  dst[q] = make_uint4(pack_half2(v[q * 8 + 0], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
-                                      pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+          if (g.store_p) {
+            fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA engine
+            named_bar_sync(1, 128);
+            if (store_leader) {                        // rows / columns beyond N are clipped by the tensor map
+              tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
+              tma_store_commit();
             }
-            if (srow) {
-              float4* dst = reinterpret_cast<float4*>(srow + ch * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            }
+            out_buf ^= 1;
           }
         }
         if (kl && row_ok) g.kl_part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = kl_acc;
-      } else {  // MODE_PV: rows = value channels, columns = query positions
-        float* orow = g.o_out + ((static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0)) * g.n_cols + col0);
+      } else {  // MODE_PV: rows = value channels, columns = query positions; 32 fp32 columns (128 B) per staged store
         for (int ch = 0; ch < chunks; ++ch) {
+          uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
+          if (store_leader) tma_store_wait_read<kOutBuffers - 1>();
+          named_bar_sync(1, 128);
           float v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
           tmem_ld_wait();
-          const int nv = nvalid - ch * 32;
-          if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(orow + ch * 32);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          for (int q = 0; q < 8; ++q)
+            *staged_chunk(buf, row_in_tile, q) = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
+                                                            __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (store_leader) {
+            tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
+            tma_store_commit();
           }
+          out_buf ^= 1;
         }
       }
 
       tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[acc]);              // 128 arrivals release the accumulator buffer
+      // 128 (x CG) arrivals on the LEADER's barrier release the accumulator buffer
+      if (CG == 1) mbar_arrive(&bars->tmem_empty[acc]);
+      else         mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (store_leader) tma_store_wait_all();             // staged bytes must have left shared memory before the CTA retires
   }
 
+  __syncwarp();                                            // single-lane role loops rejoin their warps
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal our barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -398,30 +457,48 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 tensor [batch][rows][inner] (inner contiguous), box = {64, box_rows, 1}, 128 B swizzle, OOB -> 0
-int make_tmap(CUtensorMap* m, const void* base, int inner, int rows, int batch, size_t row_pitch_bytes, size_t batch_pitch_bytes, int box_rows) {
+// tensor [batch][rows][inner] (inner contiguous) of fp16 (elem_bytes 2) or fp32 (4); box = {128 B of elements, box_rows, 1},
+// SWIZZLE_128B, out-of-bounds elements read as 0 / are not written
+int make_tmap(CUtensorMap* m, const void* base, int elem_bytes, int inner, int rows, int batch, size_t row_pitch_bytes, size_t batch_pitch_bytes,
+              int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch_bytes), static_cast<cuuint64_t>(batch_pitch_bytes)};
-  cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%d rows=%d batch=%d box_rows=%d)", (int)r, inner, rows, batch, box_rows);
   return 0;
 }
 
-// tile width: minimise (waves over 148 SMs) x (per-tile cost ~ bn + fixed overhead)
-int choose_bn(int n_cols, int other_tiles) {
+// CTA-pair (cta_group::2) or single-CTA tiles; ACAN_CTA_GROUP=1 forces the single-CTA kernels (A/B measurements)
+int cta_group() {
+  static int cg = 0;
+  if (cg == 0) {
+    const char* e = getenv("ACAN_CTA_GROUP");
+    cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cg;
+}
+
+// Tile width.  Per 64-deep k-step a CTA spends max(MMA time, operand-feed time) cycles:
+//   MMA   : 128*cg x bn x 64 MACs at 4096 MAC/cycle/SM                      = 2 * bn
+//   feed  : (16 KB of A + bn/cg rows x 128 B of B) at ~51 B/cycle/SM, the L2 -> SM rate both the bn = 160 (59 % of
+//           peak) and bn = 256 (80 %) measurements of the aggregation pass fit (profiles/r01_notes.md)
+// and the pass costs (waves over the 148 / cg tile slots) x that.  Wide tiles win unless they quantise badly.
+int choose_bn(int n_cols, int other_tiles, int cg, int step) {
   int best = kMinBN;
   double best_cost = 1e30;
-  for (int bn = kMinBN; bn <= kMaxBN; bn += 32) {
+  const int slots = kNumSMs / cg;
+  for (int bn = kMinBN; bn <= kMaxBN; bn += step) {
     const int nt = (n_cols + bn - 1) / bn;
     const long tiles = static_cast<long>(nt) * other_tiles;
-    const long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    const long waves = (tiles + slots - 1) / slots;
+    const double mma = 2.0 * bn, feed = (16384.0 + 128.0 * bn / cg) / 51.0;
+    const double cost = static_cast<double>(waves) * ((mma > feed ? mma : feed) + 40.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -460,22 +537,38 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   return w;
 }
 
-template <int MODE>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& g, cudaStream_t st) {
-  const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + static_cast<size_t>(g.bn) * BK * 2;
-  int stages = static_cast<int>(kSmemBudget / stage_bytes);
+template <int MODE, int CG>
+int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st) {
+  const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + static_cast<size_t>(g.bn / CG) * BK * 2;
+  int stages = static_cast<int>((kSmemBudget - kOutBuffers * kOutChunkBytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   g.stages = stages;
-  const size_t smem = stages * stage_bytes + sizeof(PipeBarriers) + 1024;
+  const size_t smem = stages * stage_bytes + kOutBuffers * kOutChunkBytes + sizeof(PipeBarriers) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ACAN_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ACAN_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int tiles = g.batch * g.m_tiles * g.n_tiles;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_kernel<MODE><<<grid, kGemmThreads, smem, st>>>(ta, tb, g);
+  const int slots = kNumSMs / CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((tiles < slots ? tiles : slots) * CG));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG>, ta, tb, tout, g);
+  if (e != cudaSuccess) return fail((int)e, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return launch_status("acan gemm_kernel");
+}
+
+template <int MODE>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st, int cg) {
+  return cg == 2 ? launch_gemm_cg<MODE, 2>(ta, tb, tout, g, st) : launch_gemm_cg<MODE, 1>(ta, tb, tout, g, st);
 }
 
 int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
@@ -489,31 +582,33 @@ int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
 // passes 1+2 over S = Fh Fh^T: statistics, then probabilities / sim_map / fused KL
 int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map, bool kl, int B, int N, int dk, float scale, cudaStream_t st,
                  bool need_stats, int* key_tiles) {
-  const int m_tiles = (N + BM - 1) / BM;
-  const int bn = choose_bn(N, B * m_tiles);
-  CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, w.fh, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
-  if (int e = make_tmap(&tb, w.fh, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn)) return e;
+  const int cg = cta_group();
+  const int m_tiles = (N + BM * cg - 1) / (BM * cg);
+  const int bn = choose_bn(N, B * m_tiles, cg, 64);          // P leaves in 64-column (128 B) TMA-store boxes
+  CUtensorMap ta, tb, tp;
+  if (int e = make_tmap(&ta, w.fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
+  if (int e = make_tmap(&tb, w.fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn / cg)) return e;
+  if (int e = make_tmap(&tp, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
   GemmArgs g;
   std::memset(&g, 0, sizeof(g));
   g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = dk / BK;
-  g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn); g.c = scale * kLog2e;
+  g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = scale * kLog2e;
   if (need_stats) {
     ProfScope ps(PROF_STATS, st);
     g.part = w.part;
-    if (int e = launch_gemm<MODE_STATS>(ta, tb, g, st)) return e;
+    if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;
     combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, g.n_tiles, N, B);
     if (int e = launch_status("combine_stats_kernel")) return e;
   }
   if (want_p || sim_map || kl) {
     g.stats = stats;
-    g.p_out = want_p ? w.p : nullptr;
+    g.store_p = want_p ? 1 : 0;
     g.sim_out = sim_map;
     g.logbin = kl ? w.logbin : nullptr;
     g.lnz = w.lnz;
     g.kl_part = w.kl_part;
     ProfScope ps(PROF_PROBS, st);
-    if (int e = launch_gemm<MODE_PROBS>(ta, tb, g, st)) return e;
+    if (int e = launch_gemm<MODE_PROBS>(ta, tb, tp, g, st, cg)) return e;
   }
   *key_tiles = g.n_tiles;   // callers need it to reduce kl_part
   return 0;
@@ -575,18 +670,19 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
   }
   if (value) {
     // pass 3: O^T[dv, Nq] = V[dv, Nk] * P[Nq, Nk]^T
-    const int m_tiles = dv / BM;
-    const int bn = choose_bn(N, B * m_tiles);
-    CUtensorMap ta, tb;
-    if (int e = make_tmap(&ta, w.vh, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, BM)) return e;
-    if (int e = make_tmap(&tb, w.p, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, bn)) return e;
+    const int cg = cta_group();
+    const int m_tiles = (dv + BM * cg - 1) / (BM * cg);
+    const int bn = choose_bn(N, B * m_tiles, cg, 32);        // O leaves in 32-column (128 B of fp32) TMA-store boxes
+    CUtensorMap ta, tb, to;
+    if (int e = make_tmap(&ta, w.vh, 2, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, BM)) return e;
+    if (int e = make_tmap(&tb, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, bn / cg)) return e;
+    if (int e = make_tmap(&to, ctx, 4, N, dv, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dv) * N * 4, BM)) return e;
     GemmArgs g;
     std::memset(&g, 0, sizeof(g));
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
-    g.m_rows = dv; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn); g.c = 0.f;
-    g.o_out = ctx;
+    g.m_rows = dv; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = 0.f;
     ProfScope ps(PROF_PV, st);
-    if (int e = launch_gemm<MODE_PV>(ta, tb, g, st)) return e;
+    if (int e = launch_gemm<MODE_PV>(ta, tb, to, g, st, cg)) return e;
   }
   return 0;
 }

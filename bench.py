@@ -50,14 +50,14 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -274,7 +274,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
         threads = os.cpu_count() or 1
-        times, d_cpu = cpu_reference_forward(sd, 6, 1, threads)
+        times, d_cpu = cpu_reference_forward(sd, 60, 2, threads)
         out["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "images/s", "cores": threads, "kind": "port",
                                "sample": f"B=1 image x {len(times)} forwards of the same network (oracle port, fp32 torch CPU ops), {sum(times):.1f} s"}
     else:
