@@ -54,7 +54,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2 };
 
 constexpr int kOutChunkBytes = 128 * 128;   // epilogue staging: 128 rows x 128 B (one SWIZZLE_128B TMA-store box)
-constexpr int kOutBuffers = 2;
+constexpr int kOutBuffers = 2;          // TMA-store staging ring (4 buffers measured slower: they cost an operand stage)
 
 struct GemmArgs {
   int batch, m_tiles, n_tiles, k_steps;   // m_tiles counts tiles of 128*CG rows
@@ -64,6 +64,7 @@ struct GemmArgs {
   int stages;
   uint32_t idesc;
   float c;             // scale * log2(e)
+  int skip_epilogue;   // experiments only (ACAN_SKIP_EPI=1): release the accumulator without reading it
   // MODE_STATS
   float2* part;        // [B, n_tiles, m_rows] (m2, l) partials
   // MODE_PROBS
@@ -214,7 +215,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
 
-      if constexpr (MODE == MODE_STATS) {
+      if (g.skip_epilogue) {
+        // nothing: mainloop-only timing experiment
+      } else if constexpr (MODE == MODE_STATS) {
         float m = -INFINITY, l = 0.f;                   // m in raw dot-product units
         for (int ch = 0; ch < chunks; ++ch) {
           float v[32];
@@ -300,7 +303,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
               tma_store_commit();
             }
-            out_buf ^= 1;
+            out_buf = (out_buf + 1) % kOutBuffers;
           }
         }
         if (kl && row_ok) g.kl_part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = kl_acc;
@@ -322,7 +325,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
             tma_store_commit();
           }
-          out_buf ^= 1;
+          out_buf = (out_buf + 1) % kOutBuffers;
         }
       }
 
@@ -475,6 +478,11 @@ int make_tmap(CUtensorMap* m, const void* base, int elem_bytes, int inner, int r
 }
 
 // CTA-pair (cta_group::2) or single-CTA tiles; ACAN_CTA_GROUP=1 forces the single-CTA kernels (A/B measurements)
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 int cta_group() {
   static int cg = 0;
   if (cg == 0) {
@@ -584,7 +592,7 @@ int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map,
                  bool need_stats, int* key_tiles) {
   const int cg = cta_group();
   const int m_tiles = (N + BM * cg - 1) / (BM * cg);
-  const int bn = choose_bn(N, B * m_tiles, cg, 64);          // P leaves in 64-column (128 B) TMA-store boxes
+  const int bn = env_int("ACAN_BN_QK", choose_bn(N, B * m_tiles, cg, 64));   // P leaves in 64-column (128 B) TMA-store boxes
   CUtensorMap ta, tb, tp;
   if (int e = make_tmap(&ta, w.fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
   if (int e = make_tmap(&tb, w.fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn / cg)) return e;
@@ -593,6 +601,7 @@ int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map,
   std::memset(&g, 0, sizeof(g));
   g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = dk / BK;
   g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = scale * kLog2e;
+  g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
   if (need_stats) {
     ProfScope ps(PROF_STATS, st);
     g.part = w.part;
@@ -672,7 +681,7 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
     // pass 3: O^T[dv, Nq] = V[dv, Nk] * P[Nq, Nk]^T
     const int cg = cta_group();
     const int m_tiles = (dv + BM * cg - 1) / (BM * cg);
-    const int bn = choose_bn(N, B * m_tiles, cg, 32);        // O leaves in 32-column (128 B of fp32) TMA-store boxes
+    const int bn = env_int("ACAN_BN_PV", choose_bn(N, B * m_tiles, cg, 32));   // O leaves in 32-column (128 B of fp32) TMA-store boxes
     CUtensorMap ta, tb, to;
     if (int e = make_tmap(&ta, w.vh, 2, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, BM)) return e;
     if (int e = make_tmap(&tb, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, bn / cg)) return e;
@@ -681,6 +690,7 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
     std::memset(&g, 0, sizeof(g));
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
     g.m_rows = dv; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = 0.f;
+    g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
     ProfScope ps(PROF_PV, st);
     if (int e = launch_gemm<MODE_PV>(ta, tb, to, g, st, cg)) return e;
   }

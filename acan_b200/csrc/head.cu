@@ -106,11 +106,13 @@ template <> struct Acc<ACAN_HEAD_CE_HARD> {
 };
 template <> struct Acc<ACAN_HEAD_CE_SOFT> {   // online softmax expectation of the log-depth bin centres
   float m = -INFINITY, z = 0.f, a = 0.f; int arg = 0;
-  float wk = 0.f;
-  __device__ __forceinline__ void feed_w(float v, int k, float w) {
-    if (v > m) { const float c = expf(m - v); z *= c; a *= c; m = v; arg = k; }
-    const float e = expf(v - m);
-    z += e; a += e * w;
+  // raise the running maximum to gm (>= every score of the coming group): ONE rescale per group of channels
+  __device__ __forceinline__ void lift(float gm, int garg) {
+    if (gm > m) { const float c = ex2_approx((m - gm) * 1.4426950408889634f); z *= c; a *= c; m = gm; arg = garg; }
+  }
+  __device__ __forceinline__ void feed_w(float v, int, float w) {
+    const float e = ex2_approx((v - m) * 1.4426950408889634f);
+    z += e; a = fmaf(e, w, a);
   }
   __device__ __forceinline__ float finish(const BinScale&, int& idx) const {
     idx = arg;
@@ -149,6 +151,18 @@ __global__ void __launch_bounds__(kThreads) head_kernel(const float4* __restrict
           if (c0 + u < C) {
             const int k = c0 + u;
             if constexpr (KIND == ACAN_HEAD_CE_SOFT) {
+              if (u == 0) {   // group maximum first (first index on ties), one rescale, then U independent ex2
+                float gx = v[0].x, gy = v[0].y, gz = v[0].z, gw = v[0].w; int ax = c0, ay = c0, az = c0, aw = c0;
+#pragma unroll
+                for (int t = 1; t < U; ++t)
+                  if (c0 + t < C) {
+                    if (v[t].x > gx) { gx = v[t].x; ax = c0 + t; }
+                    if (v[t].y > gy) { gy = v[t].y; ay = c0 + t; }
+                    if (v[t].z > gz) { gz = v[t].z; az = c0 + t; }
+                    if (v[t].w > gw) { gw = v[t].w; aw = c0 + t; }
+                  }
+                acc[0].lift(gx, ax); acc[1].lift(gy, ay); acc[2].lift(gz, az); acc[3].lift(gw, aw);
+              }
               // weight_k = k * log(dmax/dmin) / (K-1) + log(dmin)   (model.py:54-55, fp32 tensor expression)
               const float w = (float)k * bs.c1 / bs.inv_km1_den + bs.c0;
               acc[0].feed_w(v[u].x, k, w); acc[1].feed_w(v[u].y, k, w);
@@ -180,7 +194,9 @@ __global__ void __launch_bounds__(kThreads) head_kernel_scalar(const float* __re
       if constexpr (FROM_LOGITS) {
         acc.feed(ord_prob(src[(int64_t)(2 * k) * hw], src[(int64_t)(2 * k + 1) * hw]), k);
       } else if constexpr (KIND == ACAN_HEAD_CE_SOFT) {
-        acc.feed_w(src[(int64_t)k * hw], k, (float)k * bs.c1 / bs.inv_km1_den + bs.c0);
+        const float v = src[(int64_t)k * hw];
+        acc.lift(v, k);
+        acc.feed_w(v, k, (float)k * bs.c1 / bs.inv_km1_den + bs.c0);
       } else {
         acc.feed(src[(int64_t)k * hw], k);
       }

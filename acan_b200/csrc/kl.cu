@@ -24,6 +24,16 @@ __global__ void nearest_bins_kernel(const float* __restrict__ label, float* __re
   }
 }
 
+__global__ void nearest_logbins_kernel(const float* __restrict__ label, float* __restrict__ logbin, int B, int H, int W) {
+  const int h = H / 8, w = W / 8, N = h * w;
+  const int64_t total = (int64_t)B * N;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(q / N), n = (int)(q - (int64_t)b * N);
+    const float a = label[((int64_t)b * H + 8 * (n / w)) * W + 8 * (n % w)];
+    logbin[q] = a > 0.f ? logf(a) : -INFINITY;
+  }
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {   // all threads get the total; blockDim multiple of 32
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -43,10 +53,8 @@ __device__ __forceinline__ float affinity_ratio(float ai, float aj) {
 namespace {
 constexpr int kThreads = 256;
 
-// MODE 0: write W row.  MODE 1: KL row loss (+ optional gradient w.r.t. sim_map).
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) gt_row_kernel(const float* __restrict__ bins, const float* __restrict__ sim,
-                                                           float* __restrict__ out, float* __restrict__ grad, float grad_scale, int N) {
+// write one row of the target affinity W
+__global__ void __launch_bounds__(kThreads) gt_row_kernel(const float* __restrict__ bins, float* __restrict__ out, int N) {
   __shared__ float red[kThreads / 32];
   const int64_t row = blockIdx.x;                // b*N + i
   const int b = (int)(row / N);
@@ -56,27 +64,48 @@ __global__ void __launch_bounds__(kThreads) gt_row_kernel(const float* __restric
   for (int j = threadIdx.x; j < N; j += kThreads) z += affinity_ratio(ai, a[j]);
   z = block_sum(z, red);
   const float inv_z = z > 0.f ? 1.0f / z : 0.f;
-  if constexpr (MODE == 0) {
-    float* o = out + row * N;
-    for (int j = threadIdx.x; j < N; j += kThreads) o[j] = affinity_ratio(ai, a[j]) * inv_z;
-  } else {
-    const float* q = sim + row * N;
-    float* g = grad ? grad + row * N : nullptr;
-    float acc = 0.f;
-    for (int j = threadIdx.x; j < N; j += kThreads) {
-      const float w = affinity_ratio(ai, a[j]) * inv_z;
-      const float qv = __ldg(q + j);
-      float gv = 0.f;
-      if (w > 0.f) {
-        const float ratio = w / qv;
-        acc += w * logf(fminf(fmaxf(ratio, 1e-8f), 1e8f));
-        if (ratio > 1e-8f && ratio < 1e8f) gv = -ratio * grad_scale;   // d/dq [w log(w/q)] = -w/q
-      }
-      if (g) g[j] = gv;
-    }
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) out[row] = acc;
+  float* o = out + row * N;
+  for (int j = threadIdx.x; j < N; j += kThreads) o[j] = affinity_ratio(ai, a[j]) * inv_z;
+}
+
+// KL row loss (+ optional gradient w.r.t. sim_map) in the log domain: with la = ln(bin) (-inf for bin 0)
+//   ln W_ij = -|la_i - la_j| - ln Z_i,   Z_i = sum_j exp(-|la_i - la_j|),   term = W (clamp(ln W - ln Q, +-ln 1e8))
+// one ex2 + one lg2 per element instead of two divisions and a logf: the pass stays HBM-bound (4*N*N bytes / image).
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f, kLnClamp = 18.420680744f;
+
+__global__ void __launch_bounds__(kThreads) kl_row_kernel(const float* __restrict__ logbin, const float* __restrict__ sim,
+                                                           float* __restrict__ row_loss, float* __restrict__ grad, float grad_scale, int N) {
+  __shared__ float red[kThreads / 32];
+  const int64_t row = blockIdx.x;
+  const int b = (int)(row / N);
+  const float* la = logbin + (int64_t)b * N;
+  const float la_i = la[row - (int64_t)b * N];
+  const float* q = sim + row * N;
+  float* g = grad ? grad + row * N : nullptr;
+  if (!(la_i > -INFINITY)) {                     // bin 0: all-zero target row -> zero loss, zero gradient
+    if (g) for (int j = threadIdx.x; j < N; j += kThreads) g[j] = 0.f;
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    return;
   }
+  float z = 0.f;
+  for (int j = threadIdx.x; j < N; j += kThreads) z += ex2_approx(-fabsf(la_i - la[j]) * kLog2e);   // exp(-inf) = 0 for bin 0
+  z = block_sum(z, red);
+  const float log2_z = lg2_approx(z);            // z >= 1 (the j = i term)
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < N; j += kThreads) {
+    const float l2w = -fabsf(la_i - la[j]) * kLog2e - log2_z;        // log2 W_ij
+    const float w = ex2_approx(l2w);
+    const float qv = __ldg(q + j);
+    float gv = 0.f;
+    if (w > 0.f) {
+      const float lr = (l2w - lg2_approx(qv)) * kLn2;                // ln(W/Q); +inf when Q = 0
+      acc += w * fminf(fmaxf(lr, -kLnClamp), kLnClamp);
+      if (lr > -kLnClamp && lr < kLnClamp) gv = -__fdividef(w, qv) * grad_scale;   // d/dq [w ln(w/q)] = -w/q inside the clamp window
+    }
+    if (g) g[j] = gv;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) row_loss[row] = acc;
 }
 }  // namespace
 
@@ -105,7 +134,7 @@ extern "C" int acan_gt_sim_map(const float* dis_label, float* gt, float* bins_ws
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, bins_ws, B, H, W);
   if (int e = launch_status("acan_gt_sim_map/bins")) return e;
-  gt_row_kernel<0><<<B * N, kThreads, 0, st>>>(bins_ws, nullptr, gt, nullptr, 0.f, N);
+  gt_row_kernel<<<B * N, kThreads, 0, st>>>(bins_ws, gt, N);
   return launch_status("acan_gt_sim_map");
 }
 
@@ -117,11 +146,11 @@ extern "C" int acan_attention_loss(const float* sim_map, const float* dis_label,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope ps(PROF_KL, st);
   float* row_loss = ws;
-  float* bins = ws + (int64_t)B * N;
-  nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, bins, B, H, W);
+  float* logbin = ws + (int64_t)B * N;
+  nearest_logbins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, logbin, B, H, W);
   if (int e = launch_status("acan_attention_loss/bins")) return e;
   const float inv_rows = 1.0f / ((float)B * (float)N);
-  gt_row_kernel<1><<<B * N, kThreads, 0, st>>>(bins, sim_map, row_loss, grad_sim, grad_scale * inv_rows, N);
+  kl_row_kernel<<<B * N, kThreads, 0, st>>>(logbin, sim_map, row_loss, grad_sim, grad_scale * inv_rows, N);
   if (int e = launch_status("acan_attention_loss/rows")) return e;
   ordered_sum_kernel<<<1, 1024, 0, st>>>(row_loss, (int64_t)B * N, inv_rows, loss_out);
   return launch_status("acan_attention_loss/sum");

@@ -45,31 +45,84 @@ __global__ void __launch_bounds__(kThreads) row_mean_kernel(const float* __restr
   }
 }
 
-// out[b,o] = relu(bias[o] + sum_i W[o,i] * in[b,i]);  one warp per o
-__global__ void __launch_bounds__(kThreads) linear_relu_kernel(const float* __restrict__ in, const float* __restrict__ W,
-                                                                const float* __restrict__ bias, float* __restrict__ out,
-                                                                int B, int I, int O) {
+// out[b,o] = relu(bias[o] + sum_i W[o,i] * in[b,i]).  A CTA of 8 warps stages the input rows of up to 16 images in shared
+// memory ONCE (every output neuron needs all of them: re-reading them per neuron made the first version L2-bound at
+// 64 MB of redundant traffic), then each warp streams one weight row from HBM into registers (NI x 16 B per lane, all
+// loads in flight) and dots it with the staged rows.
+constexpr int kLinWarps = 8;
+constexpr int kLinImages = 16;
+
+template <int NI>   // I == NI * 128
+__global__ void __launch_bounds__(kLinWarps * 32) linear_relu_smem_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                                         const float* __restrict__ bias, float* __restrict__ out, int B, int O) {
+  extern __shared__ float4 xin[];                       // [images][I / 4]
+  constexpr int I4 = NI * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * kLinWarps + warp;
+  float4 w[NI];
+  if (o < O) {
+    const float4* w4 = reinterpret_cast<const float4*>(W + (int64_t)o * (I4 * 4));
+#pragma unroll
+    for (int k = 0; k < NI; ++k) w[k] = ldg_stream(w4 + lane + 32 * k);
+  }
+  const float bo = o < O ? bias[o] : 0.f;
+  for (int b0 = 0; b0 < B; b0 += kLinImages) {
+    const int nb = min(kLinImages, B - b0);
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(in + (int64_t)b0 * (I4 * 4));
+    for (int i = threadIdx.x; i < nb * I4; i += kLinWarps * 32) xin[i] = __ldg(src + i);
+    __syncthreads();
+    if (o < O) {
+      for (int b = 0; b < nb; ++b) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < NI; ++k) {
+          const float4 v = xin[b * I4 + lane + 32 * k];
+          acc += w[k].x * v.x + w[k].y * v.y + w[k].z * v.z + w[k].w * v.w;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[(int64_t)(b0 + b) * O + o] = fmaxf(acc + bo, 0.f);
+      }
+    }
+  }
+}
+
+// generic sizes: one warp per o, strided loop
+__global__ void __launch_bounds__(128) linear_relu_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int B, int I, int O) {
   const int lane = threadIdx.x & 31;
-  const int o = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= O) return;
   const float* w = W + (int64_t)o * I;
   const float bo = bias[o];
   for (int b = 0; b < B; ++b) {
     const float* v = in + (int64_t)b * I;
     float acc = 0.f;
-    if ((I & 3) == 0) {
-      const float4* w4 = reinterpret_cast<const float4*>(w);
-      const float4* v4 = reinterpret_cast<const float4*>(v);
-      for (int i = lane; i < (I >> 2); i += 32) {
-        const float4 a = __ldg(w4 + i), c = __ldg(v4 + i);
-        acc += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
-      }
-    } else {
-      for (int i = lane; i < I; i += 32) acc += w[i] * v[i];
-    }
+    for (int i = lane; i < I; i += 32) acc += w[i] * v[i];
     acc = warp_sum(acc);
     if (lane == 0) out[(int64_t)b * O + o] = fmaxf(acc + bo, 0.f);
   }
+}
+
+template <int NI>
+int launch_linear_smem(const float* in, const float* W, const float* bias, float* out, int B, int O, cudaStream_t st, const char* what) {
+  const size_t smem = static_cast<size_t>(B < kLinImages ? B : kLinImages) * NI * 128 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ACAN_CUDA(cudaFuncSetAttribute(linear_relu_smem_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinImages * NI * 128 * 4));
+    attr_set = true;
+  }
+  linear_relu_smem_kernel<NI><<<(O + kLinWarps - 1) / kLinWarps, kLinWarps * 32, smem, st>>>(in, W, bias, out, B, O);
+  return launch_status(what);
+}
+
+int launch_linear(const float* in, const float* W, const float* bias, float* out, int B, int I, int O, cudaStream_t st, const char* what) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+  if (I == 2048 && aligned) return launch_linear_smem<16>(in, W, bias, out, B, O, st, what);
+  if (I == 1024 && aligned) return launch_linear_smem<8>(in, W, bias, out, B, O, st, what);
+  if (I == 512 && aligned) return launch_linear_smem<4>(in, W, bias, out, B, O, st, what);
+  linear_relu_kernel<<<(O + 3) / 4, 128, 0, st>>>(in, W, bias, out, B, I, O);
+  return launch_status(what);
 }
 
 }  // namespace
@@ -90,8 +143,6 @@ extern "C" int acan_pool_branch_fwd(const float* x, const float* keep_mask, cons
   if (blocks > cap) blocks = cap;
   row_mean_kernel<<<(int)blocks, kThreads, 0, st>>>(x, keep_mask, mean_out, rows, N);
   if (int e = launch_status("acan_pool_branch_fwd/mean")) return e;
-  linear_relu_kernel<<<(H1 + kWarps - 1) / kWarps, kThreads, 0, st>>>(mean_out, w1, b1, hidden_out, B, C, H1);
-  if (int e = launch_status("acan_pool_branch_fwd/linear1")) return e;
-  linear_relu_kernel<<<(H2 + kWarps - 1) / kWarps, kThreads, 0, st>>>(hidden_out, w2, b2, g_out, B, H1, H2);
-  return launch_status("acan_pool_branch_fwd/linear2");
+  if (int e = launch_linear(mean_out, w1, b1, hidden_out, B, C, H1, st, "acan_pool_branch_fwd/linear1")) return e;
+  return launch_linear(hidden_out, w2, b2, g_out, B, H1, H2, st, "acan_pool_branch_fwd/linear2");
 }

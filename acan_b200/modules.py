@@ -185,19 +185,21 @@ class PixelAttentionBlock_(nn.Module):
     def key_features(self, x: torch.Tensor) -> torch.Tensor:
         """F = f_key(x), computed ONCE.  The reference evaluates the shared module twice (sadecoder.py:44-45), which
         in train() advances the BN running statistics two momentum steps with the same batch moments and bumps
-        num_batches_tracked by 2; the second step is applied in closed form here:
-        r2 = (1-m) r1 + m mu  with  m mu = r1 - (1-m) r0   =>   r2 = (2-m) r1 - (1-m) r0."""
+        num_batches_tracked by 2.  Two steps with momentum m equal one step with momentum
+        1 - (1-m)^2 = m (2 - m):  r2 = (1-m)^2 r0 + (1 - (1-m)^2) mu  -- applied by running BN once with that
+        momentum (nothing is modified in place after the forward, so autograd's saved buffers stay valid)."""
         bn = self.f_key.bn
         twice = self.training and bn.track_running_stats and bn.momentum is not None
-        if twice:
-            rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
-        feat = self.f_key(x)
-        if twice:
-            m = bn.momentum
-            with torch.no_grad():
-                bn.running_mean.mul_(2.0 - m).sub_(rm0, alpha=1.0 - m)
-                bn.running_var.mul_(2.0 - m).sub_(rv0, alpha=1.0 - m)
-                bn.num_batches_tracked += 1
+        if not twice:
+            return self.f_key(x)
+        m = bn.momentum
+        bn.momentum = m * (2.0 - m)
+        try:
+            feat = self.f_key(x)
+        finally:
+            bn.momentum = m
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
         return feat
 
     def forward_att(self, x):

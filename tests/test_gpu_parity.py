@@ -326,5 +326,10 @@ def test_training_step_gradients_against_oracle():
     sdd = {k: v.double().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     c2, s2, _ = O.self_attention_block(x.double(), sdd, "", training=True)
     ((c2 * go.double()).sum() + O.attention_loss(s2, dis.double())).backward()
+    scale = max(float(sdd[n].grad.abs().max()) for n, _ in blk.named_parameters())
     for name, p in blk.named_parameters():
-        close(p.grad, sdd[name].grad, 5e-3)
+        want = sdd[name].grad
+        if float(want.abs().max()) < 1e-6 * scale:        # analytically zero (a conv bias in front of train-mode BN): absolute check
+            assert float(p.grad.abs().max()) < 1e-4 * scale, name
+        else:
+            close(p.grad, want, 5e-3)
