@@ -32,13 +32,16 @@ SIGNATURES = {
     "acan_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_double, c_double, c_int, c_int, c_void_p]),
     "acan_continuous2discrete": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int, c_void_p]),
     "acan_pool_branch_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
+    "acan_pool_nhwc_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
+    "acan_pool_branch_fwd_nhwc": (c_int, [c_void_p, c_int] + [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "acan_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "acan_attn_fwd": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_loss": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
-    "acan_attn_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
+    "acan_attn_fwd_nhwc_f16": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
+    "acan_attn_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attention_loss": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_int, c_void_p]),
     "acan_gt_sim_map": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "acan_attention_loss_fused": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p]),
+    "acan_attention_loss_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p]),
 }
 
 _lib = None

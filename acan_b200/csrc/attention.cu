@@ -51,7 +51,9 @@ constexpr int kSmemBudget = 200 * 1024; // operand ring; barriers + alignment sl
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2 };
+// MODE_PV : O^T[dv, Nq] = V[dv, Nk] P[Nq, Nk]^T, both K-major (NCHW world), fp32 out.
+// MODE_PVT: O[Nq, dv]  = P[Nq, Nk] V[Nk, dv], B = V read in place from channels-last memory as an MN-major operand, fp16 out.
+enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2, MODE_PVT = 3 };
 
 constexpr int kOutChunkBytes = 128 * 128;   // epilogue staging: 128 rows x 128 B (one SWIZZLE_128B TMA-store box)
 constexpr int kOutBuffers = 2;          // TMA-store staging ring (4 buffers measured slower: they cost an operand stage)
@@ -152,13 +154,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (CG == 1) {
             mbar_expect_tx(&bars->full[stage], stage_bytes);
             tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, a_row, b);
-            tma_load_3d(sa + a_bytes, &tmap_b, &bars->full[stage], ks * BK, b_row, b);
+            if constexpr (MODE == MODE_PVT) {      // MN-major B: one {64 channels x 64 keys} box per 64 channels
+              for (uint32_t s = 0; s < b_rows / 64; ++s)
+                tma_load_3d(sa + a_bytes + s * 8192, &tmap_b, &bars->full[stage], b_row + static_cast<int>(s) * 64, ks * BK, b);
+            } else {
+              tma_load_3d(sa + a_bytes, &tmap_b, &bars->full[stage], ks * BK, b_row, b);
+            }
           } else {
             // both CTAs' bytes complete on the LEADER's barrier; the leader arms it for the pair's total
             if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], stage_bytes * 2);
             const uint32_t leader_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
             tma_load_3d_2sm(sa, &tmap_a, leader_bar, ks * BK, a_row, b);
-            tma_load_3d_2sm(sa + a_bytes, &tmap_b, leader_bar, ks * BK, b_row, b);
+            if constexpr (MODE == MODE_PVT) {
+              for (uint32_t s = 0; s < b_rows / 64; ++s)
+                tma_load_3d_2sm(sa + a_bytes + s * 8192, &tmap_b, leader_bar, b_row + static_cast<int>(s) * 64, ks * BK, b);
+            } else {
+              tma_load_3d_2sm(sa + a_bytes, &tmap_b, leader_bar, ks * BK, b_row, b);
+            }
           }
           if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
         }
@@ -179,7 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_k_sw128(sa + k * UMMA_K * 2), db = umma_desc_k_sw128(sb + k * UMMA_K * 2);
+            const uint64_t da = umma_desc_k_sw128(sa + k * UMMA_K * 2);
+            const uint64_t db = (MODE == MODE_PVT) ? umma_desc_mn_sw128(sb + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sb + k * UMMA_K * 2);
             if (CG == 1) umma_f16(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
             else         umma_f16_2sm(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
           }
@@ -307,6 +320,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
         if (kl && row_ok) g.kl_part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = kl_acc;
+      } else if constexpr (MODE == MODE_PVT) {   // rows = query positions, columns = value channels; 64 fp16 columns per staged store
+        for (int ch = 0; ch < chunks; ch += 2) {
+          uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
+          if (store_leader) tma_store_wait_read<kOutBuffers - 1>();
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (ch + half < chunks) {
+              float v[32];
+              tmem_ld_32x32(taddr + (ch + half) * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *staged_chunk(buf, row_in_tile, half * 4 + q) =
+                    make_uint4(pack_half2(v[q * 8 + 0], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                               pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (store_leader) {
+            tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
+            tma_store_commit();
+          }
+          out_buf = (out_buf + 1) % kOutBuffers;
+        }
       } else {  // MODE_PV: rows = value channels, columns = query positions; 32 fp32 columns (128 B) per staged store
         for (int ch = 0; ch < chunks; ++ch) {
           uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
@@ -497,11 +536,11 @@ int cta_group() {
 //   feed  : (16 KB of A + bn/cg rows x 128 B of B) at ~51 B/cycle/SM, the L2 -> SM rate both the bn = 160 (59 % of
 //           peak) and bn = 256 (80 %) measurements of the aggregation pass fit (profiles/r01_notes.md)
 // and the pass costs (waves over the 148 / cg tile slots) x that.  Wide tiles win unless they quantise badly.
-int choose_bn(int n_cols, int other_tiles, int cg, int step) {
-  int best = kMinBN;
+int choose_bn(int n_cols, int other_tiles, int cg, int step, int start = kMinBN) {
+  int best = start;
   double best_cost = 1e30;
   const int slots = kNumSMs / cg;
-  for (int bn = kMinBN; bn <= kMaxBN; bn += step) {
+  for (int bn = start; bn <= kMaxBN; bn += step) {
     const int nt = (n_cols + bn - 1) / bn;
     const long tiles = static_cast<long>(nt) * other_tiles;
     const long waves = (tiles + slots - 1) / slots;
@@ -588,14 +627,14 @@ int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
 }
 
 // passes 1+2 over S = Fh Fh^T: statistics, then probabilities / sim_map / fused KL
-int run_affinity(const Workspace& w, float2* stats, bool want_p, float* sim_map, bool kl, int B, int N, int dk, float scale, cudaStream_t st,
+int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_p, float* sim_map, bool kl, int B, int N, int dk, float scale, cudaStream_t st,
                  bool need_stats, int* key_tiles) {
   const int cg = cta_group();
   const int m_tiles = (N + BM * cg - 1) / (BM * cg);
   const int bn = env_int("ACAN_BN_QK", choose_bn(N, B * m_tiles, cg, 64));   // P leaves in 64-column (128 B) TMA-store boxes
   CUtensorMap ta, tb, tp;
-  if (int e = make_tmap(&ta, w.fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
-  if (int e = make_tmap(&tb, w.fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn / cg)) return e;
+  if (int e = make_tmap(&ta, fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
+  if (int e = make_tmap(&tb, fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn / cg)) return e;
   if (int e = make_tmap(&tp, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
   GemmArgs g;
   std::memset(&g, 0, sizeof(g));
@@ -671,7 +710,7 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
 
   int nt = 0;
-  if (int e = run_affinity(w, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  if (int e = run_affinity(w, w.fh, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
   ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
   if (dis_label) {
     ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
@@ -709,17 +748,65 @@ extern "C" int acan_attn_fwd_loss(const float* feat, const float* value, float* 
   return attn_forward_impl(feat, value, ctx, sim_map, row_stats, dis_label, H, W, loss_out, workspace, workspace_bytes, B, N, dk, dv, scale, stream);
 }
 
-extern "C" int acan_attn_rows(const void* workspace, const int* row_idx_dev, int n_rows, float* rows_out,
+// channels-last fp16 form: F and V are consumed where the convolutions left them, O is written channels-last fp16
+extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h, float* sim_map, float* row_stats,
+                                      const float* dis_label, int H, int Wd, float* loss_out,
+                                      void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(feat_h && row_stats && workspace, "acan_attn_fwd_nhwc_f16: null pointer");
+  ACAN_CHECK_ARG((value_h == nullptr) == (ctx_h == nullptr), "acan_attn_fwd_nhwc_f16: value and ctx must be given together");
+  if (int e = check_attn_shape("acan_attn_fwd_nhwc_f16", B, N, dk, value_h ? dv : 0)) return e;
+  ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N), "acan_attn_fwd_nhwc_f16: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0 && reinterpret_cast<uintptr_t>(feat_h) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(value_h) % 16 == 0 && reinterpret_cast<uintptr_t>(ctx_h) % 16 == 0,
+                 "acan_attn_fwd_nhwc_f16: workspace must be 1024-byte, tensors 16-byte aligned");
+  const Workspace w = carve(workspace, B, N, dk, dv);
+  if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_fwd_nhwc_f16: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+  if (int e = acan_device_check()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* stats = reinterpret_cast<float2*>(row_stats);
+  const __half* fh = static_cast<const __half*>(feat_h);
+  if (dis_label)
+    if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
+  int nt = 0;
+  if (int e = run_affinity(w, fh, stats, value_h != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
+  if (dis_label) {
+    ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
+    if (int e = launch_status("ordered_sum_kernel")) return e;
+  }
+  if (value_h) {
+    // O[Nq, dv] = P[Nq, Nk] * V[Nk, dv]: A = P (K-major), B = V in place (MN-major: channels contiguous)
+    const int cg = cta_group();
+    const int m_tiles = (N + BM * cg - 1) / (BM * cg);
+    const int bn = env_int("ACAN_BN_PV", choose_bn(dv, B * m_tiles, cg, 64 * cg, 64 * cg));   // 64-channel boxes per CTA
+    ACAN_CHECK_ARG(dv % 64 == 0 && bn % (64 * cg) == 0, "acan_attn_fwd_nhwc_f16: dv=%d / tile width %d not a multiple of 64 per CTA", dv, bn);
+    CUtensorMap ta, tb, to;
+    if (int e = make_tmap(&ta, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
+    if (int e = make_tmap(&tb, value_h, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, 64)) return e;
+    if (int e = make_tmap(&to, ctx_h, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, BM)) return e;
+    GemmArgs g;
+    std::memset(&g, 0, sizeof(g));
+    g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (dv + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
+    g.m_rows = N; g.n_cols = dv; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg, true); g.c = 0.f;
+    g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
+    ProfScope ps(PROF_PV, st);
+    if (int e = launch_gemm<MODE_PVT>(ta, tb, to, g, st, cg)) return e;
+  }
+  return 0;
+}
+
+extern "C" int acan_attn_rows(const void* workspace, const void* feat_pack, const int* row_idx_dev, int n_rows, float* rows_out,
                               int B, int N, int dk, int dv, float scale, void* stream) {
   ACAN_CHECK_ARG(workspace && row_idx_dev && rows_out && n_rows > 0, "acan_attn_rows: bad argument");
   if (int e = check_attn_shape("acan_attn_rows", B, N, dk, dv)) return e;
   const Workspace w = carve(const_cast<void*>(workspace), B, N, dk, dv);
-  sim_rows_kernel<<<dim3(n_rows, B), 256, dk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(w.fh, w.stats, row_idx_dev, rows_out, n_rows, N, dk,
+  const __half* fh = feat_pack ? static_cast<const __half*>(feat_pack) : w.fh;
+  sim_rows_kernel<<<dim3(n_rows, B), 256, dk * sizeof(float), static_cast<cudaStream_t>(stream)>>>(fh, w.stats, row_idx_dev, rows_out, n_rows, N, dk,
                                                                                                   scale * kLog2e);
   return launch_status("sim_rows_kernel");
 }
 
-extern "C" int acan_attention_loss_fused(void* workspace, const float* dis_label, float* loss_out,
+extern "C" int acan_attention_loss_fused(void* workspace, const void* feat_pack, const float* dis_label, float* loss_out,
                                          int B, int H, int W, int dk, int dv, float scale, void* stream) {
   ACAN_CHECK_ARG(workspace && dis_label && loss_out && H >= 8 && W >= 8, "acan_attention_loss_fused: bad argument");
   const int N = (H / 8) * (W / 8);
@@ -728,7 +815,8 @@ extern "C" int acan_attention_loss_fused(void* workspace, const float* dis_label
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = prepare_target(w, dis_label, B, H, W, st)) return e;
   int nt = 0;
-  if (int e = run_affinity(w, w.stats, false, nullptr, true, B, N, dk, scale, st, false, &nt)) return e;
+  const __half* fh = feat_pack ? static_cast<const __half*>(feat_pack) : w.fh;
+  if (int e = run_affinity(w, fh, w.stats, false, nullptr, true, B, N, dk, scale, st, false, &nt)) return e;
   ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
   return launch_status("ordered_sum_kernel");
 }

@@ -249,11 +249,25 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: fp16 A/B (K-major both), fp32 accumulate, M = 128, N = n
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128) {
+// MN-major, SWIZZLE_128B operand: the tile is stored as [K rows][64 MN elements = 128 B] blocks (what a TMA box of
+// {64 elements along MN, R rows along K} writes); `lbo_bytes` = distance between consecutive 64-element MN blocks,
+// 8-row K groups are 1024 B apart.  Stepping K by 16 adds 16 * 128 B to the start address.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // leading byte offset: next 64-element MN block
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // stride byte offset: next 8 K rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp16 A/B, fp32 accumulate, M = m, N = n; A K-major, B K-major or MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128, bool b_mn_major = false) {
   return (1u << 4)                               // c_format = F32
        | (0u << 7) | (0u << 10)                  // a_format = b_format = F16
-       | (0u << 15) | (0u << 16)                 // a_major = b_major = K
+       | (0u << 15)                              // a_major = K
+       | ((b_mn_major ? 1u : 0u) << 16)          // b_major
        | (static_cast<uint32_t>(n >> 3) << 17)   // n_dim
        | (static_cast<uint32_t>(m >> 4) << 24);  // m_dim
 }

@@ -125,6 +125,71 @@ int launch_linear(const float* in, const float* W, const float* bias, float* out
   return launch_status(what);
 }
 
+// ---- channels-last half-precision input: x [B, N, C] fp16 / bf16 (what a channels_last autocast pipeline holds).
+// Column sums: a thread owns 8 adjacent channels (one 16 B load per row), a CTA a slab of kSlabRows rows; slab partials
+// go to scratch and are reduced in a fixed order (bit-reproducible, no atomics).  Algorithmic bytes B*N*C*2.
+constexpr int kSlabRows = 32;
+
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (BF16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    } else {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      const float2 t = __half22float2(h);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) slab_colsum_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int N, int C8, int slabs) {
+  const int c8 = blockIdx.x * 256 + threadIdx.x;
+  const int slab = blockIdx.y, b = blockIdx.z;
+  if (c8 >= C8) return;
+  const int r0 = slab * kSlabRows, r1 = min(N, r0 + kSlabRows);
+  const uint4* src = x + (static_cast<int64_t>(b) * N + r0) * C8 + c8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {                       // 4 independent 16 B loads in flight
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(src + static_cast<int64_t>(r - r0 + k) * C8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8<BF16>(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+  }
+  for (; r < r1; ++r) {
+    float f[8];
+    unpack8<BF16>(__ldg(src + static_cast<int64_t>(r - r0) * C8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+  float4* dst = reinterpret_cast<float4*>(partial + ((static_cast<int64_t>(b) * slabs + slab) * C8 + c8) * 8);
+  dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+__global__ void __launch_bounds__(256) slab_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ keep,
+                                                           float* __restrict__ mean, int C, int slabs, int N, int64_t total) {
+  for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
+    const int64_t b = q / C, c = q - b * C;
+    float s = 0.f;
+    for (int t = 0; t < slabs; ++t) s += partial[(b * slabs + t) * C + c];
+    float m = s / static_cast<float>(N);
+    if (keep != nullptr) m *= keep[q] * 2.0f;
+    mean[q] = m;
+  }
+}
+
 }  // namespace
 }  // namespace acan
 
@@ -145,4 +210,30 @@ extern "C" int acan_pool_branch_fwd(const float* x, const float* keep_mask, cons
   if (int e = launch_status("acan_pool_branch_fwd/mean")) return e;
   if (int e = launch_linear(mean_out, w1, b1, hidden_out, B, C, H1, st, "acan_pool_branch_fwd/linear1")) return e;
   return launch_linear(hidden_out, w2, b2, g_out, B, H1, H2, st, "acan_pool_branch_fwd/linear2");
+}
+
+extern "C" size_t acan_pool_nhwc_scratch_floats(int B, int C, int N) {
+  if (B <= 0 || C <= 0 || N <= 0) return 0;
+  return static_cast<size_t>(B) * ((N + kSlabRows - 1) / kSlabRows) * C;
+}
+
+extern "C" int acan_pool_branch_fwd_nhwc(const void* x, int x_dtype, const float* keep_mask, const float* w1, const float* b1,
+                                         const float* w2, const float* b2, float* scratch, float* mean_out, float* hidden_out, float* g_out,
+                                         int B, int C, int N, int H1, int H2, void* stream) {
+  ACAN_CHECK_ARG(x && w1 && b1 && w2 && b2 && scratch && mean_out && hidden_out && g_out, "acan_pool_branch_fwd_nhwc: null pointer");
+  ACAN_CHECK_ARG(B > 0 && C > 0 && (C % 8) == 0 && N > 0 && H1 > 0 && H2 > 0, "acan_pool_branch_fwd_nhwc: sizes must be positive, C a multiple of 8");
+  ACAN_CHECK_ARG(x_dtype == 1 || x_dtype == 2, "acan_pool_branch_fwd_nhwc: x_dtype must be 1 (fp16) or 2 (bf16)");
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(scratch) % 16 == 0, "acan_pool_branch_fwd_nhwc: 16-byte alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PROF_POOL, st);
+  const int slabs = (N + kSlabRows - 1) / kSlabRows, C8 = C / 8;
+  const dim3 grid((C8 + 255) / 256, slabs, B);
+  if (x_dtype == 2) slab_colsum_kernel<true><<<grid, 256, 0, st>>>(static_cast<const uint4*>(x), scratch, N, C8, slabs);
+  else              slab_colsum_kernel<false><<<grid, 256, 0, st>>>(static_cast<const uint4*>(x), scratch, N, C8, slabs);
+  if (int e = launch_status("acan_pool_branch_fwd_nhwc/colsum")) return e;
+  const int64_t total = static_cast<int64_t>(B) * C;
+  slab_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(scratch, keep_mask, mean_out, C, slabs, N, total);
+  if (int e = launch_status("acan_pool_branch_fwd_nhwc/reduce")) return e;
+  if (int e = launch_linear(mean_out, w1, b1, hidden_out, B, C, H1, st, "acan_pool_branch_fwd_nhwc/linear1")) return e;
+  return launch_linear(hidden_out, w2, b2, g_out, B, H1, H2, st, "acan_pool_branch_fwd_nhwc/linear2");
 }

@@ -111,7 +111,7 @@ class SimMap(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat):
         ctx.save_for_backward(feat)
-        sim = ops.attention_forward(feat, None, want_sim_map=True)["sim_map"]
+        sim = ops.attention_forward(feat.float(), None, want_sim_map=True)["sim_map"]
         ctx.sim = sim
         return sim
 

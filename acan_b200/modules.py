@@ -277,10 +277,41 @@ class SADecoder(nn.Module):
         ones = torch.ones(b, c, 1, 1, device=device)
         return (F.dropout2d(ones, drop.p, True) > 0).view(b, c).float()
 
+    def _forward_half_inference(self, x):
+        """Inference on a half-precision channels_last feature map (autocast pipelines): F, V and x are consumed in place
+        by the channels-last kernels (no pack, no fp32 copies), ctx comes back fp16 channels_last for the merge GEMM."""
+        b = x.shape[0]
+        sa = self.saconv
+        with torch.autocast("cuda", dtype=torch.float16):
+            feat = sa.key_features(x)
+            value = sa.f_value(x)
+        out = ops.attention_forward_cl(feat, value, ws=sa._holder.ws)
+        sa._holder.ws = out["ws"]
+        sa._holder.row_stats = out["row_stats"]
+        sa._holder.gen += 1
+        self.sim_map = LazySimMap(feat, sa._holder)
+        ic, mg, dv = self.image_context, self.merge, self.value_channels
+        _, _, g = ops.pool_branch_cl(x, ic.linear1.weight, ic.linear1.bias, ic.linear2.weight, ic.linear2.bias, None)
+        w = mg.conv1.weight.view(mg.conv1.out_channels, -1)
+        bias = F.linear(g, w[:, dv:].float(), mg.conv1.bias.float())
+        y = F.conv2d(out["ctx"], self._ctx_weight_half(w, dv)) + bias.to(out["ctx"].dtype).view(b, -1, 1, 1)
+        return torch.relu_(y), self.sim_map
+
+    def _ctx_weight_half(self, w2d: torch.Tensor, dv: int) -> torch.Tensor:
+        """fp16 channels_last copy of W[:, :dv], cached until the parameter changes."""
+        key = (self.merge.conv1.weight._version, self.merge.conv1.weight.data_ptr())
+        if getattr(self, "_wctx_cache", (None, None))[0] != key:
+            wh = w2d[:, :dv].detach().to(torch.float16).reshape(w2d.shape[0], dv, 1, 1).contiguous(memory_format=torch.channels_last)
+            self._wctx_cache = (key, wh)
+        return self._wctx_cache[1]
+
     def forward(self, x):
         b = x.shape[0]
         if tuple(x.shape[2:]) != self.hw:
             raise RuntimeError(f"SADecoder built for a {self.hw} feature map, got {tuple(x.shape[2:])} (sadecoder.py:98,106)")
+        if (not self.training and not torch.is_grad_enabled() and x.dtype in (torch.float16, torch.bfloat16)
+                and self.saconv.lazy_sim_map and self.value_channels % 128 == 0):
+            return self._forward_half_inference(x)
         context, sim_map = self.saconv(x)
         self.sim_map = sim_map
         # image-level pooling branch: mean -> dropout -> MLP, never broadcast (sadecoder.py:97-106)

@@ -88,6 +88,27 @@ def pool_branch(x: torch.Tensor, w1, b1, w2, b2, keep_mask: Optional[torch.Tenso
     return mean, hid, g
 
 
+def pool_branch_cl(x: torch.Tensor, w1, b1, w2, b2, keep_mask: Optional[torch.Tensor] = None):
+    """pool_branch for a half-precision (fp16 / bf16) feature map held in channels_last memory: read in place."""
+    if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
+        raise _lib.AcanLibraryError("pool_branch_cl wants a CUDA fp16 / bf16 tensor")
+    xx = x.permute(0, 2, 3, 1).contiguous()          # no-op for channels_last input
+    b, h, w, c = xx.shape
+    w1, b1, w2, b2 = (_cuda_f32(t, "pool weight") for t in (w1, b1, w2, b2))
+    h1, h2 = w1.shape[0], w2.shape[0]
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.acan_pool_nhwc_scratch_floats(b, c, h * w)), device=xx.device, dtype=torch.float32)
+    mean = torch.empty((b, c), device=xx.device, dtype=torch.float32)
+    hid = torch.empty((b, h1), device=xx.device, dtype=torch.float32)
+    g = torch.empty((b, h2), device=xx.device, dtype=torch.float32)
+    km = _cuda_f32(keep_mask, "keep_mask") if keep_mask is not None else None
+    with torch.cuda.device(xx.device):
+        _lib.check(lib.acan_pool_branch_fwd_nhwc(xx.data_ptr(), 1 if xx.dtype == torch.float16 else 2, _lib.ptr(km), w1.data_ptr(), b1.data_ptr(),
+                                                 w2.data_ptr(), b2.data_ptr(), scratch.data_ptr(), mean.data_ptr(), hid.data_ptr(), g.data_ptr(),
+                                                 b, c, h * w, h1, h2, _lib.current_stream()), "acan_pool_branch_fwd_nhwc")
+    return mean, hid, g
+
+
 # ------------------------------------------------------------------------------------ attention
 
 class AttnWorkspace:
@@ -102,6 +123,7 @@ class AttnWorkspace:
         base = self._buf.data_ptr()
         self.ptr = (base + 1023) // 1024 * 1024
         self.scale = None
+        self.feat_pack = None     # channels-last fp16 F of the last forward when it was consumed in place (kept alive here)
 
 
 def attention_forward(feat: torch.Tensor, value: Optional[torch.Tensor], want_sim_map: bool = False,
@@ -132,7 +154,44 @@ def attention_forward(feat: torch.Tensor, value: Optional[torch.Tensor], want_si
             loss = torch.empty((), device=f.device, dtype=torch.float32)
             _lib.check(lib.acan_attn_fwd_loss(f.data_ptr(), _lib.ptr(v), _lib.ptr(ctx), _lib.ptr(sim), stats.data_ptr(), lab.data_ptr(), hh, ww,
                                               loss.data_ptr(), ws.ptr, ws.bytes, b, n, dk, dv, scale, st), "acan_attn_fwd_loss")
+    ws.feat_pack = None
     return {"ctx": ctx, "sim_map": sim, "row_stats": stats, "loss": loss, "ws": ws}
+
+
+def _nhwc_half(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[B,C,h,w] (any layout / float dtype) -> dense [B,h,w,C] fp16; a no-op view for fp16 channels_last input."""
+    if not t.is_cuda:
+        raise _lib.AcanLibraryError(f"{name} must be a CUDA tensor: acan_b200 has no CPU path")
+    t = t.permute(0, 2, 3, 1)
+    if t.dtype != torch.float16:
+        t = t.to(torch.float16)
+    return t.contiguous()
+
+
+def attention_forward_cl(feat: torch.Tensor, value: Optional[torch.Tensor], want_sim_map: bool = False,
+                         dis_label: Optional[torch.Tensor] = None, ws: Optional[AttnWorkspace] = None):
+    """Channels-last half-precision attention: feat [B,dk,h,w] / value [B,dv,h,w] as the convolutions left them
+    (fp16, channels_last memory -> consumed in place, no pack); ctx comes back [B,dv,h,w] fp16 channels_last."""
+    f = _nhwc_half(feat, "feat")
+    b, h, w, dk = f.shape
+    n = h * w
+    v = _nhwc_half(value, "value") if value is not None else None
+    dv = v.shape[3] if v is not None else 0
+    if ws is None or ws.shape != (b, n, dk, dv) or ws._buf.device != f.device:
+        ws = AttnWorkspace(b, n, dk, dv, f.device)
+    scale = float(dk) ** -0.5
+    ws.scale = scale
+    ctx = torch.empty((b, h, w, dv), device=f.device, dtype=torch.float16) if v is not None else None
+    sim = torch.empty((b, n, n), device=f.device, dtype=torch.float32) if want_sim_map else None
+    stats = torch.empty((b, n, 2), device=f.device, dtype=torch.float32)
+    lab = _cuda_f32(dis_label, "dis_label") if dis_label is not None else None
+    hh, ww = (lab.shape[-2:] if lab is not None else (0, 0))
+    loss = torch.empty((), device=f.device, dtype=torch.float32) if lab is not None else None
+    with torch.cuda.device(f.device):
+        _lib.check(_lib.load().acan_attn_fwd_nhwc_f16(f.data_ptr(), _lib.ptr(v), _lib.ptr(ctx), _lib.ptr(sim), stats.data_ptr(), _lib.ptr(lab), hh, ww,
+                                                      _lib.ptr(loss), ws.ptr, ws.bytes, b, n, dk, dv, scale, _lib.current_stream()), "acan_attn_fwd_nhwc_f16")
+    ws.feat_pack = f
+    return {"ctx": ctx.permute(0, 3, 1, 2) if ctx is not None else None, "sim_map": sim, "row_stats": stats, "loss": loss, "ws": ws}
 
 
 def attention_rows(ws: AttnWorkspace, rows: torch.Tensor) -> torch.Tensor:
@@ -141,7 +200,7 @@ def attention_rows(ws: AttnWorkspace, rows: torch.Tensor) -> torch.Tensor:
     idx = rows.to(device=ws._buf.device, dtype=torch.int32).contiguous()
     out = torch.empty((b, idx.numel(), n), device=ws._buf.device, dtype=torch.float32)
     with torch.cuda.device(ws._buf.device):
-        _lib.check(_lib.load().acan_attn_rows(ws.ptr, idx.data_ptr(), idx.numel(), out.data_ptr(), b, n, dk, dv, ws.scale, _lib.current_stream()),
+        _lib.check(_lib.load().acan_attn_rows(ws.ptr, _lib.ptr(ws.feat_pack), idx.data_ptr(), idx.numel(), out.data_ptr(), b, n, dk, dv, ws.scale, _lib.current_stream()),
                    "acan_attn_rows")
     return out
 
@@ -152,7 +211,7 @@ def attention_loss_fused(ws: AttnWorkspace, dis_label: torch.Tensor) -> torch.Te
     hh, ww = lab.shape[-2:]
     loss = torch.empty((), device=lab.device, dtype=torch.float32)
     with torch.cuda.device(lab.device):
-        _lib.check(_lib.load().acan_attention_loss_fused(ws.ptr, lab.data_ptr(), loss.data_ptr(), b, hh, ww, dk, dv, ws.scale, _lib.current_stream()),
+        _lib.check(_lib.load().acan_attention_loss_fused(ws.ptr, _lib.ptr(ws.feat_pack), lab.data_ptr(), loss.data_ptr(), b, hh, ww, dk, dv, ws.scale, _lib.current_stream()),
                    "acan_attention_loss_fused")
     return loss
 

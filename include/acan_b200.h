@@ -91,6 +91,14 @@ int acan_pool_branch_fwd(const float* x, const float* keep_mask,
                          float* mean_out, float* hidden_out, float* g_out,
                          int B, int C, int N, int H1, int H2, void* stream);
 
+/* The same for a channels-last half-precision feature map: x [B,N,C] fp16 (x_dtype 1) or bf16 (x_dtype 2), C % 8 == 0.
+ * scratch: acan_pool_nhwc_scratch_floats(B, C, N) floats (slab partial sums, reduced in a fixed order). */
+size_t acan_pool_nhwc_scratch_floats(int B, int C, int N);
+int acan_pool_branch_fwd_nhwc(const void* x, int x_dtype, const float* keep_mask,
+                              const float* w1, const float* b1, const float* w2, const float* b2,
+                              float* scratch, float* mean_out, float* hidden_out, float* g_out,
+                              int B, int C, int N, int H1, int H2, void* stream);
+
 /* ---------------------------------------------------------------- attention ----------- */
 
 /* Bytes of scratch the attention entry points need for (B, N, dk, dv).  The workspace must be 1024-byte
@@ -119,10 +127,22 @@ int acan_attn_fwd_loss(const float* feat, const float* value, float* ctx, float*
                        void* workspace, size_t workspace_bytes,
                        int B, int N, int dk, int dv, float scale, void* stream);
 
+/* Channels-last half-precision form of the two calls above, for pipelines whose convolutions already emit fp16 in
+ * channels_last memory: nothing is packed or transposed.
+ *   feat_h  [B,N,dk] fp16 (f_key output, NHWC)   -- is the K-major operand of S as it stands
+ *   value_h [B,N,dv] fp16 (f_value output, NHWC) -- read in place as an MN-major tensor-core operand; NULL = affinity only
+ *   ctx_h   [B,N,dv] fp16 (NHWC)
+ *   dis_label / loss_out: NULL, or as in acan_attn_fwd_loss.   Requires dv % 128 == 0. */
+int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h, float* sim_map, float* row_stats,
+                           const float* dis_label, int H, int W, float* loss_out,
+                           void* workspace, size_t workspace_bytes,
+                           int B, int N, int dk, int dv, float scale, void* stream);
+
 /* Selected rows of sim_map (vis_utils.py:107-121 reads rows N/4, N/2, 3N/4 only):
  *   rows_out [B, n_rows, N] fp32 for row indices row_idx[0..n_rows) (int32, device).
- * Needs the workspace left by a preceding acan_attn_fwd with the same (B, N, dk, dv). */
-int acan_attn_rows(const void* workspace, const int* row_idx, int n_rows, float* rows_out,
+ * Needs the workspace left by a preceding forward with the same (B, N, dk, dv); feat_pack = NULL after
+ * acan_attn_fwd (the pack lives in the workspace), = the feat_h pointer after acan_attn_fwd_nhwc_f16. */
+int acan_attn_rows(const void* workspace, const void* feat_pack, const int* row_idx, int n_rows, float* rows_out,
                    int B, int N, int dk, int dv, float scale, void* stream);
 
 /* ---------------------------------------------------------------- attention loss ------ */
@@ -142,8 +162,9 @@ int acan_gt_sim_map(const float* dis_label, float* gt, float* bins_ws, int B, in
 
 /* Fused, streamed form on its own: the loss straight from the fp16 operand pack and row statistics an
  * acan_attn_fwd call left in `workspace` -- sim_map is recomputed tile by tile on the tensor cores and
- * never touches HBM.  Same value as acan_attention_loss(sim_map) up to fp16-operand rounding of S. */
-int acan_attention_loss_fused(void* workspace, const float* dis_label, float* loss_out,
+ * never touches HBM.  Same value as acan_attention_loss(sim_map) up to fp16-operand rounding of S.
+ * feat_pack: as for acan_attn_rows. */
+int acan_attention_loss_fused(void* workspace, const void* feat_pack, const float* dis_label, float* loss_out,
                               int B, int H, int W, int dk, int dv, float scale, void* stream);
 
 #ifdef __cplusplus

@@ -219,6 +219,47 @@ def _attn_case(B, h, w, dk, dv, label=False, time_it=False):
             print(f"      {ev.key[:70]:70s} n={ev.count:3d} avg {ev.device_time_total/max(ev.count,1):9.1f} us")
 
 
+def _attn_cl_case(B, h, w, dk=512, dv=2048, time_it=False):
+    import torch
+    from acan_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(B * 1000 + h * w)
+    n = h * w
+    f = torch.relu(torch.randn(B, dk, h, w, device=dev)).half().contiguous(memory_format=torch.channels_last)
+    v = torch.relu(torch.randn(B, dv, h, w, device=dev)).half().contiguous(memory_format=torch.channels_last)
+    out = ops.attention_forward_cl(f, v, want_sim_map=True)
+    torch.cuda.synchronize()
+    S, P, Oref = _attn_reference(f.float(), v.float(), fp16_operands=False)
+    print(f"attn channels-last B={B} N={n}: ctx is channels_last {out['ctx'].is_contiguous(memory_format=torch.channels_last)} dtype {out['ctx'].dtype}")
+    _diag("sim_map vs fp64", out["sim_map"], P)
+    _diag("ctx vs fp64    ", out["ctx"].float().reshape(B, dv, n), Oref)
+    ref = ops.attention_forward(f.float(), v.float())
+    _diag("ctx vs NCHW fp32-ABI kernel", out["ctx"].float().reshape(B, dv, n), ref["ctx"].reshape(B, dv, n).double())
+    if time_it:
+        import ctypes
+        from acan_b200 import _lib
+        ws = out["ws"]
+        for _ in range(3):
+            ops.attention_forward_cl(f, v, ws=ws)
+        lib = _lib.load()
+        lib.acan_profile_begin(200)
+        for _ in range(20):
+            ops.attention_forward_cl(f, v, ws=ws)
+        ms = (ctypes.c_float * 7)(); cnt = (ctypes.c_int * 7)()
+        lib.acan_profile_end(ms, cnt)
+        us = [ms[k] / max(cnt[k], 1) * 1e3 for k in range(4)]
+        print(f"   stats {us[1]:.1f} us probs {us[2]:.1f} us pv {us[3]:.1f} us total {sum(us):.1f} us -> {B*5120.0*n*n/sum(us)/1e6:.0f} TFLOP/s algorithmic")
+
+
+def stage_attn_cl():
+    _attn_cl_case(1, 8, 16, 64, 128)
+    _attn_cl_case(2, 4, 6)
+    _attn_cl_case(1, 28, 38)
+    _attn_cl_case(2, 20, 80)
+    _attn_cl_case(16, 32, 44, time_it=True)
+    _attn_cl_case(32, 20, 64, time_it=True)
+
+
 def stage_attn_small():
     _attn_case(1, 8, 16, 64, 128)        # N=128: one tile, one k-step
     _attn_case(1, 8, 16, 512, 128)       # full dk: 8 k-steps through the ring

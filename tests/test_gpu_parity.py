@@ -270,6 +270,64 @@ def test_sadecoder_module_against_reference_golden(golden, name):
     assert dec.get_sim_map() is sim
 
 
+@pytest.mark.parametrize("b,h,w", [(2, 4, 6), (1, 28, 38), (2, 32, 44)])
+def test_attention_channels_last_half(b, h, w):
+    """channels-last fp16 entry point (F, V consumed in place, V as an MN-major operand) == oracle, and == the fp32-NCHW ABI."""
+    from acan_b200 import ops
+    n, dk, dv = h * w, 512, 2048
+    f = synth.feature_map(f"cl.f.{b}.{n}", b, dk, h, w).half()
+    v = synth.feature_map(f"cl.v.{b}.{n}", b, dv, h, w).half()
+    dis = O.continuous2discrete(synth.depth_label(f"cl.lab.{b}.{n}", b, h * 8, w * 8, 0.5, 10.5), *NYU)
+    out = ops.attention_forward_cl(f.to(DEV).contiguous(memory_format=torch.channels_last), v.to(DEV).contiguous(memory_format=torch.channels_last),
+                                   want_sim_map=True, dis_label=dis.to(DEV))
+    assert out["ctx"].dtype == torch.float16 and out["ctx"].shape == (b, dv, h, w)
+    sim = O.affinity(f.double())
+    ctx = O.aggregate(sim, v.double())
+    close(out["sim_map"], sim)
+    close(out["ctx"].float(), ctx)                                             # fp16 output rounding (2^-11) included
+    want = float(O.attention_loss(sim, dis.double()))
+    assert abs(float(out["loss"]) - want) <= TOL * abs(want)
+    rows = torch.tensor([n // 4, n // 2, 3 * n // 4])
+    close(ops.attention_rows(out["ws"], rows), sim[:, rows])                    # rows kernel reads the caller's pack
+    assert abs(float(ops.attention_loss_fused(out["ws"], dis.to(DEV))) - want) <= TOL * abs(want)
+
+
+def test_pool_branch_channels_last_half():
+    from acan_b200 import ops
+    sd = synth.fill_state_dict({"linear1.weight": torch.empty(512, 2048), "linear1.bias": torch.empty(512),
+                                "linear2.weight": torch.empty(512, 512), "linear2.bias": torch.empty(512)})
+    ws = [sd[k].to(DEV) for k in ("linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias")]
+    for dtype in (torch.float16, torch.bfloat16):
+        for b, h, w in ((2, 4, 6), (3, 28, 38)):
+            x = synth.feature_map("poolcl.x", b, 2048, h, w).to(dtype)
+            keep = (synth.rand("poolcl.keep", b, 2048) > 0.5).float()
+            for km in (None, keep):
+                _, _, got = ops.pool_branch_cl(x.to(DEV).contiguous(memory_format=torch.channels_last), *ws, None if km is None else km.to(DEV))
+                close(got, O.image_context(x.double(), {k: v.double() for k, v in sd.items()}, "", None if km is None else km.double()), 1e-5)
+
+
+def test_sadecoder_half_inference_path(golden):
+    """eval + no_grad + fp16 channels_last input takes the in-place channels-last kernels; against the reference golden with
+    the tolerance of fp16 convolutions (inputs / weights rounded to 11 bits, fp32 accumulation): 5e-3."""
+    from acan_b200.modules import SADecoder
+    g = golden("sadecoder_1064")
+    hh, ww, b = (int(v) for v in g["hw"])
+    dec = SADecoder(height=hh, width=ww)
+    _load_synth(dec, g["keys"], g["shapes"])
+    dec = dec.to(DEV).eval().to(memory_format=torch.channels_last)
+    x = synth.feature_map("sadecoder_1064.x", b, 2048, hh // 8, ww // 8).to(DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        out, sim = dec(x.half().contiguous(memory_format=torch.channels_last))
+    assert out.dtype == torch.float16
+    close(out.float().reshape(-1)[T(g["out_idx"]).to(DEV)], T(g["out_val"]), 5e-3)
+    close(sim.materialize().reshape(-1)[T(g["sim_idx"]).to(DEV)], T(g["sim_val"]), 5e-3)
+    dec32 = SADecoder(height=hh, width=ww)                                      # fp32 path, separate module instance
+    _load_synth(dec32, g["keys"], g["shapes"])
+    with torch.no_grad():
+        ref, _ = dec32.to(DEV).eval()(x)
+    close(out.float(), ref, 5e-3)
+
+
 def test_full_network_against_reference_golden(golden):
     """tiny ResNet ([1,1,1,1] blocks) + CAM + OR head, BN on batch statistics, dropout off -- forward dict, both
     inference modes and the beta = 1 loss through LossFunc, against the reference's own outputs."""
