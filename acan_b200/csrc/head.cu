@@ -217,6 +217,79 @@ __global__ void __launch_bounds__(kThreads) c2d_kernel(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- fused classifier tail
+// x8 bilinear upsampling (align_corners=True, the arithmetic of ATen's upsample_bilinear2d: src = dst*(in-1)/(out-1),
+// fp32) + decode_ord + inference in one kernel that reads the stride-8 logits z [B,h,w,C] (C = 2K for OR, K for CE; 0.9 MB
+// per NYU image) instead of the upsampled [B,C,8h,8w] tensor (58 MB per image written, converted, read twice).
+// A CTA produces an 8 x 32 output tile; the <= 3 x 6 source pixels it touches are staged in shared memory with the
+// channel dimension padded by 2 floats so that the 4 bilinear taps of a warp hit distinct banks.
+constexpr int kTailRows = 8, kTailCols = 32, kTailSrcR = 3, kTailSrcC = 6;
+
+template <int KIND>
+__global__ void __launch_bounds__(kTailRows * kTailCols)
+tail_kernel(const float* __restrict__ z, float* __restrict__ depth, float* __restrict__ prob, int* __restrict__ index,
+            int h, int w, int K, BinScale bs) {
+  extern __shared__ float patch[];                       // [kTailSrcR][kTailSrcC][C + 2]
+  constexpr bool OR = (KIND == ACAN_HEAD_OR_SOFT || KIND == ACAN_HEAD_OR_HARD);
+  const int C = OR ? 2 * K : K, CP = C + 2;
+  const int H = 8 * h, W = 8 * w;
+  const int b = blockIdx.z, Y0 = blockIdx.y * kTailRows, X0 = blockIdx.x * kTailCols;
+  const float rh = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float rw = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const int r0 = (int)(rh * (float)Y0), c0 = (int)(rw * (float)X0);
+  const float* zb = z + (int64_t)b * h * w * C;
+  for (int i = threadIdx.x; i < kTailSrcR * kTailSrcC * C; i += kTailRows * kTailCols) {
+    const int c = i % C, rc = i / C, cc = rc % kTailSrcC, rr = rc / kTailSrcC;
+    const int sr = min(r0 + rr, h - 1), sc = min(c0 + cc, w - 1);
+    patch[(rr * kTailSrcC + cc) * CP + c] = __ldg(zb + ((int64_t)sr * w + sc) * C + c);
+  }
+  __syncthreads();
+  const int Y = Y0 + (threadIdx.x >> 5), X = X0 + (threadIdx.x & 31);
+  if (X >= W || Y >= H) return;
+  const float h1r = rh * (float)Y, w1r = rw * (float)X;
+  const int h1 = (int)h1r, w1 = (int)w1r;
+  const int h1p = (h1 < h - 1) ? 1 : 0, w1p = (w1 < w - 1) ? 1 : 0;
+  const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+  const float* p00 = patch + ((h1 - r0) * kTailSrcC + (w1 - c0)) * CP;
+  const float* p01 = p00 + w1p * CP;
+  const float* p10 = p00 + h1p * kTailSrcC * CP;
+  const float* p11 = p10 + w1p * CP;
+  const int64_t HW = (int64_t)H * W, pix = (int64_t)Y * W + X;
+  Acc<KIND> acc;
+  for (int k = 0; k < K; ++k) {
+    if constexpr (OR) {
+      const float2 a = *reinterpret_cast<const float2*>(p00 + 2 * k), bq = *reinterpret_cast<const float2*>(p01 + 2 * k);
+      const float2 c = *reinterpret_cast<const float2*>(p10 + 2 * k), d = *reinterpret_cast<const float2*>(p11 + 2 * k);
+      const float y0 = h0l * (w0l * a.x + w1l * bq.x) + h1l * (w0l * c.x + w1l * d.x);
+      const float y1 = h0l * (w0l * a.y + w1l * bq.y) + h1l * (w0l * c.y + w1l * d.y);
+      const float pk = ord_prob(y0, y1);
+      acc.feed(pk, k);
+      if (prob != nullptr) prob[((int64_t)b * K + k) * HW + pix] = pk;
+    } else {
+      const float v = h0l * (w0l * p00[k] + w1l * p01[k]) + h1l * (w0l * p10[k] + w1l * p11[k]);
+      if constexpr (KIND == ACAN_HEAD_CE_SOFT) {
+        acc.lift(v, k);
+        acc.feed_w(v, k, (float)k * bs.c1 / bs.inv_km1_den + bs.c0);
+      } else {
+        acc.feed(v, k);
+      }
+      if (prob != nullptr) prob[((int64_t)b * K + k) * HW + pix] = v;
+    }
+  }
+  int idx;
+  depth[(int64_t)b * HW + pix] = acc.finish(bs, idx);
+  if (index != nullptr) index[(int64_t)b * HW + pix] = idx;
+}
+
+template <int KIND>
+int launch_tail(const float* z, float* depth, float* prob, int32_t* index, int B, int h, int w, int K, BinScale bs, cudaStream_t st) {
+  const int C = (KIND == ACAN_HEAD_OR_SOFT || KIND == ACAN_HEAD_OR_HARD) ? 2 * K : K;
+  const size_t smem = (size_t)kTailSrcR * kTailSrcC * (C + 2) * sizeof(float);
+  const dim3 grid((8 * w + kTailCols - 1) / kTailCols, h, B);     // 8 output rows per source row
+  tail_kernel<KIND><<<grid, kTailRows * kTailCols, smem, st>>>(z, depth, prob, index, h, w, K, bs);
+  return launch_status("acan_tail_fwd");
+}
+
 inline int grid_for(int64_t work_items) {
   const int64_t want = (work_items + kThreads - 1) / kThreads;
   const int64_t cap = (int64_t)kNumSMs * kBlocksPerSM;
@@ -289,4 +362,22 @@ extern "C" int acan_continuous2discrete(const float* depth, float* bins, int64_t
   c2d_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(depth, bins, n, (float)d_min, (float)d_max,
                                                                               (float)std::log(d_max / d_min), (float)(K - 1));
   return launch_status("acan_continuous2discrete");
+}
+
+extern "C" int acan_tail_fwd(const float* z_nhwc, float* depth, float* prob, int32_t* index, int B, int h, int w, int K,
+                             double d_min, double d_max, int kind, void* stream) {
+  ACAN_CHECK_ARG(z_nhwc && depth, "acan_tail_fwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && h > 0 && w > 0 && K > 1 && K <= 2048, "acan_tail_fwd: B=%d h=%d w=%d K=%d invalid", B, h, w, K);
+  ACAN_CHECK_ARG(d_min > 0 && d_max > d_min, "acan_tail_fwd: need 0 < d_min < d_max");
+  ACAN_CHECK_ARG(kind >= 0 && kind <= 3, "acan_tail_fwd: kind %d unknown", kind);
+  ACAN_CHECK_ARG(B <= 65535 && h <= 65535, "acan_tail_fwd: grid too large");
+  BinScale bs{(float)(K - 1), (float)std::log(d_max / d_min), (float)std::log(d_min)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PROF_HEAD, st);
+  switch (kind) {
+    case ACAN_HEAD_OR_SOFT: return launch_tail<ACAN_HEAD_OR_SOFT>(z_nhwc, depth, prob, index, B, h, w, K, bs, st);
+    case ACAN_HEAD_OR_HARD: return launch_tail<ACAN_HEAD_OR_HARD>(z_nhwc, depth, prob, index, B, h, w, K, bs, st);
+    case ACAN_HEAD_CE_SOFT: return launch_tail<ACAN_HEAD_CE_SOFT>(z_nhwc, depth, prob, index, B, h, w, K, bs, st);
+    default:                return launch_tail<ACAN_HEAD_CE_HARD>(z_nhwc, depth, prob, index, B, h, w, K, bs, st);
+  }
 }

@@ -1,0 +1,133 @@
+"""Inference-time graph optimisation of the host network around the hot path (library calls only).
+
+``optimize_for_inference(net)`` returns a frozen fp16 / channels_last copy of an ``acan_b200.network.ResNet`` in which
+  * every eval-mode BatchNorm is folded into the convolution in front of it (an exact algebraic rewrite:
+    W' = W * g / sqrt(var + eps),  b' = beta + (b - mean) * g / sqrt(var + eps)),
+  * conv + bias + ReLU and conv + bias + residual-add + ReLU are single cuDNN fused-epilogue calls
+    (``torch.cudnn_convolution_relu`` / ``torch.cudnn_convolution_add_relu``),
+so the only kernels left between the convolutions are the hand-written ones of the context aggregation module and
+the fused classifier tail.  In the profile of the unfused network the BN / ReLU / add kernels were 40-60 % of the step
+(``profiles/``); none of this touches the reference's semantics beyond fp16 rounding, and the result is checked against
+the unfused network in ``tests/test_gpu_parity.py``.  The returned module has the reference's ``forward`` /
+``inference`` / ``predict_depth`` surface but NOT its ``state_dict`` layout -- it is an inference artefact, not a checkpoint.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .network import Bottleneck, ResNet
+
+
+def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """(weight, bias) of the convolution equal to bn(conv(x)) in eval mode, in fp32."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return w * scale.view(-1, 1, 1, 1), bn.bias.detach().float() + (b - bn.running_mean.detach().float()) * scale
+
+
+class FusedConv(nn.Module):
+    """conv + bias (+ residual) (+ ReLU) as one cuDNN call on fp16 channels_last tensors."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, stride, padding, dilation, relu: bool):
+        super().__init__()
+        self.register_buffer("weight", weight.to(torch.float16).contiguous(memory_format=torch.channels_last))
+        self.register_buffer("bias", bias.to(torch.float16).contiguous())
+        self.stride, self.padding, self.dilation, self.relu = tuple(stride), tuple(padding), tuple(dilation), relu
+        self._fused_ok = True
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._fused_ok and self.relu:
+            try:
+                if residual is None:
+                    return torch.cudnn_convolution_relu(x, self.weight, self.bias, self.stride, self.padding, self.dilation, 1)
+                return torch.cudnn_convolution_add_relu(x, self.weight, residual, 1.0, self.bias, self.stride, self.padding, self.dilation, 1)
+            except RuntimeError:
+                self._fused_ok = False          # configuration the fused-epilogue path does not support: plain calls from now on
+        y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation)
+        if residual is not None:
+            y = y + residual
+        return torch.relu_(y) if self.relu else y
+
+
+class FusedBottleneck(nn.Module):
+    def __init__(self, blk: Bottleneck):
+        super().__init__()
+        def fc(conv, bn, relu):
+            w, b = fold_conv_bn(conv, bn)
+            return FusedConv(w, b, conv.stride, conv.padding, conv.dilation, relu)
+        self.c1, self.c2, self.c3 = fc(blk.conv1, blk.bn1, True), fc(blk.conv2, blk.bn2, True), fc(blk.conv3, blk.bn3, True)
+        self.project = fc(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
+
+    def forward(self, x):
+        skip = x if self.project is None else self.project(x)
+        return self.c3(self.c2(self.c1(x)), skip)
+
+
+class InferenceNet(nn.Module):
+    """frozen fp16 channels_last network: fused backbone -> SADecoder (half-precision kernel path) -> fused tail."""
+
+    def __init__(self, net: ResNet):
+        super().__init__()
+        if net.use_inter:
+            raise NotImplementedError("optimize_for_inference: the auxiliary (alpha != 0) branch is a training-time output")
+        w, b = fold_conv_bn(net.conv1, net.bn1)
+        self.stem = FusedConv(w, b, net.conv1.stride, net.conv1.padding, net.conv1.dilation, True)
+        self.maxpool = net.maxpool
+        self.blocks = nn.Sequential(*[FusedBottleneck(blk) for layer in (net.layer1, net.layer2, net.layer3, net.layer4) for blk in layer])
+        self.decoder = copy.deepcopy(net.decoder)
+        key = self.decoder.saconv.f_key                 # F = ReLU(BN(conv(x))) -> one fused call as well
+        wk, bk = fold_conv_bn(key.conv, key.bn)
+        self.decoder.saconv.fused_key = FusedConv(wk, bk, key.conv.stride, key.conv.padding, key.conv.dilation, True)
+        val = self.decoder.saconv.f_value
+        self.decoder.saconv.fused_value = nn.Sequential(
+            FusedConv(val.conv1.weight.detach(), val.conv1.bias.detach(), val.conv1.stride, val.conv1.padding, val.conv1.dilation, True),
+            FusedConv(val.conv2.weight.detach(), val.conv2.bias.detach(), val.conv2.stride, val.conv2.padding, val.conv2.dilation, True))
+        self.classifier_conv = copy.deepcopy(net.classifier.conv).half().to(memory_format=torch.channels_last)
+        self.min_depth, self.max_depth, self.num_classes = net.min_depth, net.max_depth, net.num_classes
+        self.classifierType, self.inferenceType = net.classifierType, net.inferenceType
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def _features(self, x):
+        x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
+        x = self.blocks(self.maxpool(self.stem(x)))
+        x, sim_map = self.decoder(x)
+        return self.classifier_conv(x), sim_map
+
+    @torch.no_grad()
+    def forward(self, x):
+        from .modules import LazyProb
+        z, sim_map = self._features(x)
+        y = LazyProb(z, "OR" if self.classifierType == "OR" else "CE", self.min_depth, self.max_depth, self.num_classes)
+        return {"inter_y": None, "sim_map": sim_map, "y": y}
+
+    @torch.no_grad()
+    def inference(self, y):
+        from . import ops
+        from .modules import LazyProb
+        if isinstance(y, list):
+            y = y[-1]
+        if isinstance(y, dict):
+            y = y["y"]
+        mode = "soft" if self.inferenceType == "soft" else "hard"
+        if isinstance(y, LazyProb):
+            return y.depth(mode)
+        return ops.head_inference(y, "OR" if self.classifierType == "OR" else "CE", mode, self.min_depth, self.max_depth, self.num_classes)
+
+    @torch.no_grad()
+    def predict_depth(self, x):
+        return self.inference(self.forward(x))
+
+
+def optimize_for_inference(net: ResNet) -> InferenceNet:
+    """frozen, BN-folded, fused-epilogue fp16 copy of ``net`` (which must hold calibrated / trained BN statistics)."""
+    if not isinstance(net, ResNet):
+        raise TypeError("optimize_for_inference expects an acan_b200.network.ResNet")
+    return InferenceNet(net.eval())

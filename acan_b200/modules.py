@@ -137,6 +137,70 @@ class LazySimMap:
         return getattr(self.materialize(), name)
 
 
+class LazyProb:
+    """Stand-in for the forward dict's ``'y'`` ([B,K,H,W] bin probabilities / scores) in eval mode.
+
+    The reference upsamples the stride-8 logits x8 and decodes them at full resolution (model.py:123-125, 228-230) only for
+    ``inference(y)`` to reduce them to one depth per pixel (depthest_trainer.py:184-185).  This handle keeps the stride-8
+    logits; ``ResNet.inference`` recognises it and runs the fused tail kernel (``acan_tail_fwd``: upsample + decode_ord +
+    head, the full-resolution tensor never exists).  Any other use materialises the real tensor with the same kernel."""
+
+    def __init__(self, z: torch.Tensor, classifier: str, d_min: float, d_max: float, n_c: int):
+        self._z, self._cls, self._dmin, self._dmax, self._k = z, classifier, d_min, d_max, n_c
+        self._dense = None
+
+    @property
+    def shape(self):
+        b, _, h, w = self._z.shape
+        return torch.Size((b, self._k, 8 * h, 8 * w))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 4
+
+    @property
+    def device(self):
+        return self._z.device
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def depth(self, mode: str, want_index: bool = False):
+        return ops.tail_inference(self._z, self._cls, mode, self._dmin, self._dmax, self._k, want_index=want_index)
+
+    def materialize(self) -> torch.Tensor:
+        if self._dense is None:
+            _, self._dense = ops.tail_inference(self._z, self._cls, "soft", self._dmin, self._dmax, self._k, want_prob=True)
+        return self._dense
+
+    def __getitem__(self, key):
+        return self.materialize()[key]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        return f"LazyProb(shape={tuple(self.shape)}, materialised={self._dense is not None})"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def conv(a):
+            if isinstance(a, LazyProb):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(conv(x) for x in a)
+            return a
+        return func(*conv(args), **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
 class _Holder:
     """per-module slot for the attention workspace of the latest forward (operand pack, row statistics)."""
     ws = None
@@ -282,9 +346,12 @@ class SADecoder(nn.Module):
         by the channels-last kernels (no pack, no fp32 copies), ctx comes back fp16 channels_last for the merge GEMM."""
         b = x.shape[0]
         sa = self.saconv
-        with torch.autocast("cuda", dtype=torch.float16):
-            feat = sa.key_features(x)
-            value = sa.f_value(x)
+        if getattr(sa, "fused_key", None) is not None:          # BN-folded, fused-epilogue convolutions (inference.py)
+            feat, value = sa.fused_key(x), sa.fused_value(x)
+        else:
+            with torch.autocast("cuda", dtype=torch.float16):
+                feat = sa.key_features(x)
+                value = sa.f_value(x)
         out = ops.attention_forward_cl(feat, value, ws=sa._holder.ws)
         sa._holder.ws = out["ws"]
         sa._holder.row_stats = out["row_stats"]

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import functions as fn
 from . import ops
-from .modules import AttentionLoss2d, LazySimMap, SADecoder, _init_like_reference
+from .modules import AttentionLoss2d, LazyProb, LazySimMap, SADecoder, _init_like_reference
 
 
 def continuous2discrete(depth, d_min, d_max, n_c):
@@ -64,6 +64,8 @@ class BaseClassificationModel_(nn.Module):
             y = y["y"]
         cls = "OR" if self.classifierType == "OR" else "CE"
         mode = "soft" if self.inferenceType == "soft" else "hard"
+        if isinstance(y, LazyProb):                      # eval: fused upsample + decode_ord + head on the stride-8 logits
+            return y.depth(mode)
         return ops.head_inference(y, cls, mode, self.min_depth, self.max_depth, self.num_classes)
 
     def forward(self):
@@ -141,6 +143,7 @@ class ResNet(BaseClassificationModel_):
         self.decoder = make_decoder(height, width, decoderType)
         self.use_inter = self.alpha != 0.0
         self.interout, self.classifier = make_classifier(classifierType, num_classes, self.use_inter, channel1=1024, channel2=2048)
+        self.lazy_head = True            # eval: 'y' is a LazyProb handle (False: always materialise like the reference)
         self.parameter_initialization()
 
     def parameter_initialization(self):
@@ -167,6 +170,13 @@ class ResNet(BaseClassificationModel_):
         sim_map = None
         if self.decoderType == "attention":
             x, sim_map = self.decoder(x)
+        if self.lazy_head and not self.training and not torch.is_grad_enabled():
+            # eval: keep the stride-8 logits; inference() fuses upsample + decode_ord + head
+            y = LazyProb(self.classifier.conv(x), "OR" if self.classifierType == "OR" else "CE",
+                         self.min_depth, self.max_depth, self.num_classes)
+            if self.use_inter and self.classifierType == "OR":
+                inter_y = self.decode_ord(inter_y)
+            return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
         y = self.classifier(x)
         if self.classifierType == "OR":
             y = self.decode_ord(y)
@@ -180,10 +190,9 @@ class ResNet(BaseClassificationModel_):
         (the [B,K,H,W] probability tensor is never written).  Same result as inference(forward(x))."""
         _, feat = self.encode(x)
         feat, _ = self.decoder(feat)
-        y = self.classifier(feat)
         cls = "OR" if self.classifierType == "OR" else "CE"
         mode = "soft" if self.inferenceType == "soft" else "hard"
-        return ops.head_inference(y, cls, mode, self.min_depth, self.max_depth, self.num_classes, from_logits=(cls == "OR"))
+        return ops.tail_inference(self.classifier.conv(feat), cls, mode, self.min_depth, self.max_depth, self.num_classes)
 
     class LossFunc(nn.Module):
         """model.py:235-272: loss1 + alpha * loss2 + beta * loss3.  ``preds['sim_map']`` may be a LazySimMap."""

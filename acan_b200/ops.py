@@ -59,6 +59,27 @@ def head_inference(x: torch.Tensor, classifier: str, mode: str, d_min: float, d_
     return (depth, index) if want_index else depth
 
 
+def tail_inference(z: torch.Tensor, classifier: str, mode: str, d_min: float, d_max: float, n_c: int,
+                   want_prob: bool = False, want_index: bool = False):
+    """Fused classifier tail: stride-8 logits z [B,C,h,w] (any float dtype / layout) -> depth [B,1,8h,8w]
+    (+ 'y' = decode_ord(upsample(z)) [B,K,8h,8w] and / or the int32 bin index)."""
+    kind = HEAD_KINDS[("OR" if classifier == "OR" else "CE", "soft" if mode == "soft" else "hard")]
+    if not z.is_cuda:
+        raise _lib.AcanLibraryError("z must be a CUDA tensor: acan_b200 has no CPU path")
+    zz = z.permute(0, 2, 3, 1).float().contiguous()        # [B,h,w,C] fp32: 0.9 MB per NYU image
+    b, h, w, c = zz.shape
+    if c != (2 * n_c if classifier == "OR" else n_c):
+        raise _lib.AcanLibraryError(f"tail input has {c} channels")
+    depth = torch.empty((b, 1, 8 * h, 8 * w), device=zz.device, dtype=torch.float32)
+    prob = torch.empty((b, n_c, 8 * h, 8 * w), device=zz.device, dtype=torch.float32) if want_prob else None
+    index = torch.empty((b, 1, 8 * h, 8 * w), device=zz.device, dtype=torch.int32) if want_index else None
+    with torch.cuda.device(zz.device):
+        _lib.check(_lib.load().acan_tail_fwd(zz.data_ptr(), depth.data_ptr(), _lib.ptr(prob), _lib.ptr(index), b, h, w, n_c,
+                                             float(d_min), float(d_max), kind, _lib.current_stream()), "acan_tail_fwd")
+    out = (depth,) + ((prob,) if want_prob else ()) + ((index,) if want_index else ())
+    return out[0] if len(out) == 1 else out
+
+
 def continuous2discrete(depth: torch.Tensor, d_min: float, d_max: float, n_c: int) -> torch.Tensor:
     d = _cuda_f32(depth, "depth")
     out = torch.empty_like(d)

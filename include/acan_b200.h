@@ -75,6 +75,15 @@ int acan_decode_ord_bwd(const float* prob, const float* grad_prob, float* grad_l
 int acan_head_fwd(const float* in, float* depth, int32_t* index, int B, int K, int64_t HW,
                   double d_min, double d_max, int kind, int from_logits, void* stream);
 
+/* Fused classifier tail: the x8 bilinear upsampling (align_corners=True) of make_classifier
+ * (model.py:123-125), decode_ord (model.py:40-45) and the inference head (model.py:47-99) in one kernel that reads the
+ * STRIDE-8 logits and never materialises the [B,2K,H,W] tensor.
+ *   z_nhwc  [B,h,w,C] fp32, C = 2K (OR kinds) or K (CE kinds): output of classifier.conv, channels last
+ *   depth   [B,1,8h,8w];  prob: NULL, or [B,K,8h,8w] receiving decode_ord(upsample(z)) (the forward dict's 'y');
+ *   index   NULL or int32 [B,1,8h,8w]. */
+int acan_tail_fwd(const float* z_nhwc, float* depth, float* prob, int32_t* index, int B, int h, int w, int K,
+                  double d_min, double d_max, int kind, void* stream);
+
 /* continuous2discrete (model.py:19-23, torch-0.4 semantics): metres -> bin index as float, 0 outside (d_min,d_max). */
 int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream);
 

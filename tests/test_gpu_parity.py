@@ -110,6 +110,35 @@ def test_head_full_size_properties(B, H, W, params):
     close(d1[sub], O.hard_ordinal_regression(prob[sub].cpu(), dmin, dmax, K), 1e-6)
 
 
+@pytest.mark.parametrize("b,h,w,params", [(2, 4, 6, NYU), (1, 28, 38, NYU), (2, 20, 64, (1.98, 80.0, 80))])
+def test_fused_tail_against_oracle(b, h, w, params):
+    """acan_tail_fwd (x8 bilinear align_corners + decode_ord + head from the stride-8 logits) vs upsample -> decode -> head."""
+    from acan_b200 import ops
+    dmin, dmax, K = params
+    z = 2.0 * synth.randn(f"tail.z.{b}.{h}.{w}", b, 2 * K, h, w)
+    up = torch.nn.functional.interpolate(z.double(), scale_factor=8, mode="bilinear", align_corners=True)
+    prob = O.decode_ord(up)
+    d, y, idx = ops.tail_inference(z.to(DEV), "OR", "soft", dmin, dmax, K, want_prob=True, want_index=True)
+    close(y, prob, 1e-5)
+    close(d, O.soft_ordinal_regression(prob, dmin, dmax, K), 1e-5)
+    d, idx = ops.tail_inference(z.to(DEV), "OR", "hard", dmin, dmax, K, want_index=True)
+    want = O.hard_ordinal_index(prob)
+    # a bin whose p is within fp32 rounding of 0.5 may land on either side of the threshold: allow 1e-4 of the pixels, one bin
+    diff = (idx.cpu().long() - want).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-4
+    # the kernel's own 'y' and its own index are consistent bit for bit
+    assert torch.equal(idx.long(), (y > 0.5).sum(1, keepdim=True))
+    zc = z[:, :K].contiguous()
+    upc = torch.nn.functional.interpolate(zc.double(), scale_factor=8, mode="bilinear", align_corners=True)
+    close(ops.tail_inference(zc.to(DEV), "CE", "soft", dmin, dmax, K), O.soft_cross_entropy(upc, dmin, dmax, K), 1e-5)
+    d, idx = ops.tail_inference(zc.to(DEV), "CE", "hard", dmin, dmax, K, want_index=True)
+    assert float((idx.cpu().long() != O.hard_cross_entropy_index(upc)).float().mean()) < 1e-4
+    # half-precision channels_last logits (what the autocast pipeline hands over) go through the same entry
+    zh = z.half().to(DEV).contiguous(memory_format=torch.channels_last)
+    close(ops.tail_inference(zh, "OR", "soft", dmin, dmax, K), O.soft_ordinal_regression(O.decode_ord(
+        torch.nn.functional.interpolate(z.half().double(), scale_factor=8, mode="bilinear", align_corners=True)), dmin, dmax, K), 1e-5)
+
+
 def test_decode_ord_backward_matches_autograd():
     from acan_b200 import functions as fn
     y = (2 * torch.randn(2, 160, 8, 12, device=DEV)).requires_grad_(True)
@@ -363,8 +392,17 @@ def test_full_network_against_reference_golden(golden):
     gk = net.decoder.saconv.f_key.conv.weight.grad
     assert gk is not None and torch.isfinite(gk).all() and float(gk.abs().max()) > 0
     net.inferenceType = "soft"
+    from acan_b200.modules import LazyProb
+    net.eval()
     with torch.no_grad():
-        close(net.predict_depth(x), net.inference(net(x)), 1e-5)                    # fused eval shortcut == two-step
+        lazy = net(x)                                                                # eval: 'y' is a LazyProb handle
+        assert isinstance(lazy["y"], LazyProb) and tuple(lazy["y"].shape) == (b, NYU[2], hh, ww)
+        d_lazy = net.inference(lazy)                                                 # fused tail kernel
+        net.lazy_head = False
+        full = net(x)                                                                # reference-style: upsample, decode_ord, head
+        close(d_lazy, net.inference(full), 1e-5)
+        close(lazy["y"].materialize(), full["y"], 1e-5)
+        close(net.predict_depth(x), d_lazy, 1e-6)
 
 
 def test_training_step_gradients_against_oracle():
@@ -391,3 +429,33 @@ def test_training_step_gradients_against_oracle():
             assert float(p.grad.abs().max()) < 1e-4 * scale, name
         else:
             close(p.grad, want, 5e-3)
+
+
+def test_optimize_for_inference_matches_unfused_network():
+    """BN folding + fused conv epilogues + fp16 channels_last + half-precision CAM path + fused tail == the fp32 network
+    within fp16 rounding (2e-2 on depth over a [1,1,1,1] backbone), on calibrated BN statistics."""
+    from acan_b200.inference import optimize_for_inference
+    from acan_b200.network import ResNet
+    hh, ww, b = 64, 96, 2
+    torch.manual_seed(synth.SEED)
+    net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=0, layers=[1, 1, 1, 1]).to(DEV)
+    x = synth.rand("opt.x", b, 3, hh, ww).to(DEV)
+    for m in net.modules():                                   # calibration: batch statistics -> running buffers (SURVEY §8d)
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()
+    net.train()
+    with torch.no_grad():
+        net(x)
+    net.eval()
+    with torch.no_grad():
+        want = net.inference(net(x))
+    fast = optimize_for_inference(net)
+    out = fast(x)
+    got = fast.inference(out)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    close(got, want, 2e-2)
+    close(fast.predict_depth(x), got, 1e-6)
+    n = out["sim_map"].shape[1]
+    close(out["sim_map"].rows([n // 2]), net(x)["sim_map"].materialize()[:, [n // 2]], 2e-2)
