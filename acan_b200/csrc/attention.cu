@@ -45,7 +45,7 @@ constexpr int UMMA_K = 16;
 constexpr int kMaxBN = 256;
 constexpr int kMinBN = 64;
 constexpr int kTmemCols = 512;          // 2 accumulator buffers x 256 fp32 columns
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;       // TMA warp + MMA warp + 2 x 4 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024; // operand ring; barriers + alignment slack come on top
 constexpr float kLog2e = 1.4426950408889634f;
@@ -67,6 +67,7 @@ struct GemmArgs {
   uint32_t idesc;
   float c;             // scale * log2(e)
   int skip_epilogue;   // experiments only (ACAN_SKIP_EPI=1): release the accumulator without reading it
+  long long* trace;    // experiments only (ACAN_TRACE=1): per-tile clock64 stamps of CTA 0: [tile][4] = mma start, mma issued, epi start, epi end
   // MODE_STATS
   float2* part;        // [B, n_tiles, m_rows] (m2, l) partials
   // MODE_PROBS
@@ -127,7 +128,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < g.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 128 * CG); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 8 * CG); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -183,6 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 0] = clock64();
         const uint32_t d_tmem = tmem_base + acc * kMaxBN;
         for (int ks = 0; ks < g.k_steps; ++ks) {
           mbar_wait(&bars->full[stage], phase);
@@ -201,16 +203,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
         }
         if (CG == 1) umma_commit(&bars->tmem_full[acc]); else umma_commit_2sm(&bars->tmem_full[acc], 3);   // -> epilogue(s)
+        if (g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 1] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps
+    // Each group covers the 128 TMEM lanes (warp % 4 = lane quarter) and owns alternate column chunks of the tile, its
+    // own staging buffer and its own named barrier, so the two groups run decoupled and two warps share every SM
+    // sub-partition: one group's tcgen05.ld / MUFU latency hides under the other's issue (the 4-warp version measured
+    // ~1140 cycles of exposed latency per 64-column chunk and made the QK passes epilogue-bound).
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int group = (warp - 2) >> 2;                  // 0: warps 2-5, 1: warps 6-9
     const int row_in_tile = quarter * 32 + lane;
-    const bool store_leader = (threadIdx.x == 64);      // warp 2, lane 0 issues the TMA stores
-    uint32_t acc = 0, acc_phase = 0, out_buf = 0;
+    const bool store_leader = ((threadIdx.x - 64) & 127) == 0;   // lane 0 of each group's first warp issues its TMA stores
+    uint8_t* const buf = out_stage + group * kOutChunkBytes;
+    const int bar_id = 1 + group;
+    uint32_t acc = 0, acc_phase = 0;
     const uint32_t leader_empty0 = (CG == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0) : 0u;
     const uint32_t leader_empty1 = (CG == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[1]), 0) : 0u;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -223,16 +233,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int col0 = nt * g.bn;
       const int nvalid = min(g.bn, g.n_cols - col0);   // >= 1 by construction of n_tiles
       const int chunks = (nvalid + 31) >> 5;
+      const size_t part_idx = (static_cast<size_t>(b) * (2 * g.n_tiles) + 2 * nt + group) * g.m_rows + row;   // per (key tile, group) partials
 
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (g.trace && blockIdx.x == 0 && threadIdx.x == 64) g.trace[(tile / tile_step) * 4 + 2] = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
 
-      if (g.skip_epilogue) {
+      if (g.skip_epilogue == 1) {
         // nothing: mainloop-only timing experiment
       } else if constexpr (MODE == MODE_STATS) {
         float m = -INFINITY, l = 0.f;                   // m in raw dot-product units
-        for (int ch = 0; ch < chunks; ++ch) {
+        for (int ch = group; ch < chunks; ch += 2) {
           float v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
           tmem_ld_wait();
@@ -247,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) s += ex2_approx(fmaf(v[j], g.c, -mc));
           l += s;
         }
-        if (row_ok) g.part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = make_float2(m * g.c, l);
+        if (row_ok) g.part[part_idx] = make_float2(m * g.c, l);        // (-inf, 0) when this group had no chunk
       } else if constexpr (MODE == MODE_PROBS) {
         float m2 = 0.f, inv_l = 0.f, la_i = 0.f, lnz_i = 0.f, log2_l = 0.f;
         const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
@@ -261,12 +273,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float kl_acc = 0.f;
         const float* la_cols = kl ? g.logbin + static_cast<size_t>(b) * g.n_cols + col0 : nullptr;
         float* srow = g.sim_out ? g.sim_out + (brow * g.n_cols + col0) : nullptr;
-        // 64 columns (= 128 B of fp16) per staged TMA store
-        for (int ch = 0; ch < chunks; ch += 2) {
-          uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
+        // 64 columns (= 128 B of fp16) per staged TMA store; this group takes every other 64-column chunk
+        for (int ch = 2 * group; ch < chunks; ch += 4) {
           if (g.store_p) {
-            if (store_leader) tma_store_wait_read<kOutBuffers - 1>();   // the store that last used `buf` has drained it
-            named_bar_sync(1, 128);
+            if (store_leader) tma_store_wait_read<0>();       // this group's previous store has drained `buf`
+            named_bar_sync(bar_id, 128);
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -292,8 +303,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   }
                 }
               }
+              if (g.skip_epilogue != 3) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
+                for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
+              }
               if (g.store_p) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -311,20 +324,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           if (g.store_p) {
             fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA engine
-            named_bar_sync(1, 128);
-            if (store_leader) {                        // rows / columns beyond N are clipped by the tensor map
+            named_bar_sync(bar_id, 128);
+            if (store_leader && g.skip_epilogue != 2) { // rows / columns beyond N are clipped by the tensor map
               tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
               tma_store_commit();
             }
-            out_buf = (out_buf + 1) % kOutBuffers;
           }
         }
-        if (kl && row_ok) g.kl_part[(static_cast<size_t>(b) * g.n_tiles + nt) * g.m_rows + row] = kl_acc;
+        if (kl && row_ok) g.kl_part[part_idx] = kl_acc;
       } else if constexpr (MODE == MODE_PVT) {   // rows = query positions, columns = value channels; 64 fp16 columns per staged store
-        for (int ch = 0; ch < chunks; ch += 2) {
-          uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
-          if (store_leader) tma_store_wait_read<kOutBuffers - 1>();
-          named_bar_sync(1, 128);
+        for (int ch = 2 * group; ch < chunks; ch += 4) {
+          if (store_leader) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             if (ch + half < chunks) {
@@ -339,18 +350,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (store_leader) {
             tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
             tma_store_commit();
           }
-          out_buf = (out_buf + 1) % kOutBuffers;
         }
       } else {  // MODE_PV: rows = value channels, columns = query positions; 32 fp32 columns (128 B) per staged store
-        for (int ch = 0; ch < chunks; ++ch) {
-          uint8_t* buf = out_stage + out_buf * kOutChunkBytes;
-          if (store_leader) tma_store_wait_read<kOutBuffers - 1>();
-          named_bar_sync(1, 128);
+        for (int ch = group; ch < chunks; ch += 2) {
+          if (store_leader) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
           float v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
           tmem_ld_wait();
@@ -359,19 +368,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             *staged_chunk(buf, row_in_tile, q) = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
                                                             __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (store_leader) {
             tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
             tma_store_commit();
           }
-          out_buf = (out_buf + 1) % kOutBuffers;
         }
       }
 
+      if (g.trace && blockIdx.x == 0 && threadIdx.x == 64) g.trace[(tile / tile_step) * 4 + 3] = clock64();
       tc_fence_before();
-      // 128 (x CG) arrivals on the LEADER's barrier release the accumulator buffer
-      if (CG == 1) mbar_arrive(&bars->tmem_empty[acc]);
-      else         mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);
+      // one arrival per epilogue warp (8 x CG) on the LEADER's barrier releases the accumulator buffer
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&bars->tmem_empty[acc]);
+        else         mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -570,7 +582,7 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   Workspace w;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return reinterpret_cast<uint8_t*>(base) + o; };
-  const size_t nt_max = (N + kMinBN - 1) / kMinBN;
+  const size_t nt_max = 2 * ((N + kMinBN - 1) / kMinBN);      // one partial per (key tile, epilogue group)
   w.fh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * dk * 2));
   w.vh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * dv * N * 2));
   w.p = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * N * 2));
@@ -645,7 +657,7 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
     ProfScope ps(PROF_STATS, st);
     g.part = w.part;
     if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;
-    combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, g.n_tiles, N, B);
+    combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, 2 * g.n_tiles, N, B);
     if (int e = launch_status("combine_stats_kernel")) return e;
   }
   if (want_p || sim_map || kl) {
@@ -655,10 +667,25 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
     g.logbin = kl ? w.logbin : nullptr;
     g.lnz = w.lnz;
     g.kl_part = w.kl_part;
-    ProfScope ps(PROF_PROBS, st);
-    if (int e = launch_gemm<MODE_PROBS>(ta, tb, tp, g, st, cg)) return e;
+    static long long* trace_buf = nullptr;
+    if (env_int("ACAN_TRACE", 0) && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
+    g.trace = env_int("ACAN_TRACE", 0) ? trace_buf : nullptr;
+    {
+      ProfScope ps(PROF_PROBS, st);
+      if (int e = launch_gemm<MODE_PROBS>(ta, tb, tp, g, st, cg)) return e;
+    }
+    if (g.trace) {
+      long long h[512];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      int n = (g.batch * g.m_tiles * g.n_tiles + kNumSMs / cg - 1) / (kNumSMs / cg);
+      if (n > 12) n = 12;
+      fprintf(stderr, "PROBS trace, CTA 0 (cycles rel. to first MMA start): tile: mma_start mma_issued | epilogue start end\n");
+      for (int i = 0; i < n; ++i)
+        fprintf(stderr, "  %2d: %7lld %7lld | %7lld %7lld\n", i, h[i * 4] - h[0], h[i * 4 + 1] - h[0], h[i * 4 + 2] - h[0], h[i * 4 + 3] - h[0]);
+      g.trace = nullptr;
+    }
   }
-  *key_tiles = g.n_tiles;   // callers need it to reduce kl_part
+  *key_tiles = 2 * g.n_tiles;   // kl_part slices per row (key tile x epilogue group): callers reduce over them
   return 0;
 }
 

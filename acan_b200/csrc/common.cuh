@@ -193,8 +193,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics.  NOT .release.cluster: a cluster-scope release drains and
+// invalidates L1 and cost ~2000 cycles per tile in the first version of the pair kernels (profiles/r01_notes.md); the
+// accumulator hand-over it guards is ordered by tcgen05.fence::before_thread_sync, not by the generic-proxy release.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair into its OWN shared memory, completing on the mbarrier at cluster address `bar_addr`
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, int c2) {
