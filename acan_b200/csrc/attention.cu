@@ -67,6 +67,10 @@ struct GemmArgs {
   uint32_t idesc;
   float c;             // scale * log2(e)
   int skip_epilogue;   // experiments only (ACAN_SKIP_EPI=1): release the accumulator without reading it
+  const int* img_skip; // MODE_STATS: images whose flag is non-zero need no statistics pass (their tiles are skipped by all roles)
+  int unnorm;          // MODE_PROBS: write p~ = exp2(S*c - shift_i) un-normalised and emit per-row partial sums of the ROUNDED values
+  float* lpart;        //   [B, 2*n_tiles, N] those partial sums
+  const float* inv_l;  // MODE_PV / MODE_PVT: [B, N] 1 / l_i applied per query while the accumulator leaves TMEM (null = already normalised)
   long long* trace;    // experiments only (ACAN_TRACE=1): per-tile clock64 stamps of CTA 0: [tile][4] = mma start, mma issued, epi start, epi end
   // MODE_STATS
   float2* part;        // [B, n_tiles, m_rows] (m2, l) partials
@@ -149,6 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int b = tile / (g.n_tiles * g.m_tiles);
         const int a_row = (mt * CG + static_cast<int>(cta_rank)) * BM;
         const int b_row = nt * g.bn + static_cast<int>(cta_rank * b_rows);
+        if (MODE == MODE_STATS && g.img_skip != nullptr && __ldg(g.img_skip + b) != 0) continue;
         for (int ks = 0; ks < g.k_steps; ++ks) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
@@ -182,6 +187,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        if (MODE == MODE_STATS && g.img_skip != nullptr && __ldg(g.img_skip + tile / (g.n_tiles * g.m_tiles)) != 0) continue;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 0] = clock64();
@@ -234,6 +240,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int nvalid = min(g.bn, g.n_cols - col0);   // >= 1 by construction of n_tiles
       const int chunks = (nvalid + 31) >> 5;
       const size_t part_idx = (static_cast<size_t>(b) * (2 * g.n_tiles) + 2 * nt + group) * g.m_rows + row;   // per (key tile, group) partials
+      if (MODE == MODE_STATS && g.img_skip != nullptr && __ldg(g.img_skip + b) != 0) continue;
 
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -265,8 +272,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
         {
           const float2 st = g.stats[brow];
-          m2 = st.x; inv_l = 1.0f / st.y; log2_l = lg2_approx(st.y);
+          m2 = st.x;
+          if (g.unnorm) { inv_l = 1.0f; } else { inv_l = 1.0f / st.y; log2_l = lg2_approx(st.y); }
         }
+        float l_acc = 0.f;                               // un-normalised mode: sum of the fp16-ROUNDED p~ this group wrote
         const bool kl = g.logbin != nullptr;
         bool kl_row = false;
         if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; kl_row = row_ok && la_i > -INFINITY; }
@@ -303,6 +312,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   }
                 }
               }
+              if (g.unnorm) {
+                if (nv < 32) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) if (j >= nv) v[j] = -INFINITY;   // columns beyond N: p~ = 0
+                }
+                uint32_t h[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  h[j] = pack_half2(ex2_approx(v[2 * j]), ex2_approx(v[2 * j + 1]));
+                  const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+                  l_acc += r.x + r.y;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *staged_chunk(buf, row_in_tile, half * 4 + q) = make_uint4(h[q * 4 + 0], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
+                continue;
+              }
               if (g.skip_epilogue != 3) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
@@ -332,7 +358,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
         if (kl && row_ok) g.kl_part[part_idx] = kl_acc;
+        if (g.unnorm && row_ok) g.lpart[part_idx] = l_acc;
       } else if constexpr (MODE == MODE_PVT) {   // rows = query positions, columns = value channels; 64 fp16 columns per staged store
+        const float rs = g.inv_l ? __ldg(g.inv_l + static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0)) : 1.0f;
         for (int ch = 2 * group; ch < chunks; ch += 4) {
           if (store_leader) tma_store_wait_read<0>();
           named_bar_sync(bar_id, 128);
@@ -342,6 +370,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               float v[32];
               tmem_ld_32x32(taddr + (ch + half) * 32, v);
               tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= rs;
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *staged_chunk(buf, row_in_tile, half * 4 + q) =
@@ -363,6 +393,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           float v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
           tmem_ld_wait();
+          if (g.inv_l) {                                  // columns are the queries here
+            const float* il = g.inv_l + static_cast<size_t>(b) * g.n_cols + col0 + ch * 32;
+            const int nvq = nvalid - ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= (j < nvq) ? __ldg(il + j) : 0.f;
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *staged_chunk(buf, row_in_tile, q) = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
@@ -442,6 +478,81 @@ __global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __rest
     float l = 0.f;
     for (int t = 0; t < n_tiles; ++t) { const float2 v = p[static_cast<size_t>(t) * N]; l += v.y * ex2_approx(v.x - m); }
     stats[q] = make_float2(m, l);
+  }
+}
+
+// Cauchy-Schwarz row shift (inference fast path, no statistics pass): with d_i = S_ii * c (log2 units) and Q = K = F,
+//   d_i <= max_j S_ij * c <= sqrt(d_i * d_max),
+// so shift_i = sqrt(d_i * d_max) - 14 keeps p~ = exp2(S_ij*c - shift_i) <= 2^14 (no fp16 overflow) and every entry within
+// 2^-10 of the row maximum a normal fp16 as long as sqrt(d_i d_max) - d_i <= d_max / 4 <= 18, i.e. d_max <= 72 (S up to
+// ~50 in natural units; random-init / BN'd features give ~16).  Images above that limit take the exact max instead.
+constexpr float kShiftHeadroom = 14.0f, kSafeDiagMax = 72.0f;
+
+__global__ void __launch_bounds__(256) diag_kernel(const __half* __restrict__ fh, float* __restrict__ diag, int dk, float c, int64_t rows) {
+  // one warp per row, 4 rows per warp in flight
+  const int lane = threadIdx.x & 31;
+  const int64_t r0 = (blockIdx.x * 8LL + (threadIdx.x >> 5)) * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < dk / 8; k += 32) {
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = (r0 + q < rows) ? __ldg(reinterpret_cast<const uint4*>(fh + (r0 + q) * dk) + k) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        s[q] = fmaf(t.x, t.x, fmaf(t.y, t.y, s[q]));
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float t = warp_sum(s[q]) * c;
+    if (lane == 0 && r0 + q < rows) diag[r0 + q] = t;
+  }
+}
+
+// one CTA per image: d_max, then the row shifts and the per-image "bound is safe" flag
+__global__ void __launch_bounds__(256) shift_kernel(const float* __restrict__ diag, float2* __restrict__ stats, int* __restrict__ img_skip, int N) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float* d = diag + static_cast<size_t>(b) * N;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, d[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float dm = 0.f;
+  for (int i = 0; i < 8; ++i) dm = fmaxf(dm, red[i]);
+  for (int i = threadIdx.x; i < N; i += 256) stats[static_cast<size_t>(b) * N + i] = make_float2(sqrtf(d[i] * dm) - kShiftHeadroom, 0.f);
+  if (threadIdx.x == 0) img_skip[b] = (dm <= kSafeDiagMax) ? 1 : 0;
+}
+
+// images the bound is not safe for: shift_i = exact row maximum from the statistics-pass partials
+__global__ void __launch_bounds__(256) combine_max_kernel(const float2* __restrict__ part, const int* __restrict__ img_skip, float2* __restrict__ stats,
+                                                           int n_parts, int N, int64_t total) {
+  for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
+    const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
+    if (img_skip[b] != 0) continue;
+    const float2* p = part + static_cast<size_t>(b) * n_parts * N + i;
+    float m = -INFINITY;
+    for (int t = 0; t < n_parts; ++t) m = fmaxf(m, p[static_cast<size_t>(t) * N].x);
+    stats[q].x = m;
+  }
+}
+
+// l_i = sum of the partial sums of the rounded p~; stats <- (shift_i, l_i), inv_l <- 1 / l_i
+__global__ void __launch_bounds__(256) combine_l_kernel(const float* __restrict__ lpart, float2* __restrict__ stats, float* __restrict__ inv_l,
+                                                         int n_parts, int N, int64_t total) {
+  for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
+    const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
+    const float* p = lpart + static_cast<size_t>(b) * n_parts * N + i;
+    float l = 0.f;
+    for (int t = 0; t < n_parts; ++t) l += p[static_cast<size_t>(t) * N];
+    stats[q].y = l;
+    inv_l[q] = 1.0f / l;
   }
 }
 
@@ -572,7 +683,11 @@ struct Workspace {
   float* bins;     // [B, N]
   float* logbin;   // [B, N]
   float* lnz;      // [B, N]
-  float* kl_part;  // [B, ceil(N/kMinBN), N]
+  float* kl_part;  // [B, 2*ceil(N/kMinBN), N]   (also the l partials of the un-normalised probability pass)
+  float* diag;     // [B, N]  S_ii * c
+  float* inv_l;    // [B, N]
+  int* dmax_bits;  // [B]
+  int* img_skip;   // [B]
   size_t bytes;
 };
 
@@ -592,6 +707,10 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   w.logbin = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.lnz = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.kl_part = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
+  w.diag = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.inv_l = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.dmax_bits = reinterpret_cast<int*>(take(static_cast<size_t>(B) * 4));
+  w.img_skip = reinterpret_cast<int*>(take(static_cast<size_t>(B) * 4));
   w.bytes = off;
   return w;
 }
@@ -689,6 +808,51 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
   return 0;
 }
 
+// Inference fast path over S = Fh Fh^T: no statistics pass.  Row shifts come from the Cauchy-Schwarz bound (diag_kernel,
+// shift_kernel); the probability pass writes un-normalised fp16 p~ and per-row sums of exactly those rounded values; the
+// aggregation pass divides by them.  Images whose diagonal is too large for the bound (img_skip == 0) still get the exact
+// row maximum: the statistics kernel is launched for them alone (its tiles for the other images are skipped on device).
+int run_affinity_fast(const Workspace& w, const __half* fh, float2* stats, int B, int N, int dk, float scale, cudaStream_t st) {
+  const int cg = cta_group();
+  const int m_tiles = (N + BM * cg - 1) / (BM * cg);
+  const int bn = env_int("ACAN_BN_QK", choose_bn(N, B * m_tiles, cg, 64));
+  CUtensorMap ta, tb, tp;
+  if (int e = make_tmap(&ta, fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
+  if (int e = make_tmap(&tb, fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, bn / cg)) return e;
+  if (int e = make_tmap(&tp, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
+  GemmArgs g;
+  std::memset(&g, 0, sizeof(g));
+  g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = dk / BK;
+  g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = scale * kLog2e;
+  g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  const int grid_rows = static_cast<int>((rows + 255) / 256);
+  {
+    ProfScope ps(PROF_STATS, st);
+    diag_kernel<<<static_cast<int>((rows + 31) / 32), 256, 0, st>>>(fh, w.diag, dk, g.c, rows);
+    if (int e = launch_status("diag_kernel")) return e;
+    shift_kernel<<<B, 256, 0, st>>>(w.diag, stats, w.img_skip, N);
+    if (int e = launch_status("shift_kernel")) return e;
+    g.part = w.part;
+    g.img_skip = w.img_skip;
+    if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;
+    combine_max_kernel<<<grid_rows, 256, 0, st>>>(w.part, w.img_skip, stats, 2 * g.n_tiles, N, rows);
+    if (int e = launch_status("combine_max_kernel")) return e;
+  }
+  {
+    ProfScope ps(PROF_PROBS, st);
+    g.img_skip = nullptr;
+    g.stats = stats;
+    g.store_p = 1;
+    g.unnorm = 1;
+    g.lpart = w.kl_part;
+    if (int e = launch_gemm<MODE_PROBS>(ta, tb, tp, g, st, cg)) return e;
+    combine_l_kernel<<<grid_rows, 256, 0, st>>>(w.kl_part, stats, w.inv_l, 2 * g.n_tiles, N, rows);
+    if (int e = launch_status("combine_l_kernel")) return e;
+  }
+  return 0;
+}
+
 int prepare_target(const Workspace& w, const float* dis_label, int B, int H, int Wd, cudaStream_t st) {
   const int N = (H / 8) * (Wd / 8);
   nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, w.bins, B, H, Wd);
@@ -737,7 +901,12 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
 
   int nt = 0;
-  if (int e = run_affinity(w, w.fh, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  const bool fast = value && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  if (fast) {
+    if (int e = run_affinity_fast(w, w.fh, stats, B, N, dk, scale, st)) return e;
+  } else {
+    if (int e = run_affinity(w, w.fh, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  }
   ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
   if (dis_label) {
     ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
@@ -757,6 +926,7 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
     g.m_rows = dv; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = 0.f;
     g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
+    g.inv_l = fast ? w.inv_l : nullptr;
     ProfScope ps(PROF_PV, st);
     if (int e = launch_gemm<MODE_PV>(ta, tb, to, g, st, cg)) return e;
   }
@@ -795,7 +965,12 @@ extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, v
   if (dis_label)
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
   int nt = 0;
-  if (int e = run_affinity(w, fh, stats, value_h != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  const bool fast = value_h && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  if (fast) {
+    if (int e = run_affinity_fast(w, fh, stats, B, N, dk, scale, st)) return e;
+  } else {
+    if (int e = run_affinity(w, fh, stats, value_h != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+  }
   ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
   if (dis_label) {
     ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
@@ -816,6 +991,7 @@ extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, v
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (dv + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
     g.m_rows = N; g.n_cols = dv; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg, true); g.c = 0.f;
     g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
+    g.inv_l = fast ? w.inv_l : nullptr;
     ProfScope ps(PROF_PV, st);
     if (int e = launch_gemm<MODE_PVT>(ta, tb, to, g, st, cg)) return e;
   }

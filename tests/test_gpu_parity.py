@@ -243,11 +243,13 @@ def test_attention_full_size_properties():
     vv = v.reshape(b, 2048, -1)
     assert bool((ctx <= vv.max(-1, keepdim=True).values * (1 + 2e-3) + 1e-6).all()) and bool((ctx >= -1e-6).all())
     close(ctx, torch.matmul(vv, sim.transpose(1, 2)))
+    fast = ops.attention_forward(f, v)                                             # no sim_map requested: statistics-free fast path
+    close(fast["ctx"].reshape(b, 2048, -1), ctx, 5e-4)                             # same result as the exact-statistics path
     out2 = ops.attention_forward(f, 2.0 * v)
-    close(out2["ctx"].reshape(b, 2048, -1), 2.0 * ctx, 1e-6)                       # exactly linear in V (power-of-two scale)
+    close(out2["ctx"], 2.0 * fast["ctx"], 1e-6)                                    # exactly linear in V (power-of-two scale)
     perm = torch.randperm(b, device=DEV)
     out3 = ops.attention_forward(f[perm].contiguous(), v[perm].contiguous())
-    assert torch.equal(out3["ctx"], out["ctx"][perm])                             # images are independent units
+    assert torch.equal(out3["ctx"], fast["ctx"][perm])                            # images are independent units
 
 
 def test_attention_backward_against_oracle_autograd():
@@ -294,9 +296,41 @@ def test_sadecoder_module_against_reference_golden(golden, name):
     vis = sim.cpu()[:b][:, pts]                                                   # the vis_utils.py:107-121 access pattern
     dense = sim.materialize()
     close(dense.reshape(-1)[T(g["sim_idx"]).to(DEV)], T(g["sim_val"]))
-    close(vis, dense[:, pts].cpu(), 1e-4)          # CUDA-core row kernel vs tcgen05 tiles: same fp16 operands, different summation order
+    close(vis, dense[:, pts].cpu(), 5e-4)          # CUDA-core row kernel (row sums of the rounded fp16 p~) vs tcgen05 tiles (exact row sums)
     close(dense.sum(-1), T(g["sim_rowsum"]), 1e-5)
     assert dec.get_sim_map() is sim
+
+
+@pytest.mark.parametrize("b,h,w,gain", [(2, 4, 6, 1.0), (1, 28, 38, 1.0), (2, 32, 44, 1.0), (2, 20, 64, 3.0), (3, 8, 16, 2.5)])
+def test_attention_statistics_free_path(b, h, w, gain):
+    """Inference (no sim_map, no loss): row shifts from the Cauchy-Schwarz bound instead of a statistics pass, un-normalised
+    fp16 probabilities, normalisation in the aggregation epilogue.  gain > 1 scales F so that S_ii * log2(e) exceeds the
+    safe limit (72) and the per-image exact-max fallback runs -- for ALL images (gain 3) or for image 0 only (gain 2.5)."""
+    from acan_b200 import ops
+    n, dk, dv = h * w, 512, 2048
+    f = synth.feature_map(f"sf.f.{b}.{n}", b, dk, h, w)
+    v = synth.feature_map(f"sf.v.{b}.{n}", b, dv, h, w)
+    if gain == 3.0:
+        f = f * gain
+    elif gain != 1.0:
+        f[0] = f[0] * gain
+    sim = O.affinity(f.double())
+    ctx = O.aggregate(sim, v.double())
+    for cl in (False, True):
+        if cl:
+            out = ops.attention_forward_cl(f.half().to(DEV).contiguous(memory_format=torch.channels_last),
+                                           v.half().to(DEV).contiguous(memory_format=torch.channels_last))
+            want = O.aggregate(O.affinity(f.half().double()), v.half().double())
+        else:
+            out, want = ops.attention_forward(f.to(DEV), v.to(DEV)), ctx
+        assert out["sim_map"] is None
+        close(out["ctx"].float(), want)
+        st = out["row_stats"].double().cpu()                                      # (shift_i, l_i): P = exp2(S c - shift) / l still holds
+        lse = (st[..., 0] + torch.log2(st[..., 1])) * math.log(2.0)
+        ff = (f.half() if cl else f).double().reshape(b, dk, n)
+        close(lse, torch.logsumexp(torch.matmul(ff.transpose(1, 2), ff) * dk ** -0.5, -1), 5e-4)
+        rows = torch.tensor([0, n // 2, n - 1])
+        close(ops.attention_rows(out["ws"], rows), (O.affinity(f.half().double()) if cl else sim)[:, rows])
 
 
 @pytest.mark.parametrize("b,h,w", [(2, 4, 6), (1, 28, 38), (2, 32, 44)])
