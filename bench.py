@@ -110,7 +110,10 @@ def build_net(device):
     for m in bns:
         m.momentum = 0.1
     from acan_b200.inference import optimize_for_inference
-    return optimize_for_inference(net.eval())        # BN folded into the convolutions, fused conv epilogues, fp16 channels_last
+    net.eval()
+    fast = optimize_for_inference(net)               # BN folded into the convolutions, fused conv epilogues, fp16 channels_last
+    fast.source_state = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}   # for the CPU baseline (same weights)
+    return fast
 
 
 def step_device(net, images):
@@ -289,7 +292,7 @@ def main():
     }
 
     if world == 1 and not args.no_cpu_baseline:
-        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        sd = net.source_state
         threads = os.cpu_count() or 1
         times, d_cpu = cpu_reference_forward(sd, 60, 2, threads)
         out["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "images/s", "cores": threads, "kind": "port",
