@@ -38,6 +38,8 @@ SIGNATURES = {
     "acan_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "acan_attn_fwd": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_loss": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
+    "acan_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "acan_attn_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_nhwc_f16": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attention_loss": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_int, c_void_p]),

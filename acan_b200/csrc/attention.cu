@@ -27,6 +27,7 @@
 // the rounding of TF32, at the bf16 MMA rate) with fp32 accumulation; bf16 operands miss the 1e-3 parity
 // bar on sim_map.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -53,7 +54,8 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 // MODE_PV : O^T[dv, Nq] = V[dv, Nk] P[Nq, Nk]^T, both K-major (NCHW world), fp32 out.
 // MODE_PVT: O[Nq, dv]  = P[Nq, Nk] V[Nk, dv], B = V read in place from channels-last memory as an MN-major operand, fp16 out.
-enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2, MODE_PVT = 3 };
+// MODE_DS : backward: acc = dP[Nq, Nk] = dO^T V; epilogue dS = P o (dP - delta_i) (+ attention-loss term), scaled fp16 out.
+enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2, MODE_PVT = 3, MODE_DS = 4 };
 
 constexpr int kOutChunkBytes = 128 * 128;   // epilogue staging: 128 rows x 128 B (one SWIZZLE_128B TMA-store box)
 constexpr int kOutBuffers = 2;          // TMA-store staging ring (4 buffers measured slower: they cost an operand stage)
@@ -70,6 +72,11 @@ struct GemmArgs {
   const int* img_skip; // MODE_STATS: images whose flag is non-zero need no statistics pass (their tiles are skipped by all roles)
   int unnorm;          // MODE_PROBS: write p~ = exp2(S*c - shift_i) un-normalised and emit per-row partial sums of the ROUNDED values
   float* lpart;        //   [B, 2*n_tiles, N] those partial sums
+  const float* ds_delta; // MODE_DS: [B, N] delta_i = sum_c dO[c,i] O[c,i]
+  const __half* ds_p;    //   [B, N, N] fp16 probabilities
+  const float* ds_klT;   //   [B, N] in-window target mass T_i (attention-loss term), with logbin / lnz above
+  float ds_gk;           //   dLoss/dloss3 / (B N)
+  const float* gscale; // backward: device pair (s, 1/s), the power-of-two gradient scale that keeps fp16 dO / dS in range
   const float* inv_l;  // MODE_PV / MODE_PVT: [B, N] 1 / l_i applied per query while the accumulator leaves TMEM (null = already normalised)
   long long* trace;    // experiments only (ACAN_TRACE=1): per-tile clock64 stamps of CTA 0: [tile][4] = mma start, mma issued, epi start, epi end
   // MODE_STATS
@@ -80,7 +87,8 @@ struct GemmArgs {
   float* sim_out;      // [B, N, N] fp32 or null (rare path: plain vector stores)
   const float* logbin; // [B, N] ln(bin) (-inf for bin 0) or null  -> fused KL
   const float* lnz;    // [B, N] ln(Z_i) of the target affinity (unused when bin_i == 0)
-  float* kl_part;      // [B, n_tiles, N] per-row partial losses
+  float* kl_part;      // [B, 2*n_tiles, N] per-row partial losses
+  float* klw_part;     // null, or [B, 2*n_tiles, N] per-row partial sums of the in-window target mass T_i (backward)
 };
 
 struct __align__(8) PipeBarriers {
@@ -104,7 +112,8 @@ __device__ __forceinline__ uint4* staged_chunk(uint8_t* buf, int r, int j) {
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues M = 256 MMAs that read both
 // shared memories and write both TMEMs, so the L2 -> SM operand traffic per FLOP drops by (128+BN)/(128+BN/2).
-template <int MODE, int CG>
+// AMN / BMN: that operand is read as an MN-major tile (64-element-wide {MN x 64 K-row} TMA boxes, 8 KB apart).
+template <int MODE, int CG, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
@@ -159,8 +168,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           if (CG == 1) {
             mbar_expect_tx(&bars->full[stage], stage_bytes);
-            tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, a_row, b);
-            if constexpr (MODE == MODE_PVT) {      // MN-major B: one {64 channels x 64 keys} box per 64 channels
+            if constexpr (AMN) {                   // MN-major A: two {64 rows-of-A x 64 k} boxes
+              for (uint32_t s = 0; s < BM / 64; ++s)
+                tma_load_3d(sa + s * 8192, &tmap_a, &bars->full[stage], a_row + static_cast<int>(s) * 64, ks * BK, b);
+            } else {
+              tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, a_row, b);
+            }
+            if constexpr (BMN) {                   // MN-major B: one {64 rows-of-B x 64 k} box per 64 rows
               for (uint32_t s = 0; s < b_rows / 64; ++s)
                 tma_load_3d(sa + a_bytes + s * 8192, &tmap_b, &bars->full[stage], b_row + static_cast<int>(s) * 64, ks * BK, b);
             } else {
@@ -170,8 +184,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             // both CTAs' bytes complete on the LEADER's barrier; the leader arms it for the pair's total
             if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], stage_bytes * 2);
             const uint32_t leader_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
-            tma_load_3d_2sm(sa, &tmap_a, leader_bar, ks * BK, a_row, b);
-            if constexpr (MODE == MODE_PVT) {
+            if constexpr (AMN) {
+              for (uint32_t s = 0; s < BM / 64; ++s)
+                tma_load_3d_2sm(sa + s * 8192, &tmap_a, leader_bar, a_row + static_cast<int>(s) * 64, ks * BK, b);
+            } else {
+              tma_load_3d_2sm(sa, &tmap_a, leader_bar, ks * BK, a_row, b);
+            }
+            if constexpr (BMN) {
               for (uint32_t s = 0; s < b_rows / 64; ++s)
                 tma_load_3d_2sm(sa + a_bytes + s * 8192, &tmap_b, leader_bar, b_row + static_cast<int>(s) * 64, ks * BK, b);
             } else {
@@ -199,8 +218,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_k_sw128(sa + k * UMMA_K * 2);
-            const uint64_t db = (MODE == MODE_PVT) ? umma_desc_mn_sw128(sb + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sb + k * UMMA_K * 2);
+            const uint64_t da = AMN ? umma_desc_mn_sw128(sa + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sa + k * UMMA_K * 2);
+            const uint64_t db = BMN ? umma_desc_mn_sw128(sb + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sb + k * UMMA_K * 2);
             if (CG == 1) umma_f16(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
             else         umma_f16_2sm(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
           }
@@ -279,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const bool kl = g.logbin != nullptr;
         bool kl_row = false;
         if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; kl_row = row_ok && la_i > -INFINITY; }
-        float kl_acc = 0.f;
+        float kl_acc = 0.f, klw_acc = 0.f;
         const float* la_cols = kl ? g.logbin + static_cast<size_t>(b) * g.n_cols + col0 : nullptr;
         float* srow = g.sim_out ? g.sim_out + (brow * g.n_cols + col0) : nullptr;
         // 64 columns (= 128 B of fp16) per staged TMA store; this group takes every other 64-column chunk
@@ -309,6 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     const float w = ex2_approx(lnw * kLog2e);                    // 0 when a_j = 0
                     const float lr = fminf(fmaxf(lnw - lnq, -18.420680744f), 18.420680744f);   // ln clamp(W/Q, 1e-8, 1e8)
                     kl_acc += (w > 0.f) ? w * lr : 0.f;
+                    klw_acc += (w > 0.f && fabsf(lnw - lnq) < 18.420680744f) ? w : 0.f;
                   }
                 }
               }
@@ -358,7 +378,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
         if (kl && row_ok) g.kl_part[part_idx] = kl_acc;
+        if (kl && g.klw_part && row_ok) g.klw_part[part_idx] = klw_acc;
         if (g.unnorm && row_ok) g.lpart[part_idx] = l_acc;
+      } else if constexpr (MODE == MODE_DS) {
+        // acc = dP_ij.  dS_ij = P_ij (dP_ij - delta_i) - gk (W_ij [in clamp window] - P_ij T_i),  gk = dLoss/dloss3 / (B N)
+        const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
+        const float gs = g.gscale ? __ldg(g.gscale) : 1.0f;          // dP already carries the scale (dO was packed scaled)
+        const float delta_i = g.ds_delta[brow] * gs;
+        const float gks = g.ds_gk * gs;
+        const bool kl = g.logbin != nullptr;
+        float la_i = 0.f, lnz_i = 0.f, t_i = 0.f;
+        if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; t_i = g.ds_klT[brow]; }
+        const bool kl_row = kl && la_i > -INFINITY;
+        const float* la_cols = kl ? g.logbin + static_cast<size_t>(b) * g.n_cols + col0 : nullptr;
+        const __half* prow = g.ds_p + (brow * g.n_cols + col0);
+        for (int ch = 2 * group; ch < chunks; ch += 4) {
+          if (store_leader) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int chh = ch + half;
+            if (chh < chunks) {
+              float v[32];
+              tmem_ld_32x32(taddr + chh * 32, v);
+              tmem_ld_wait();
+              const int nv = nvalid - chh * 32;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pu = make_uint4(0, 0, 0, 0);
+                if (row_ok && q * 8 < nv) pu = __ldg(reinterpret_cast<const uint4*>(prow + chh * 32) + q);
+                const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 pp = __half22float2(*reinterpret_cast<const __half2*>(&pw[e]));
+                  const int j = q * 8 + e * 2;
+                  float d0 = pp.x * (v[j] - delta_i), d1 = pp.y * (v[j + 1] - delta_i);
+                  if (kl_row) {
+                    const float lw0 = -fabsf(la_i - __ldg(la_cols + chh * 32 + j)) - lnz_i, lw1 = -fabsf(la_i - __ldg(la_cols + chh * 32 + j + 1)) - lnz_i;
+                    const float w0 = ex2_approx(lw0 * kLog2e), w1 = ex2_approx(lw1 * kLog2e);
+                    const float lq0 = lg2_approx(pp.x) * kLn2, lq1 = lg2_approx(pp.y) * kLn2;
+                    const float in0 = (w0 > 0.f && fabsf(lw0 - lq0) < 18.420680744f) ? w0 : 0.f;
+                    const float in1 = (w1 > 0.f && fabsf(lw1 - lq1) < 18.420680744f) ? w1 : 0.f;
+                    d0 -= gks * (in0 - pp.x * t_i);
+                    d1 -= gks * (in1 - pp.y * t_i);
+                  } else if (kl) {
+                    // all-zero target row: only the softmax coupling term survives (T_i = 0 -> nothing)
+                  }
+                  v[j] = d0; v[j + 1] = d1;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  o[e] = pack_half2(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+                }
+                *staged_chunk(buf, row_in_tile, half * 4 + q) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (store_leader) {
+            tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
+            tma_store_commit();
+          }
+        }
       } else if constexpr (MODE == MODE_PVT) {   // rows = query positions, columns = value channels; 64 fp16 columns per staged store
         const float rs = g.inv_l ? __ldg(g.inv_l + static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0)) : 1.0f;
         for (int ch = 2 * group; ch < chunks; ch += 4) {
@@ -393,6 +479,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           float v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
           tmem_ld_wait();
+          if (g.gscale) {                                 // backward outputs: undo the gradient scale
+            const float us = __ldg(g.gscale + 1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= us;
+          }
           if (g.inv_l) {                                  // columns are the queries here
             const float* il = g.inv_l + static_cast<size_t>(b) * g.n_cols + col0 + ch * 32;
             const int nvq = nvalid - ch * 32;
@@ -556,6 +647,103 @@ __global__ void __launch_bounds__(256) combine_l_kernel(const float* __restrict_
   }
 }
 
+// ---- backward helpers
+// fp32 -> fp16 / bf16, same layout (clamped to the fp16 range for fp16)
+template <bool BF16>
+__global__ void __launch_bounds__(256) pack_cast_kernel(const float4* __restrict__ v, uint4* __restrict__ out, int64_t n8, const float* __restrict__ gscale) {
+  const float sc = gscale ? __ldg(gscale) : 1.0f;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
+    float4 a = ldg_stream(v + 2 * i), b = ldg_stream(v + 2 * i + 1);
+    a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc; b.x *= sc; b.y *= sc; b.z *= sc; b.w *= sc;
+    if (BF16) {
+      auto pk = [](float x, float y) { const __nv_bfloat162 h = __floats2bfloat162_rn(x, y); return *reinterpret_cast<const uint32_t*>(&h); };
+      out[i] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), pk(b.z, b.w));
+    } else {
+      auto cl = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
+      out[i] = make_uint4(pack_half2(cl(a.x), cl(a.y)), pack_half2(cl(a.z), cl(a.w)), pack_half2(cl(b.x), cl(b.y)), pack_half2(cl(b.z), cl(b.w)));
+    }
+  }
+}
+
+// delta[b,i] = sum_c dO[b,c,i] * O[b,c,i]   (= sum_j P_ij dP_ij, the softmax-backward row term)
+__global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ go, const float* __restrict__ o, float* __restrict__ delta,
+                                                     int* __restrict__ amax_bits, int C, int N) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y, i = blockIdx.x * 32 + (threadIdx.x & 31), wv = threadIdx.x >> 5;
+  float s = 0.f, am = 0.f;
+  if (i < N) {
+    const size_t base = static_cast<size_t>(b) * C * N + i;
+    for (int c = wv; c < C; c += 8) {
+      const float gv = __ldg(go + base + static_cast<size_t>(c) * N);
+      s = fmaf(gv, __ldg(o + base + static_cast<size_t>(c) * N), s);
+      am = fmaxf(am, fabsf(gv));
+    }
+  }
+  am = warp_max(am);
+  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_int(am));   // |dO| max over the tensor (one atomic per warp)
+  red[wv][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (wv == 0 && i < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    delta[static_cast<size_t>(b) * N + i] = t;
+  }
+}
+
+// out[q] = sum_t parts[b, t, i]
+__global__ void __launch_bounds__(256) sum_parts_kernel(const float* __restrict__ parts, float* __restrict__ out, int n_parts, int N, int64_t total) {
+  for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
+    const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
+    const float* p = parts + static_cast<size_t>(b) * n_parts * N + i;
+    float s = 0.f;
+    for (int t = 0; t < n_parts; ++t) s += p[static_cast<size_t>(t) * N];
+    out[q] = s;
+  }
+}
+
+// (s, 1/s): power of two that brings amax |dO| to 2^-2, or a host-chosen value when amax_bits is null
+__global__ void gscale_kernel(const int* __restrict__ amax_bits, float host_scale, float* __restrict__ sc) {
+  float s = host_scale;
+  if (amax_bits != nullptr) {
+    const float am = __int_as_float(*amax_bits);
+    s = (am > 0.f && am < INFINITY) ? exp2f(-2.0f - ceilf(log2f(am))) : 1.0f;
+  }
+  sc[0] = s;
+  sc[1] = 1.0f / s;
+}
+
+__global__ void __launch_bounds__(256) scaled_sum_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, float scale_in,
+                                                          const float* __restrict__ gscale, int64_t n4) {
+  const float scale = scale_in * __ldg(gscale + 1);
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(scale * (x.x + y.x), scale * (x.y + y.y), scale * (x.z + y.z), scale * (x.w + y.w));
+  }
+}
+
+// attention-loss-only dS (no aggregation gradient): dS_ij = -gk (W_ij [in window] - P_ij T_i), one CTA per row, scaled fp16 out
+__global__ void __launch_bounds__(256) kl_ds_kernel(const __half* __restrict__ p, const float* __restrict__ logbin, const float* __restrict__ lnz,
+                                                     const float* __restrict__ klT, __half* __restrict__ ds, float gk, int N) {
+  const int64_t row = blockIdx.x;
+  const int b = static_cast<int>(row / N);
+  const float la_i = logbin[row], lnz_i = lnz[row], t_i = klT[row];
+  const float* la = logbin + static_cast<size_t>(b) * N;
+  const __half* pr = p + row * N;
+  __half* dr = ds + row * N;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    const float pv = __half2float(pr[j]);
+    float d = 0.f;
+    if (la_i > -INFINITY) {
+      const float lw = -fabsf(la_i - la[j]) - lnz_i;
+      const float w = ex2_approx(lw * kLog2e);
+      const float in = (w > 0.f && fabsf(lw - lg2_approx(pv) * kLn2) < 18.420680744f) ? w : 0.f;
+      d = -gk * (in - pv * t_i);
+    }
+    dr[j] = __float2half_rn(d);
+  }
+}
+
 // per row: ln(bin) and ln(Z_i), Z_i = sum_j min(a_i/a_j, a_j/a_i)   (target-affinity normaliser, losses.py:40-46)
 __global__ void __launch_bounds__(256) gt_norm_kernel(const float* __restrict__ bins, float* __restrict__ logbin, float* __restrict__ lnz, int N) {
   __shared__ float red[8];
@@ -715,7 +903,7 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   return w;
 }
 
-template <int MODE, int CG>
+template <int MODE, int CG, bool AMN, bool BMN>
 int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st) {
   const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + static_cast<size_t>(g.bn / CG) * BK * 2;
   int stages = static_cast<int>((kSmemBudget - kOutBuffers * kOutChunkBytes) / stage_bytes);
@@ -724,7 +912,7 @@ int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const size_t smem = stages * stage_bytes + kOutBuffers * kOutChunkBytes + sizeof(PipeBarriers) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ACAN_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ACAN_CUDA((cudaFuncSetAttribute(gemm_kernel<MODE, CG, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
     attr_set = true;
   }
   const int tiles = g.batch * g.m_tiles * g.n_tiles;
@@ -739,14 +927,14 @@ int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG>, ta, tb, tout, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG, AMN, BMN>, ta, tb, tout, g);
   if (e != cudaSuccess) return fail((int)e, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return launch_status("acan gemm_kernel");
 }
 
-template <int MODE>
+template <int MODE, bool AMN = false, bool BMN = (MODE == MODE_PVT)>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st, int cg) {
-  return cg == 2 ? launch_gemm_cg<MODE, 2>(ta, tb, tout, g, st) : launch_gemm_cg<MODE, 1>(ta, tb, tout, g, st);
+  return cg == 2 ? launch_gemm_cg<MODE, 2, AMN, BMN>(ta, tb, tout, g, st) : launch_gemm_cg<MODE, 1, AMN, BMN>(ta, tb, tout, g, st);
 }
 
 int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
@@ -759,7 +947,7 @@ int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
 
 // passes 1+2 over S = Fh Fh^T: statistics, then probabilities / sim_map / fused KL
 int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_p, float* sim_map, bool kl, int B, int N, int dk, float scale, cudaStream_t st,
-                 bool need_stats, int* key_tiles) {
+                 bool need_stats, int* key_tiles, float* klw_part = nullptr) {
   const int cg = cta_group();
   const int m_tiles = (N + BM * cg - 1) / (BM * cg);
   const int bn = env_int("ACAN_BN_QK", choose_bn(N, B * m_tiles, cg, 64));   // P leaves in 64-column (128 B) TMA-store boxes
@@ -786,6 +974,7 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
     g.logbin = kl ? w.logbin : nullptr;
     g.lnz = w.lnz;
     g.kl_part = w.kl_part;
+    g.klw_part = klw_part;
     static long long* trace_buf = nullptr;
     if (env_int("ACAN_TRACE", 0) && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
     g.trace = env_int("ACAN_TRACE", 0) ? trace_buf : nullptr;
@@ -1022,4 +1211,174 @@ extern "C" int acan_attention_loss_fused(void* workspace, const void* feat_pack,
   if (int e = run_affinity(w, fh, w.stats, false, nullptr, true, B, N, dk, scale, st, false, &nt)) return e;
   ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
   return launch_status("ordered_sum_kernel");
+}
+
+// ------------------------------------------------------------------------------------ backward
+namespace acan {
+namespace {
+
+struct BwdWorkspace {
+  Workspace f;             // forward-style scratch: fh, vh, p, part, stats, bins, logbin, lnz, kl_part, ...
+  __half* doh;             // [B, dv, N] fp16   grad_ctx
+  __half* ds;              // [B, N, N]  fp16   dS * s  (s = power-of-two gradient scale)
+  __half* fb;              // [B, dk, N] fp16   F in its NCHW layout (A operand of the dF GEMMs)
+  float* gscale;           // [2]  (s, 1/s)
+  int* amax_bits;          // [1]  max |dO| as int bits
+  float* klw_part;         // [B, 2*ceil(N/64), N]
+  float* klT;              // [B, N]
+  float* delta;            // [B, N]
+  float* df1;              // [B, dk, N]
+  float* df2;              // [B, dk, N]
+  size_t bytes;
+};
+
+BwdWorkspace carve_bwd(void* base, int B, int N, int dk, int dv) {
+  BwdWorkspace w;
+  w.f = carve(base, B, N, dk, dv);
+  size_t off = w.f.bytes;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return reinterpret_cast<uint8_t*>(base) + o; };
+  const size_t nt_max = 2 * ((N + kMinBN - 1) / kMinBN);
+  w.doh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * dv * N * 2));
+  w.ds = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * N * 2));
+  w.fb = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * dk * N * 2));
+  w.gscale = reinterpret_cast<float*>(take(16));
+  w.amax_bits = reinterpret_cast<int*>(take(16));
+  w.klw_part = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
+  w.klT = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.delta = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.df1 = reinterpret_cast<float*>(take(static_cast<size_t>(B) * dk * N * 4));
+  w.df2 = reinterpret_cast<float*>(take(static_cast<size_t>(B) * dk * N * 4));
+  w.bytes = off;
+  return w;
+}
+
+int cast_launch(const float* src, void* dst, int64_t n, const float* gscale, cudaStream_t st, const char* what) {
+  const int64_t n8 = n / 8;
+  int64_t blocks = (n8 + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pack_cast_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n8, gscale);
+  return launch_status(what);
+}
+
+GemmArgs gemm_args(int B, int m_rows, int n_cols, int k, int bn, int cg, uint32_t idesc) {
+  GemmArgs g;
+  std::memset(&g, 0, sizeof(g));
+  g.batch = B; g.m_tiles = (m_rows + BM * cg - 1) / (BM * cg); g.n_tiles = (n_cols + bn - 1) / bn; g.k_steps = (k + BK - 1) / BK;
+  g.m_rows = m_rows; g.n_cols = n_cols; g.bn = bn; g.idesc = idesc;
+  return g;
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" size_t acan_attn_bwd_workspace_bytes(int B, int N, int dk, int dv) {
+  if (B <= 0 || N <= 0 || dk <= 0 || dv <= 0) return 0;
+  return carve_bwd(nullptr, B, N, dk, dv).bytes;
+}
+
+// Gradients of ctx = aggregate(softmax(F^T F scale), V) (+ grad_loss * attention loss) w.r.t. F and V, on tcgen05.
+//   dV = dO P        dP = dO^T V        dS = P o (dP - delta) [+ loss term]        dF = scale * F (dS + dS^T)
+extern "C" int acan_attn_bwd(const float* feat, const float* value, const float* ctx, const float* row_stats, const float* grad_ctx,
+                             const float* dis_label, int H, int Wd, float grad_loss,
+                             float* grad_feat, float* grad_value, void* workspace, size_t workspace_bytes,
+                             int B, int N, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(feat && row_stats && grad_feat && workspace, "acan_attn_bwd: null pointer");
+  const bool agg = grad_ctx != nullptr;           // aggregation gradient present (else: attention-loss gradient only)
+  ACAN_CHECK_ARG(!agg || (value && ctx && grad_value), "acan_attn_bwd: value, ctx and grad_value are required with grad_ctx");
+  ACAN_CHECK_ARG(agg || dis_label, "acan_attn_bwd: nothing to differentiate (no grad_ctx, no label)");
+  if (int e = check_attn_shape("acan_attn_bwd", B, N, dk, dv)) return e;
+  ACAN_CHECK_ARG(N % 8 == 0 && (static_cast<int64_t>(dk) * N) % 8 == 0, "acan_attn_bwd: N must be a multiple of 8");
+  ACAN_CHECK_ARG(!dis_label || (H / 8) * (Wd / 8) == N, "acan_attn_bwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "acan_attn_bwd: workspace must be 1024-byte aligned");
+  const BwdWorkspace w = carve_bwd(workspace, B, N, dk, dv);
+  if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_bwd: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+  if (int e = acan_device_check()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cg = cta_group();
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  const int grid_rows = static_cast<int>((rows + 255) / 256);
+
+  // operand packs
+  pack_feat_kernel<<<dim3((N + 63) / 64, dk / 64, B), 256, 0, st>>>(feat, w.f.fh, dk, N);
+  if (int e = launch_status("pack_feat_kernel")) return e;
+  if (int e = cast_launch(feat, w.fb, static_cast<int64_t>(B) * dk * N, nullptr, st, "pack F (NCHW fp16)")) return e;
+  const float gk = dis_label ? grad_loss / (static_cast<float>(B) * static_cast<float>(N)) : 0.f;
+  if (agg) {
+    // delta_i and max |dO| in one pass over dO; the power-of-two scale s keeps fp16 dO and dS in range whatever the loss scale
+    ACAN_CUDA(cudaMemsetAsync(w.amax_bits, 0, 4, st));
+    delta_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(grad_ctx, ctx, w.delta, w.amax_bits, dv, N);
+    if (int e = launch_status("delta_kernel")) return e;
+    gscale_kernel<<<1, 1, 0, st>>>(w.amax_bits, 1.0f, w.gscale);
+    if (int e = launch_status("gscale_kernel")) return e;
+    if (int e = cast_launch(value, w.f.vh, static_cast<int64_t>(B) * dv * N, nullptr, st, "pack V")) return e;
+    if (int e = cast_launch(grad_ctx, w.doh, static_cast<int64_t>(B) * dv * N, w.gscale, st, "pack dO")) return e;
+  } else {
+    // loss-only: |dS| <= gk, bring it to ~1
+    gscale_kernel<<<1, 1, 0, st>>>(nullptr, std::exp2(-std::ceil(std::log2(std::fabs(gk) > 0.f ? std::fabs(gk) : 1.0f))), w.gscale);
+    if (int e = launch_status("gscale_kernel")) return e;
+  }
+  // normalised P from the saved statistics (+ in-window target mass T_i for the loss term)
+  ACAN_CUDA(cudaMemcpyAsync(w.f.stats, row_stats, static_cast<size_t>(rows) * 8, cudaMemcpyDeviceToDevice, st));
+  if (dis_label)
+    if (int e = prepare_target(w.f, dis_label, B, H, Wd, st)) return e;
+  int parts = 0;
+  if (int e = run_affinity(w.f, w.f.fh, w.f.stats, true, nullptr, dis_label != nullptr, B, N, dk, scale, st, false, &parts, w.klw_part)) return e;
+  if (dis_label) {
+    sum_parts_kernel<<<grid_rows, 256, 0, st>>>(w.klw_part, w.klT, parts, N, rows);
+    if (int e = launch_status("sum_parts_kernel")) return e;
+  }
+  CUtensorMap ta, tb, to;
+
+  if (agg) {
+    {  // dV[c, j] = sum_i dO[c, i] P[i, j]: A = dOh (K-major over i), B = P read MN-major (j contiguous), fp32 NCHW out
+      const int m_tiles = (dv + BM * cg - 1) / (BM * cg);
+      const int bn = choose_bn(N, B * m_tiles, cg, 64 * cg, 64 * cg);
+      if (int e = make_tmap(&ta, w.doh, 2, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, BM)) return e;
+      if (int e = make_tmap(&tb, w.f.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, 64)) return e;
+      if (int e = make_tmap(&to, grad_value, 4, N, dv, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dv) * N * 4, BM)) return e;
+      GemmArgs g = gemm_args(B, dv, N, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, false, false));
+      g.gscale = w.gscale;
+      if (int e = launch_gemm<MODE_PV, false, true>(ta, tb, to, g, st, cg)) return e;
+    }
+    {  // dP[i, j] = sum_c dO[c, i] V[c, j] (both operands MN-major from their NCHW packs) -> dS epilogue, scaled fp16 out
+      const int m_tiles = (N + BM * cg - 1) / (BM * cg);
+      const int bn = choose_bn(N, B * m_tiles, cg, 64 * cg, 64 * cg);
+      if (int e = make_tmap(&ta, w.doh, 2, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, 64)) return e;
+      if (int e = make_tmap(&tb, w.f.vh, 2, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, 64)) return e;
+      if (int e = make_tmap(&to, w.ds, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
+      GemmArgs g = gemm_args(B, N, N, dv, bn, cg, umma_idesc_f16(bn, BM * cg, true, true, false));
+      g.ds_delta = w.delta; g.ds_p = w.f.p; g.ds_klT = w.klT; g.ds_gk = gk; g.gscale = w.gscale;
+      g.logbin = dis_label ? w.f.logbin : nullptr; g.lnz = w.f.lnz;
+      if (int e = launch_gemm<MODE_DS, true, true>(ta, tb, to, g, st, cg)) return e;
+    }
+  } else {
+    kl_ds_kernel<<<static_cast<int>(rows), 256, 0, st>>>(w.f.p, w.f.logbin, w.f.lnz, w.klT, w.ds,
+                                                         gk * std::exp2(-std::ceil(std::log2(std::fabs(gk) > 0.f ? std::fabs(gk) : 1.0f))), N);
+    if (int e = launch_status("kl_ds_kernel")) return e;
+  }
+  {  // dF[c, i] = scale / s * sum_j (dS[i, j] + dS[j, i]) F[c, j]: two fp16 GEMMs over the same (scaled) dS buffer
+    const int m_tiles = (dk + BM * cg - 1) / (BM * cg);
+    if (int e = make_tmap(&ta, w.fb, 2, N, dk, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dk) * N * 2, BM)) return e;
+    {
+      const int bn = choose_bn(N, B * m_tiles, cg, 32);
+      if (int e = make_tmap(&tb, w.ds, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, bn / cg)) return e;
+      if (int e = make_tmap(&to, w.df1, 4, N, dk, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dk) * N * 4, BM)) return e;
+      GemmArgs g = gemm_args(B, dk, N, N, bn, cg, umma_idesc_f16(bn, BM * cg, false, false, false));
+      if (int e = launch_gemm<MODE_PV, false, false>(ta, tb, to, g, st, cg)) return e;       // sum_j F[c,j] dS[i,j]
+    }
+    {
+      const int bn = choose_bn(N, B * m_tiles, cg, 64 * cg, 64 * cg);
+      if (int e = make_tmap(&tb, w.ds, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, 64)) return e;
+      if (int e = make_tmap(&to, w.df2, 4, N, dk, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dk) * N * 4, BM)) return e;
+      GemmArgs g = gemm_args(B, dk, N, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, false, false));
+      if (int e = launch_gemm<MODE_PV, false, true>(ta, tb, to, g, st, cg)) return e;        // sum_j F[c,j] dS[j,i]
+    }
+    const int64_t n4 = static_cast<int64_t>(B) * dk * N / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    scaled_sum_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(w.df1), reinterpret_cast<const float4*>(w.df2),
+                                                                reinterpret_cast<float4*>(grad_feat), scale, w.gscale, n4);
+    if (int e = launch_status("scaled_sum_kernel")) return e;
+  }
+  return 0;
 }

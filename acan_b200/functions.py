@@ -3,9 +3,9 @@
 Forward passes are the hand-written kernels of ``csrc/`` (through the C ABI).  Backward:
   * decode_ord        -- CUDA kernel (``acan_decode_ord_bwd``)
   * attention loss    -- CUDA kernel (gradient w.r.t. sim_map comes out of ``acan_attention_loss``)
-  * attention core    -- round 1: sim_map is re-materialised by the tcgen05 kernels and the three gradient
-                         GEMMs (dV, dP, dF) are cuBLAS calls through torch.matmul; the tcgen05 backward is the
-                         next row (DESIGN.md §"what comes next").  No CPU path anywhere.
+  * attention core    -- tcgen05 kernels (``acan_attn_bwd``): P recomputed from the saved row statistics, dV and dP as
+                         TMA/UMMA GEMMs, dS (with the attention-loss term) formed in the dP epilogue, dF from two bf16 GEMMs
+                         over dS and its transpose (read in place as an MN-major operand).  No CPU path anywhere.
 The reference has no custom Function: gradients follow what autograd derives for
 sadecoder.py:42-49,80-90 and losses.py:18-33, including Q and K sharing F (dF gets both sides of dS).
 """
@@ -73,6 +73,7 @@ class Attention(torch.autograd.Function):
     forward(feat [B,dk,h,w], value [B,dv,h,w], dis_label [B,1,H,W] | None, holder)
       -> (context [B,dv,h,w], loss 0-dim (0 when no label))
     ``holder`` is a python object that receives ``.ws`` (operand pack / statistics) for lazy sim_map access.
+    backward: acan_attn_bwd (tcgen05: dV, dP -> dS with the loss term fused, dF).
     """
 
     @staticmethod
@@ -81,32 +82,22 @@ class Attention(torch.autograd.Function):
         holder.ws = out["ws"]
         holder.row_stats = out["row_stats"]
         holder.gen = getattr(holder, "gen", 0) + 1
-        ctx.save_for_backward(feat, value, dis_label if dis_label is not None else torch.empty(0, device=feat.device))
+        ctx.save_for_backward(feat, value, out["ctx"], out["row_stats"], dis_label if dis_label is not None else torch.empty(0, device=feat.device))
         loss = out["loss"] if out["loss"] is not None else torch.zeros((), device=feat.device)
         return out["ctx"], loss
 
     @staticmethod
     def backward(ctx, grad_ctx, grad_loss):
-        feat, value, dis_label = ctx.saved_tensors
-        b, dk, h, w = feat.shape
-        n = h * w
-        dv = value.shape[1]
-        sim = ops.attention_forward(feat, None, want_sim_map=True)["sim_map"]          # tcgen05 re-materialisation
-        go = grad_ctx.reshape(b, dv, n).float()
-        v = value.reshape(b, dv, n).float()
-        f = feat.reshape(b, dk, n).float()
-        g_value = torch.matmul(go, sim)                                                # dV[c,j] = sum_i dO[c,i] P[i,j]
-        dp = torch.matmul(go.transpose(1, 2), v)                                       # dP[i,j] = sum_c dO[c,i] V[c,j]
-        if dis_label.numel():
-            _, gq = ops.attention_loss(sim, dis_label, want_grad=True)                 # CUDA: dL/dQ with the clamp window
-            dp = dp + gq * grad_loss
-        ds = _softmax_backward(sim, dp)
-        g_feat = torch.matmul(f, ds + ds.transpose(1, 2)) * (dk ** -0.5)               # Q and K are both F
+        feat, value, out, row_stats, dis_label = ctx.saved_tensors
+        lab = dis_label if dis_label.numel() else None
+        g_feat, g_value = ops.attention_backward(feat, row_stats, value, out, grad_ctx, lab, float(grad_loss) if lab is not None else 0.0)
         return g_feat.view_as(feat), g_value.view_as(value), None, None
 
 
 class SimMap(torch.autograd.Function):
-    """sim_map [B,N,N] materialised on request (forward_att, sadecoder.py:42-49)."""
+    """sim_map [B,N,N] materialised on request (forward_att, sadecoder.py:42-49).  Backward through a dense, caller-made
+    gradient w.r.t. sim_map is the one place left on cuBLAS (nobody on the reference's path differentiates a materialised
+    sim_map except the attention loss, which has its own fused backward)."""
 
     @staticmethod
     def forward(ctx, feat):

@@ -431,15 +431,12 @@ class FusedAttentionLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, dis_label, lazy):
         ctx.save_for_backward(feat, dis_label)
-        return ops.attention_loss_fused(lazy._ws(), dis_label)
+        ws = lazy._ws()
+        ctx.row_stats = lazy._holder.row_stats if ws is lazy._holder.ws else ops.attention_forward(feat.float(), None)["row_stats"]
+        return ops.attention_loss_fused(ws, dis_label)
 
     @staticmethod
     def backward(ctx, grad_out):
         feat, dis_label = ctx.saved_tensors
-        b, dk = feat.shape[:2]
-        sim = ops.attention_forward(feat, None, want_sim_map=True)["sim_map"]
-        _, gq = ops.attention_loss(sim, dis_label, want_grad=True)
-        ds = sim * (gq - (gq * sim).sum(-1, keepdim=True))
-        f = feat.reshape(b, dk, -1).float()
-        g = torch.matmul(f, ds + ds.transpose(1, 2)) * (dk ** -0.5) * grad_out
+        g, _ = ops.attention_backward(feat, ctx.row_stats, dis_label=dis_label, grad_loss=float(grad_out))   # loss-only branch of acan_attn_bwd
         return g.view_as(feat), None, None

@@ -215,6 +215,40 @@ def attention_forward_cl(feat: torch.Tensor, value: Optional[torch.Tensor], want
     return {"ctx": ctx.permute(0, 3, 1, 2) if ctx is not None else None, "sim_map": sim, "row_stats": stats, "loss": loss, "ws": ws}
 
 
+_bwd_scratch = {}
+
+
+def attention_backward(feat: torch.Tensor, row_stats: torch.Tensor, value: Optional[torch.Tensor] = None,
+                       ctx: Optional[torch.Tensor] = None, grad_ctx: Optional[torch.Tensor] = None,
+                       dis_label: Optional[torch.Tensor] = None, grad_loss: float = 0.0):
+    """(grad_feat, grad_value | None) from the tcgen05 backward (acan_attn_bwd)."""
+    f = _cuda_f32(feat, "feat")
+    b, dk, h, w = f.shape
+    n = h * w
+    st = _cuda_f32(row_stats, "row_stats")
+    agg = grad_ctx is not None
+    v = _cuda_f32(value, "value") if agg else None
+    o = _cuda_f32(ctx, "ctx") if agg else None
+    go = _cuda_f32(grad_ctx, "grad_ctx") if agg else None
+    dv = v.shape[1] if agg else 128
+    lab = _cuda_f32(dis_label, "dis_label") if dis_label is not None else None
+    hh, ww = (lab.shape[-2:] if lab is not None else (0, 0))
+    lib = _lib.load()
+    nbytes = int(lib.acan_attn_bwd_workspace_bytes(b, n, dk, dv))
+    key = (f.device, nbytes)
+    if key not in _bwd_scratch:                      # one scratch buffer per (device, size), reused across steps
+        _bwd_scratch.clear()
+        _bwd_scratch[key] = torch.empty(nbytes + 1024, device=f.device, dtype=torch.uint8)
+    buf = _bwd_scratch[key]
+    ptr = (buf.data_ptr() + 1023) // 1024 * 1024
+    gf = torch.empty_like(f)
+    gv = torch.empty_like(v) if agg else None
+    with torch.cuda.device(f.device):
+        _lib.check(lib.acan_attn_bwd(f.data_ptr(), _lib.ptr(v), _lib.ptr(o), st.data_ptr(), _lib.ptr(go), _lib.ptr(lab), hh, ww, float(grad_loss),
+                                     gf.data_ptr(), _lib.ptr(gv), ptr, nbytes, b, n, dk, dv, float(dk) ** -0.5, _lib.current_stream()), "acan_attn_bwd")
+    return gf, gv
+
+
 def attention_rows(ws: AttnWorkspace, rows: torch.Tensor) -> torch.Tensor:
     """sim_map[:, rows, :] -> [B, len(rows), N] from the operand pack of the last forward (vis_utils.py:107-121)."""
     b, n, dk, dv = ws.shape

@@ -136,6 +136,21 @@ int acan_attn_fwd_loss(const float* feat, const float* value, float* ctx, float*
                        void* workspace, size_t workspace_bytes,
                        int B, int N, int dk, int dv, float scale, void* stream);
 
+/* Backward of acan_attn_fwd / acan_attn_fwd_loss on the tensor cores (the reference relies on autograd through
+ * sadecoder.py:42-49,85-87 and losses.py:18-33; Q and K share F, so dF collects both sides of dS):
+ *   dV = dO P      dP = dO^T V      dS = P o (dP - delta_i) - g/(B N) (W o [clamp window] - P T_i)      dF = scale F (dS + dS^T)
+ *   feat, value, ctx (the forward output), row_stats: as given to / returned by the forward call (fp32 NCHW)
+ *   grad_ctx   [B,dv,N] fp32, or NULL when only the attention loss is differentiated (value / ctx / grad_value unused)
+ *   dis_label  NULL, or the forward's label: adds grad_loss * d(attention loss)/dF
+ *   grad_feat  [B,dk,N] fp32, grad_value [B,dv,N] fp32.   workspace: acan_attn_bwd_workspace_bytes(), 1024-byte aligned.
+ * P is recomputed from row_stats; every tensor-core operand is fp16 with fp32 accumulation, dO and dS pre-multiplied by a
+ * power of two chosen on the device from max|dO| (so the loss scale cannot push them out of the fp16 range). */
+size_t acan_attn_bwd_workspace_bytes(int B, int N, int dk, int dv);
+int acan_attn_bwd(const float* feat, const float* value, const float* ctx, const float* row_stats, const float* grad_ctx,
+                  const float* dis_label, int H, int W, float grad_loss,
+                  float* grad_feat, float* grad_value, void* workspace, size_t workspace_bytes,
+                  int B, int N, int dk, int dv, float scale, void* stream);
+
 /* Channels-last half-precision form of the two calls above, for pipelines whose convolutions already emit fp16 in
  * channels_last memory: nothing is packed or transposed.
  *   feat_h  [B,N,dk] fp16 (f_key output, NHWC)   -- is the K-major operand of S as it stands
