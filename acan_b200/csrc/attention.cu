@@ -673,7 +673,18 @@ __global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ go
   float s = 0.f, am = 0.f;
   if (i < N) {
     const size_t base = static_cast<size_t>(b) * C * N + i;
-    for (int c = wv; c < C; c += 8) {
+    int c = wv;
+    for (; c + 24 < C; c += 32) {                        // 4 independent row pairs in flight per thread
+      float gv[4], ov[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        gv[u] = __ldg(go + base + static_cast<size_t>(c + 8 * u) * N);
+        ov[u] = __ldg(o + base + static_cast<size_t>(c + 8 * u) * N);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s = fmaf(gv[u], ov[u], s); am = fmaxf(am, fabsf(gv[u])); }
+    }
+    for (; c < C; c += 8) {
       const float gv = __ldg(go + base + static_cast<size_t>(c) * N);
       s = fmaf(gv, __ldg(o + base + static_cast<size_t>(c) * N), s);
       am = fmaxf(am, fabsf(gv));
@@ -746,25 +757,21 @@ __global__ void __launch_bounds__(256) kl_ds_kernel(const __half* __restrict__ p
 
 // per row: ln(bin) and ln(Z_i), Z_i = sum_j min(a_i/a_j, a_j/a_i)   (target-affinity normaliser, losses.py:40-46)
 __global__ void __launch_bounds__(256) gt_norm_kernel(const float* __restrict__ bins, float* __restrict__ logbin, float* __restrict__ lnz, int N) {
-  __shared__ float red[8];
-  const int64_t row = blockIdx.x;
-  const int b = static_cast<int>(row / N);
+  // grid (ceil(N/256), B): the image's log-bins are staged in shared memory, one thread per row sums exp(-|la_i - la_j|)
+  extern __shared__ float la[];
+  const int b = blockIdx.y;
   const float* a = bins + static_cast<size_t>(b) * N;
-  const float ai = a[row - static_cast<int64_t>(b) * N];
-  float z = 0.f;
-  for (int j = threadIdx.x; j < N; j += 256) {
-    const float aj = a[j], lo = fminf(ai, aj), hi = fmaxf(ai, aj);
-    z += lo > 0.f ? lo / hi : 0.f;
-  }
-  z = warp_sum(z);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = z;
+  for (int j = threadIdx.x; j < N; j += 256) { const float v = a[j]; la[j] = v > 0.f ? logf(v) * kLog2e : -INFINITY; }   // log2 units
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    logbin[row] = ai > 0.f ? logf(ai) : -INFINITY;
-    lnz[row] = t > 0.f ? logf(t) : 0.f;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const float li = la[i];
+  float z = 0.f;
+  if (li > -INFINITY) {
+    for (int j = 0; j < N; ++j) z += ex2_approx(-fabsf(li - la[j]));      // exp2(-inf) = 0 for bin 0
   }
+  logbin[static_cast<size_t>(b) * N + i] = li > -INFINITY ? li * kLn2 : -INFINITY;
+  lnz[static_cast<size_t>(b) * N + i] = z > 0.f ? lg2_approx(z) * kLn2 : 0.f;
 }
 
 // selected rows of sim_map on CUDA cores (3 rows per image for the TensorBoard figure, vis_utils.py:107-121)
@@ -1046,7 +1053,7 @@ int prepare_target(const Workspace& w, const float* dis_label, int B, int H, int
   const int N = (H / 8) * (Wd / 8);
   nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, w.bins, B, H, Wd);
   if (int e = launch_status("nearest_bins_kernel")) return e;
-  gt_norm_kernel<<<B * N, 256, 0, st>>>(w.bins, w.logbin, w.lnz, N);
+  gt_norm_kernel<<<dim3((N + 255) / 256, B), 256, static_cast<size_t>(N) * sizeof(float), st>>>(w.bins, w.logbin, w.lnz, N);
   return launch_status("gt_norm_kernel");
 }
 
