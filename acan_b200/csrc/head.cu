@@ -381,3 +381,124 @@ extern "C" int acan_tail_fwd(const float* z_nhwc, float* depth, float* prob, int
     default:                return launch_tail<ACAN_HEAD_CE_HARD>(z_nhwc, depth, prob, index, B, h, w, K, bs, st);
   }
 }
+
+// ---------------------------------------------------------------- ordinal-regression loss
+// OrdinalRegression2d with the reference's live configuration (losses.py:103-158: reduction='sum', no class weights,
+// ignore_index) fused with decode_ord (model.py:40-45): per valid pixel
+//     loss = - sum_{k <  l} log clamp(p_k, 1e-8, 1e8) - sum_{k >= l} log clamp(1 - p_k, 1e-8, 1e8),   p_k = e1 / (e0 + e1)
+// averaged over the pixels whose label != ignore_index.  Forward reads the pair logits once (640*HW B / image at K = 80)
+// instead of decode_ord + ~10 elementwise passes over [B,K,H,W]; backward re-reads them and writes d/dlogits directly
+// (d/dy1 = -(1-p) below the label, +p at / above it, inside the clamp windows; d/dy0 = -d/dy1), so the probability
+// tensor and its gradient never exist.
+namespace acan {
+namespace {
+
+__device__ __forceinline__ float ord_term(float p, bool below) {
+  const float q = below ? p : 1.0f - p;
+  return -logf(fminf(fmaxf(q, 1e-8f), 1e8f));
+}
+
+__global__ void __launch_bounds__(kThreads) ord_loss_fwd_kernel(const float4* __restrict__ y, const int64_t* __restrict__ label,
+                                                                 float2* __restrict__ partial, int K, int64_t hw4, int64_t total, int ignore_index) {
+  __shared__ float red_s[kThreads / 32], red_c[kThreads / 32];
+  float sum = 0.f, cnt = 0.f;
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t b = q / hw4, x = q - b * hw4;
+    const float4* src = y + b * (int64_t)(2 * K) * hw4 + x;
+    const longlong2 la = *reinterpret_cast<const longlong2*>(label + (b * hw4 + x) * 4);
+    const longlong2 lb = *reinterpret_cast<const longlong2*>(label + (b * hw4 + x) * 4 + 2);
+    const int l[4] = {(int)la.x, (int)la.y, (int)lb.x, (int)lb.y};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; k += 4) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k + (u >> 1) < K) v[u] = ldg_stream(src + (int64_t)(2 * k + u) * hw4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k + u < K) {
+          const int kk = k + u;
+          acc[0] += ord_term(ord_prob(v[2 * u].x, v[2 * u + 1].x), kk < l[0]);
+          acc[1] += ord_term(ord_prob(v[2 * u].y, v[2 * u + 1].y), kk < l[1]);
+          acc[2] += ord_term(ord_prob(v[2 * u].z, v[2 * u + 1].z), kk < l[2]);
+          acc[3] += ord_term(ord_prob(v[2 * u].w, v[2 * u + 1].w), kk < l[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (l[i] != ignore_index) { sum += acc[i]; cnt += 1.f; }
+  }
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = sum; red_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f, c = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) { s += red_s[i]; c += red_c[i]; }
+    partial[blockIdx.x] = make_float2(s, c);
+  }
+}
+
+__global__ void ord_loss_final_kernel(const float2* __restrict__ partial, int n, float* __restrict__ loss, float* __restrict__ count) {
+  // one warp, fixed order
+  float s = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) { s += partial[i].x; c += partial[i].y; }
+  s = warp_sum(s); c = warp_sum(c);
+  if (threadIdx.x == 0) { *loss = s / c; *count = c; }      // mean over an empty set is NaN, as torch's .mean() gives
+}
+
+__global__ void __launch_bounds__(kThreads) ord_loss_bwd_kernel(const float4* __restrict__ y, const int64_t* __restrict__ label,
+                                                                 const float* __restrict__ count, const float* __restrict__ grad_out,
+                                                                 float4* __restrict__ gy, int K, int64_t hw4, int64_t total, int ignore_index) {
+  const float g = __ldg(grad_out) / __ldg(count);
+  // total = B*K*hw4 quads of (pair k, 4 pixels)
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t bk = q / hw4, x = q - bk * hw4;
+    const int64_t b = bk / K;
+    const int k = (int)(bk - b * K);
+    const float4 a = ldg_stream(y + (2 * bk) * hw4 + x), c = ldg_stream(y + (2 * bk + 1) * hw4 + x);
+    const longlong2 la = *reinterpret_cast<const longlong2*>(label + (b * hw4 + x) * 4);
+    const longlong2 lb = *reinterpret_cast<const longlong2*>(label + (b * hw4 + x) * 4 + 2);
+    auto one = [&](float y0, float y1, int l) {
+      if (l == ignore_index) return 0.f;
+      const float p = ord_prob(y0, y1);
+      if (k < l) return (p > 1e-8f && p < 1e8f) ? -(1.0f - p) * g : 0.f;            // d/dy1 of -log p
+      const float qv = 1.0f - p;
+      return (qv > 1e-8f && qv < 1e8f) ? p * g : 0.f;                               // d/dy1 of -log (1 - p)
+    };
+    float4 d;
+    d.x = one(a.x, c.x, (int)la.x); d.y = one(a.y, c.y, (int)la.y); d.z = one(a.z, c.z, (int)lb.x); d.w = one(a.w, c.w, (int)lb.y);
+    gy[(2 * bk + 1) * hw4 + x] = d;
+    gy[(2 * bk) * hw4 + x] = make_float4(-d.x, -d.y, -d.z, -d.w);
+  }
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" int acan_ordinal_loss_ws_floats(void) { return 2 * acan::kNumSMs * acan::kBlocksPerSM + 8; }
+
+extern "C" int acan_ordinal_loss_fwd(const float* logits, const int64_t* label, float* loss_out, float* count_out, float* ws,
+                                     int B, int K, int64_t HW, int ignore_index, void* stream) {
+  ACAN_CHECK_ARG(logits && label && loss_out && count_out && ws, "acan_ordinal_loss_fwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 0 && HW > 0 && HW % 4 == 0, "acan_ordinal_loss_fwd: need positive sizes and HW %% 4 == 0 (HW=%lld)", (long long)HW);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(logits) % 16 == 0 && reinterpret_cast<uintptr_t>(label) % 16 == 0 && reinterpret_cast<uintptr_t>(ws) % 8 == 0,
+                 "acan_ordinal_loss_fwd: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t hw4 = HW / 4, total = (int64_t)B * hw4;
+  const int grid = grid_for(total);
+  ord_loss_fwd_kernel<<<grid, kThreads, 0, st>>>(reinterpret_cast<const float4*>(logits), label, reinterpret_cast<float2*>(ws), K, hw4, total, ignore_index);
+  if (int e = launch_status("acan_ordinal_loss_fwd")) return e;
+  ord_loss_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float2*>(ws), grid, loss_out, count_out);
+  return launch_status("acan_ordinal_loss_fwd/final");
+}
+
+extern "C" int acan_ordinal_loss_bwd(const float* logits, const int64_t* label, const float* count, const float* grad_out, float* grad_logits,
+                                     int B, int K, int64_t HW, int ignore_index, void* stream) {
+  ACAN_CHECK_ARG(logits && label && count && grad_out && grad_logits, "acan_ordinal_loss_bwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 0 && HW > 0 && HW % 4 == 0, "acan_ordinal_loss_bwd: need positive sizes and HW %% 4 == 0");
+  const int64_t hw4 = HW / 4, total = (int64_t)B * K * hw4;
+  ord_loss_bwd_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(logits), label, count, grad_out, reinterpret_cast<float4*>(grad_logits), K, hw4, total, ignore_index);
+  return launch_status("acan_ordinal_loss_bwd");
+}

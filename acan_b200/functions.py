@@ -33,6 +33,23 @@ class DecodeOrd(torch.autograd.Function):
         return ops.decode_ord_backward(prob, grad_prob.contiguous())
 
 
+class FusedOrdinalLoss(torch.autograd.Function):
+    """OrdinalRegression2d(reduction='sum', ignore_index) o decode_ord on the full-resolution pair logits (losses.py:103-158,
+    model.py:40-45): one read of the logits forward, one read + one write backward; the probabilities never exist."""
+
+    @staticmethod
+    def forward(ctx, logits, label, ignore_index):
+        loss, count, y, lab = ops.ordinal_loss_forward(logits, label, ignore_index)
+        ctx.save_for_backward(y, lab, count)
+        ctx.ignore_index = ignore_index
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        y, lab, count = ctx.saved_tensors
+        return ops.ordinal_loss_backward(y, lab, count, grad_out, ctx.ignore_index), None, None
+
+
 class PoolBranch(torch.autograd.Function):
     """SADecoder.image_context without the broadcast (sadecoder.py:97-106) -> g [B,H2]."""
 

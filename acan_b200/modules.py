@@ -201,6 +201,72 @@ class LazyProb:
         return getattr(self.materialize(), name)
 
 
+class LazyLogitsProb:
+    """Training-mode stand-in for ``'y'`` = decode_ord(upsampled logits) ([B,K,H,W]).  Holds the full-resolution pair logits
+    (with their autograd history); the drop-in ``OrdinalRegression2d`` consumes them through the fused loss kernel and
+    ``inference`` through the from-logits head, so the probability tensor and its gradient are never materialised.  Any
+    other consumer (e.g. the reference's own loss classes) gets ``decode_ord(logits)`` with the usual autograd."""
+
+    def __init__(self, logits: torch.Tensor, n_c: int):
+        self._logits, self._k, self._dense = logits, n_c, None
+
+    @property
+    def logits(self):
+        return self._logits
+
+    @property
+    def shape(self):
+        b, _, h, w = self._logits.shape
+        return torch.Size((b, self._k, h, w))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 4
+
+    @property
+    def device(self):
+        return self._logits.device
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    @property
+    def requires_grad(self):
+        return self._logits.requires_grad
+
+    def materialize(self) -> torch.Tensor:
+        if self._dense is None:
+            self._dense = fn.DecodeOrd.apply(self._logits.float())
+        return self._dense
+
+    def __getitem__(self, key):
+        return self.materialize()[key]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        return f"LazyLogitsProb(shape={tuple(self.shape)}, materialised={self._dense is not None})"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def conv(a):
+            if isinstance(a, LazyLogitsProb):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(conv(x) for x in a)
+            return a
+        return func(*conv(args), **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
 class _Holder:
     """per-module slot for the attention workspace of the latest forward (operand pack, row statistics)."""
     ws = None

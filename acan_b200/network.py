@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import functions as fn
 from . import ops
-from .modules import AttentionLoss2d, LazyProb, LazySimMap, SADecoder, _init_like_reference
+from .modules import AttentionLoss2d, LazyLogitsProb, LazyProb, LazySimMap, SADecoder, _init_like_reference
 
 
 def continuous2discrete(depth, d_min, d_max, n_c):
@@ -66,6 +66,8 @@ class BaseClassificationModel_(nn.Module):
         mode = "soft" if self.inferenceType == "soft" else "hard"
         if isinstance(y, LazyProb):                      # eval: fused upsample + decode_ord + head on the stride-8 logits
             return y.depth(mode)
+        if isinstance(y, LazyLogitsProb):                # training-mode handle: decode_ord fused into the head
+            return ops.head_inference(y.logits.detach(), cls, mode, self.min_depth, self.max_depth, self.num_classes, from_logits=True)
         return ops.head_inference(y, cls, mode, self.min_depth, self.max_depth, self.num_classes)
 
     def forward(self):
@@ -179,7 +181,8 @@ class ResNet(BaseClassificationModel_):
             return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
         y = self.classifier(x)
         if self.classifierType == "OR":
-            y = self.decode_ord(y)
+            # lazy_head: 'y' keeps the pair logits; the drop-in ordinal loss / inference fuse decode_ord
+            y = LazyLogitsProb(y.float(), self.num_classes) if self.lazy_head else self.decode_ord(y)
             if self.use_inter:
                 inter_y = self.decode_ord(inter_y)
         return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
@@ -226,8 +229,9 @@ class ResNet(BaseClassificationModel_):
 
 
 class OrdinalRegression2d(nn.Module):
-    """losses.py:64-158 with reduction='sum', no class weights: OUT OF SCOPE for the kernels (SURVEY §2 row 5,
-    next row f-2); plain torch so that the training step runs without the reference installed."""
+    """losses.py:64-158 with reduction='sum', no class weights (the reference's live configuration).  Given the lazy
+    training-mode 'y' handle it runs the fused decode_ord + loss kernels (SURVEY §8f row f-2, acan_ordinal_loss_fwd/bwd);
+    given a dense probability tensor it is the plain torch restatement."""
 
     def __init__(self, ignore_index=0, reduction="sum", use_weights=False, weight=None):
         super().__init__()
@@ -236,6 +240,8 @@ class OrdinalRegression2d(nn.Module):
         self.ignore_index = ignore_index
 
     def forward(self, pred, label):
+        if isinstance(pred, LazyLogitsProb) and pred.shape[2] * pred.shape[3] % 4 == 0:
+            return fn.FusedOrdinalLoss.apply(pred.logits, label, self.ignore_index)      # fused with decode_ord, one pass
         b, c, h, w = pred.shape
         k = torch.arange(c, device=pred.device).view(1, c, 1, 1)
         below = (k < label.view(b, 1, h, w)).to(pred.dtype)
@@ -283,4 +289,12 @@ def install(net, criterion=None):
         setattr(net, name, types.MethodType(getattr(BaseClassificationModel_, name), net))
     if criterion is not None and getattr(criterion, "AttentionLoss", None) is not None:
         criterion.AttentionLoss = AttentionLoss2d(scale=1)
+    app = getattr(criterion, "AppearanceLoss", None) if criterion is not None else None
+    if (type(app).__name__ == "OrdinalRegression2d" and not getattr(app, "use_weights", False)
+            and getattr(app, "reduction", "sum") == "sum" and getattr(app, "ignore_index", 0) is not None):
+        criterion.AppearanceLoss = OrdinalRegression2d(ignore_index=app.ignore_index)     # fused decode_ord + loss kernels
+    net.lazy_head = True
+    fwd = ResNet.forward
+    net.forward = types.MethodType(fwd, net)          # forward with the lazy 'y' handles (same dict, same keys)
+    net.encode = types.MethodType(ResNet.encode, net)
     return net

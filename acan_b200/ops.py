@@ -80,6 +80,33 @@ def tail_inference(z: torch.Tensor, classifier: str, mode: str, d_min: float, d_
     return out[0] if len(out) == 1 else out
 
 
+def ordinal_loss_forward(logits: torch.Tensor, label: torch.Tensor, ignore_index: int = 0):
+    """(loss 0-dim, count 0-dim): OrdinalRegression2d fused with decode_ord on full-resolution pair logits [B,2K,H,W]."""
+    y = _cuda_f32(logits, "logits")
+    b, c2, h, w = y.shape
+    lab = label.to(device=y.device, dtype=torch.int64).contiguous()
+    if lab.numel() != b * h * w:
+        raise _lib.AcanLibraryError(f"label {tuple(lab.shape)} does not match logits {tuple(y.shape)}")
+    lib = _lib.load()
+    loss = torch.empty((), device=y.device, dtype=torch.float32)
+    count = torch.empty((), device=y.device, dtype=torch.float32)
+    ws = torch.empty(int(lib.acan_ordinal_loss_ws_floats()), device=y.device, dtype=torch.float32)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.acan_ordinal_loss_fwd(y.data_ptr(), lab.data_ptr(), loss.data_ptr(), count.data_ptr(), ws.data_ptr(), b, c2 // 2, h * w,
+                                             int(ignore_index), _lib.current_stream()), "acan_ordinal_loss_fwd")
+    return loss, count, y, lab
+
+
+def ordinal_loss_backward(logits: torch.Tensor, label: torch.Tensor, count: torch.Tensor, grad_out: torch.Tensor, ignore_index: int = 0):
+    b, c2, h, w = logits.shape
+    g = grad_out.detach().to(device=logits.device, dtype=torch.float32).reshape(1).contiguous()
+    out = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().acan_ordinal_loss_bwd(logits.data_ptr(), label.data_ptr(), count.data_ptr(), g.data_ptr(), out.data_ptr(), b, c2 // 2, h * w,
+                                                     int(ignore_index), _lib.current_stream()), "acan_ordinal_loss_bwd")
+    return out
+
+
 def continuous2discrete(depth: torch.Tensor, d_min: float, d_max: float, n_c: int) -> torch.Tensor:
     d = _cuda_f32(depth, "depth")
     out = torch.empty_like(d)

@@ -84,6 +84,17 @@ int acan_head_fwd(const float* in, float* depth, int32_t* index, int B, int K, i
 int acan_tail_fwd(const float* z_nhwc, float* depth, float* prob, int32_t* index, int B, int h, int w, int K,
                   double d_min, double d_max, int kind, void* stream);
 
+/* OrdinalRegression2d in the reference's live configuration (losses.py:103-158: reduction='sum', no class weights,
+ * ignore_index) fused with decode_ord (model.py:40-45) -- SURVEY.md §8f row f-2.
+ *   logits [B,2K,HW] fp32 (full-resolution pair logits), label [B,HW] int64 bin indices, HW % 4 == 0
+ *   loss_out / count_out: 1 float each (mean over valid pixels; number of valid pixels, kept for backward)
+ *   ws: acan_ordinal_loss_ws_floats() floats.   backward: grad_logits [B,2K,HW] = grad_out * dloss/dlogits. */
+int acan_ordinal_loss_ws_floats(void);
+int acan_ordinal_loss_fwd(const float* logits, const int64_t* label, float* loss_out, float* count_out, float* ws,
+                          int B, int K, int64_t HW, int ignore_index, void* stream);
+int acan_ordinal_loss_bwd(const float* logits, const int64_t* label, const float* count, const float* grad_out, float* grad_logits,
+                          int B, int K, int64_t HW, int ignore_index, void* stream);
+
 /* continuous2discrete (model.py:19-23, torch-0.4 semantics): metres -> bin index as float, 0 outside (d_min,d_max). */
 int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream);
 

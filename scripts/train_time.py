@@ -49,3 +49,16 @@ def step():
     opt.step()
 t = ev_time(step, iters=5, warm=3)
 print(f"full training step (fp32/TF32 convs, beta=1), B={B}: {t*1e3:.1f} ms -> {B/t:.1f} images/s")
+
+# the same step with 16-bit autocast convolutions + channels_last (the attention / loss / head kernels are unchanged)
+net = net.to(memory_format=torch.channels_last)
+xc = x.contiguous(memory_format=torch.channels_last)
+def step_amp():
+    opt.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o = net(xc)
+        l1, _, l3, tot = crit(o, y, 1)
+    tot.backward()
+    opt.step()
+t = ev_time(step_amp, iters=5, warm=3)
+print(f"full training step (bf16 autocast + channels_last convs, beta=1), B={B}: {t*1e3:.1f} ms -> {B/t:.1f} images/s")

@@ -139,6 +139,29 @@ def test_fused_tail_against_oracle(b, h, w, params):
         torch.nn.functional.interpolate(z.half().double(), scale_factor=8, mode="bilinear", align_corners=True)), dmin, dmax, K), 1e-5)
 
 
+@pytest.mark.parametrize("b,h,w", [(2, 8, 12), (3, 64, 96)])
+def test_fused_ordinal_loss_against_oracle(b, h, w):
+    """acan_ordinal_loss_fwd / _bwd (OrdinalRegression2d o decode_ord) vs autograd through the oracle; includes label 0
+    (ignored pixels), saturated logits (clamp windows) and the all-bins-below / all-bins-above extremes."""
+    from acan_b200 import functions as fn
+    K = 80
+    # logits of scale 1.5: |y1 - y0| stays below ~13, so 1 - p never rounds to 0 in fp32 where fp64 keeps it above the 1e-8
+    # clamp (the reference itself evaluates 1 - p in fp32); the clamp windows are exercised by the two planted pairs instead
+    y = 1.5 * synth.randn(f"ord.y.{h}", b, 2 * K, h, w)
+    y[0, 0:2, 0, 0] = torch.tensor([60.0, -60.0])          # p -> 0: log clamp(p) hits 1e-8 when the label is above bin 0
+    y[0, 2:4, 0, 1] = torch.tensor([-60.0, 60.0])          # p -> 1: log clamp(1 - p)
+    lab = O.continuous2discrete(synth.depth_label(f"ord.lab.{h}", b, h, w, 0.5, 10.5), *NYU).squeeze(1).long()
+    lab[0, 0, 0], lab[0, 0, 1], lab[0, 0, 2], lab[0, 0, 3] = 5, 1, 79, 0
+    yd = y.to(DEV).requires_grad_(True)
+    loss = fn.FusedOrdinalLoss.apply(yd, lab.to(DEV), 0)
+    (2.5 * loss).backward()
+    yc = y.double().requires_grad_(True)
+    want = O.ordinal_regression_loss(O.decode_ord(yc), lab)
+    (2.5 * want).backward()
+    assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+    close(yd.grad, yc.grad, 1e-5)
+
+
 def test_decode_ord_backward_matches_autograd():
     from acan_b200 import functions as fn
     y = (2 * torch.randn(2, 160, 8, 12, device=DEV)).requires_grad_(True)
