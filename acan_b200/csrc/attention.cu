@@ -70,7 +70,7 @@ struct GemmArgs {
   float c;             // scale * log2(e)
   int skip_epilogue;   // experiments only (ACAN_SKIP_EPI=1): release the accumulator without reading it
   const int* img_skip; // MODE_STATS: images whose flag is non-zero need no statistics pass (their tiles are skipped by all roles)
-  int unnorm;          // MODE_PROBS: write p~ = exp2(S*c - shift_i) un-normalised and emit per-row partial sums of the ROUNDED values
+  int unnorm;          // MODE_PROBS: write p~ = exp2(S*c - shift_i) un-normalised and emit per-row partial sums
   float* lpart;        //   [B, 2*n_tiles, N] those partial sums
   const float* ds_delta; // MODE_DS: [B, N] delta_i = sum_c dO[c,i] O[c,i]
   const __half* ds_p;    //   [B, N, N] fp16 probabilities
@@ -294,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           m2 = st.x;
           if (g.unnorm) { inv_l = 1.0f; } else { inv_l = 1.0f / st.y; log2_l = lg2_approx(st.y); }
         }
-        float l_acc = 0.f;                               // un-normalised mode: sum of the fp16-ROUNDED p~ this group wrote
+        float l_acc = 0.f;                               // un-normalised mode: sum of the fp16-rounded p~ this group wrote
         const bool kl = g.logbin != nullptr;
         bool kl_row = false;
         if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; kl_row = row_ok && la_i > -INFINITY; }
@@ -342,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 for (int j = 0; j < 16; ++j) {
                   h[j] = pack_half2(ex2_approx(v[2 * j]), ex2_approx(v[2 * j + 1]));
                   const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-                  l_acc += r.x + r.y;
+                  l_acc += r.x + r.y;          // the ROUNDED values: sum_j P_ij == 1 for what the aggregation pass reads (measurably more accurate)
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -579,46 +579,51 @@ __global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __rest
 // ~50 in natural units; random-init / BN'd features give ~16).  Images above that limit take the exact max instead.
 constexpr float kShiftHeadroom = 14.0f, kSafeDiagMax = 72.0f;
 
-__global__ void __launch_bounds__(256) diag_kernel(const __half* __restrict__ fh, float* __restrict__ diag, int dk, float c, int64_t rows) {
-  // one warp per row, 4 rows per warp in flight
-  const int lane = threadIdx.x & 31;
-  const int64_t r0 = (blockIdx.x * 8LL + (threadIdx.x >> 5)) * 4;
+// grid (ceil(N/32), B): each CTA computes d_i for 32 rows (one warp per row, 4 rows per warp in flight); the CTA that
+// finishes an image last (counter in global memory, self-resetting) derives d_max, the row shifts and the image's flag.
+__global__ void __launch_bounds__(256) diag_shift_kernel(const __half* __restrict__ fh, float* __restrict__ diag, float2* __restrict__ stats,
+                                                          int* __restrict__ img_skip, int* __restrict__ counters, int N, int dk, float c) {
+  __shared__ float red[8];
+  __shared__ int is_last;
+  const int lane = threadIdx.x & 31, b = blockIdx.y;
+  const int i0 = blockIdx.x * 32 + (threadIdx.x >> 5) * 4;
+  const __half* base = fh + static_cast<size_t>(b) * N * dk;
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   for (int k = lane; k < dk / 8; k += 32) {
     uint4 u[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) u[q] = (r0 + q < rows) ? __ldg(reinterpret_cast<const uint4*>(fh + (r0 + q) * dk) + k) : make_uint4(0, 0, 0, 0);
+    for (int q = 0; q < 4; ++q) u[q] = (i0 + q < N) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(i0 + q) * dk) + k) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
         s[q] = fmaf(t.x, t.x, fmaf(t.y, t.y, s[q]));
       }
     }
   }
+  float* d = diag + static_cast<size_t>(b) * N;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float t = warp_sum(s[q]) * c;
-    if (lane == 0 && r0 + q < rows) diag[r0 + q] = t;
+    if (lane == 0 && i0 + q < N) d[i0 + q] = t;
   }
-}
-
-// one CTA per image: d_max, then the row shifts and the per-image "bound is safe" flag
-__global__ void __launch_bounds__(256) shift_kernel(const float* __restrict__ diag, float2* __restrict__ stats, int* __restrict__ img_skip, int N) {
-  __shared__ float red[8];
-  const int b = blockIdx.x;
-  const float* d = diag + static_cast<size_t>(b) * N;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counters + b, 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   float m = 0.f;
-  for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, d[i]);
+  for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, __ldcg(d + i));
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  if (lane == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   float dm = 0.f;
   for (int i = 0; i < 8; ++i) dm = fmaxf(dm, red[i]);
-  for (int i = threadIdx.x; i < N; i += 256) stats[static_cast<size_t>(b) * N + i] = make_float2(sqrtf(d[i] * dm) - kShiftHeadroom, 0.f);
-  if (threadIdx.x == 0) img_skip[b] = (dm <= kSafeDiagMax) ? 1 : 0;
+  for (int i = threadIdx.x; i < N; i += 256) stats[static_cast<size_t>(b) * N + i] = make_float2(sqrtf(__ldcg(d + i) * dm) - kShiftHeadroom, 0.f);
+  if (threadIdx.x == 0) { img_skip[b] = (dm <= kSafeDiagMax) ? 1 : 0; counters[b] = 0; }
 }
 
 // images the bound is not safe for: shift_i = exact row maximum from the statistics-pass partials
@@ -881,7 +886,7 @@ struct Workspace {
   float* kl_part;  // [B, 2*ceil(N/kMinBN), N]   (also the l partials of the un-normalised probability pass)
   float* diag;     // [B, N]  S_ii * c
   float* inv_l;    // [B, N]
-  int* dmax_bits;  // [B]
+  int* dmax_bits;  // [B]  arrival counters of diag_shift_kernel (zero between calls: the last CTA of an image resets its counter)
   int* img_skip;   // [B]
   size_t bytes;
 };
@@ -1025,10 +1030,9 @@ int run_affinity_fast(const Workspace& w, const __half* fh, float2* stats, int B
   const int grid_rows = static_cast<int>((rows + 255) / 256);
   {
     ProfScope ps(PROF_STATS, st);
-    diag_kernel<<<static_cast<int>((rows + 31) / 32), 256, 0, st>>>(fh, w.diag, dk, g.c, rows);
-    if (int e = launch_status("diag_kernel")) return e;
-    shift_kernel<<<B, 256, 0, st>>>(w.diag, stats, w.img_skip, N);
-    if (int e = launch_status("shift_kernel")) return e;
+    ACAN_CUDA(cudaMemsetAsync(w.dmax_bits, 0, static_cast<size_t>(B) * 4, st));
+    diag_shift_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(fh, w.diag, stats, w.img_skip, w.dmax_bits, N, dk, g.c);
+    if (int e = launch_status("diag_shift_kernel")) return e;
     g.part = w.part;
     g.img_skip = w.img_skip;
     if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;
