@@ -48,7 +48,7 @@ constexpr int kMinBN = 64;
 constexpr int kTmemCols = 512;          // 2 accumulator buffers x 256 fp32 columns
 constexpr int kGemmThreads = 320;       // TMA warp + MMA warp + 2 x 4 epilogue warps
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 200 * 1024; // operand ring; barriers + alignment slack come on top
+constexpr int kSmemBudget = 225 * 1024; // operand ring + epilogue staging; barriers + alignment slack (~1.2 KB) come on top (227 KB max)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
