@@ -131,3 +131,56 @@ def optimize_for_inference(net: ResNet) -> InferenceNet:
     if not isinstance(net, ResNet):
         raise TypeError("optimize_for_inference expects an acan_b200.network.ResNet")
     return InferenceNet(net.eval())
+
+
+class StreamedPredictor:
+    """Host-to-host inference with the copies off the critical path (the role ``DataPrefetcher`` plays in the reference's
+    trainer, trainers/trainer.py:23-49): while batch i computes, batch i+1 is uploaded on a copy stream and the depth of
+    batch i-1 is downloaded on another.  ``submit(host_images) -> host depth of the PREVIOUS submission (or None)``;
+    ``flush()`` returns the last one.  Host tensors should be pinned; every step still moves its own input and output."""
+
+    def __init__(self, net, device=None):
+        self.net = net
+        self.device = device or next(net.buffers()).device
+        self.h2d, self.d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self._pending = None          # (event, host_out) of the download in flight
+        self._slots = [None, None]    # device input double buffer
+        self._i = 0
+
+    @torch.no_grad()
+    def submit(self, host_images: torch.Tensor):
+        cur = torch.cuda.current_stream(self.device)
+        slot = self._i & 1
+        self._i += 1
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_stream(cur)                         # the slot's previous consumer (two steps ago) has been enqueued
+            x = host_images.to(self.device, non_blocking=True)
+            self._slots[slot] = x
+            up = torch.cuda.Event()
+            up.record(self.h2d)
+        cur.wait_event(up)
+        x.record_stream(cur)
+        depth = self.net.inference(self.net(x))
+        done = torch.cuda.Event()
+        done.record(cur)
+        prev = self._collect()
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(done)
+            host_out = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
+            host_out.copy_(depth, non_blocking=True)
+            depth.record_stream(self.d2h)
+            ev = torch.cuda.Event()
+            ev.record(self.d2h)
+        self._pending = (ev, host_out)
+        return prev
+
+    def _collect(self):
+        if self._pending is None:
+            return None
+        ev, out = self._pending
+        ev.synchronize()
+        self._pending = None
+        return out
+
+    def flush(self):
+        return self._collect()
