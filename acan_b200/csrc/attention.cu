@@ -51,6 +51,7 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 225 * 1024; // operand ring + epilogue staging; barriers + alignment slack (~1.2 KB) come on top (227 KB max)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kShiftHeadroom = 14.0f, kSafeDiagMax = 72.0f;   // statistics-free probability pass, see diag_kernel
 
 // MODE_PV : O^T[dv, Nq] = V[dv, Nk] P[Nq, Nk]^T, both K-major (NCHW world), fp32 out.
 // MODE_PVT: O[Nq, dv]  = P[Nq, Nk] V[Nk, dv], B = V read in place from channels-last memory as an MN-major operand, fp16 out.
@@ -58,6 +59,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2, MODE_PVT = 3, MODE_DS = 4 };
 
 constexpr int kOutChunkBytes = 128 * 128;   // epilogue staging: 128 rows x 128 B (one SWIZZLE_128B TMA-store box)
+constexpr int kDmaxSlots = 64;          // images whose diagonal maximum a probability-pass CTA caches in shared memory
 constexpr int kOutBuffers = 2;          // TMA-store staging ring (4 buffers measured slower: they cost an operand stage)
 
 struct GemmArgs {
@@ -69,7 +71,13 @@ struct GemmArgs {
   uint32_t idesc;
   float c;             // scale * log2(e)
   int skip_epilogue;   // experiments only (ACAN_SKIP_EPI=1): release the accumulator without reading it
-  const int* img_skip; // MODE_STATS: images whose flag is non-zero need no statistics pass (their tiles are skipped by all roles)
+  const float* dpart;  // fast path: [B, n_dpart] per-CTA maxima of the diagonal d_i = S_ii * c (diag_kernel); an image is "safe" when its
+  int n_dpart;         //   maximum is <= kSafeDiagMax.  MODE_STATS skips the tiles of safe images (and exits at once when all are).
+  const float* diag;   // MODE_PROBS (unnorm): [B, N] d_i, the row shift is derived from it in the epilogue
+  float2* stats_w;     // fast path: row_stats being produced -- PROBS writes .x (shift_i), PVT / combine_l write .y (l_i)
+  float2* stats_w2;    //   second copy kept in the workspace for acan_attn_rows / acan_attention_loss_fused (may be null)
+  const float* l_in;   // MODE_PVT: [B, l_parts, N] partial row sums of p~ written by the PROBS pass; 1 / sum is applied per query
+  int l_parts;
   int unnorm;          // MODE_PROBS: write p~ = exp2(S*c - shift_i) un-normalised and emit per-row partial sums
   float* lpart;        //   [B, 2*n_tiles, N] those partial sums
   const float* ds_delta; // MODE_DS: [B, N] delta_i = sum_c dO[c,i] O[c,i]
@@ -78,6 +86,7 @@ struct GemmArgs {
   float ds_gk;           //   dLoss/dloss3 / (B N)
   const float* gscale; // backward: device pair (s, 1/s), the power-of-two gradient scale that keeps fp16 dO / dS in range
   const float* inv_l;  // MODE_PV / MODE_PVT: [B, N] 1 / l_i applied per query while the accumulator leaves TMEM (null = already normalised)
+  int pdl;             // host only: launch as a programmatic dependent of the previous kernel in the stream (one of ours, see griddep_wait)
   long long* trace;    // experiments only (ACAN_TRACE=1): per-tile clock64 stamps of CTA 0: [tile][4] = mma start, mma issued, epi start, epi end
   // MODE_STATS
   float2* part;        // [B, n_tiles, m_rows] (m2, l) partials
@@ -97,6 +106,7 @@ struct __align__(8) PipeBarriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  float dmax[kDmaxSlots];   // probability pass, inference path: per-image maxima of the diagonal
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -107,6 +117,38 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // 16-byte chunk j (0..7) of row r (0..127) inside a 128 B-per-row SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint4* staged_chunk(uint8_t* buf, int r, int j) {
   return reinterpret_cast<uint4*>(buf + r * 128 + ((j ^ (r & 7)) << 4));
+}
+
+// One 32-column half of a 64-column staged chunk of the un-normalised probability pass: p~ = exp2(S*c - shift_i) -> fp16 ->
+// swizzled staging row; returns the sum of the ROUNDED values (what the aggregation pass will read: measurably more accurate
+// than summing the fp32 values).  Columns >= nv lie beyond N: p~ = 0.
+__device__ __forceinline__ float probs_unnorm_half(float (&v)[32], int nv, float c, float m2, uint8_t* buf, int row_in_tile, int half) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], c, -m2);
+  if (nv < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j >= nv) v[j] = -INFINITY;
+  }
+  uint32_t h[16];
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    h[j] = pack_half2(ex2_approx(v[2 * j]), ex2_approx(v[2 * j + 1]));
+    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+    s0 += r.x;
+    s1 += r.y;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *staged_chunk(buf, row_in_tile, half * 4 + q) = make_uint4(h[q * 4 + 0], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
+  return s0 + s1;
+}
+
+// max_i d_i of image b from the per-CTA maxima diag_kernel left (<= 13 values for N <= 1664)
+__device__ __forceinline__ float image_dmax(const float* __restrict__ dpart, int n_dpart, int b) {
+  float m = 0.f;
+  for (int t = 0; t < n_dpart; ++t) m = fmaxf(m, __ldg(dpart + static_cast<size_t>(b) * n_dpart + t));
+  return m;
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
@@ -126,9 +168,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* out_stage = smem + static_cast<size_t>(g.stages) * stage_bytes;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(out_stage + kOutBuffers * kOutChunkBytes);
+  float* const dmax_s = bars->dmax;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();       // the next pass may start its prologue as soon as this grid's CTAs are resident
+  if (MODE == MODE_STATS && g.dpart != nullptr) {
+    griddep_wait();
+    // fallback statistics pass of the inference path: nothing to do unless some image's diagonal exceeds the safe bound
+    // (every CTA of the grid, and both CTAs of a pair, reach the same verdict from the same values)
+    float m = 0.f;
+    for (int i = threadIdx.x; i < g.batch * g.n_dpart; i += kGemmThreads) m = fmaxf(m, __ldg(g.dpart + i));
+    if (!__syncthreads_or(m > kSafeDiagMax)) return;
+  }
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int total_tiles = g.batch * g.m_tiles * g.n_tiles;
   const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
@@ -151,6 +203,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (CG == 2) cluster_sync_all(); else __syncthreads();      // barrier inits + TMEM address visible (pair-wide)
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  griddep_wait();                    // PDL: everything above overlapped the previous kernel's tail; its results are visible from here
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one thread per CTA)
@@ -162,7 +215,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int b = tile / (g.n_tiles * g.m_tiles);
         const int a_row = (mt * CG + static_cast<int>(cta_rank)) * BM;
         const int b_row = nt * g.bn + static_cast<int>(cta_rank * b_rows);
-        if (MODE == MODE_STATS && g.img_skip != nullptr && __ldg(g.img_skip + b) != 0) continue;
+        if (MODE == MODE_STATS && g.dpart != nullptr && image_dmax(g.dpart, g.n_dpart, b) <= kSafeDiagMax) continue;
         for (int ks = 0; ks < g.k_steps; ++ks) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
@@ -206,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        if (MODE == MODE_STATS && g.img_skip != nullptr && __ldg(g.img_skip + tile / (g.n_tiles * g.m_tiles)) != 0) continue;
+        if (MODE == MODE_STATS && g.dpart != nullptr && image_dmax(g.dpart, g.n_dpart, tile / (g.n_tiles * g.m_tiles)) <= kSafeDiagMax) continue;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 0] = clock64();
@@ -246,6 +299,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint8_t* const buf = out_stage + group * kOutChunkBytes;
     const int bar_id = 1 + group;
     uint32_t acc = 0, acc_phase = 0;
+    if (MODE == MODE_PROBS && g.unnorm) {                 // per-image diagonal maxima, once per CTA (epilogue warps only)
+      const int t = threadIdx.x - 64;
+      if (t < g.batch && t < kDmaxSlots) dmax_s[t] = image_dmax(g.dpart, g.n_dpart, t);
+      named_bar_sync(3, 256);
+    }
     const uint32_t leader_empty0 = (CG == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[0]), 0) : 0u;
     const uint32_t leader_empty1 = (CG == 2) ? mapa_u32(smem_u32(&bars->tmem_empty[1]), 0) : 0u;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -259,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int nvalid = min(g.bn, g.n_cols - col0);   // >= 1 by construction of n_tiles
       const int chunks = (nvalid + 31) >> 5;
       const size_t part_idx = (static_cast<size_t>(b) * (2 * g.n_tiles) + 2 * nt + group) * g.m_rows + row;   // per (key tile, group) partials
-      if (MODE == MODE_STATS && g.img_skip != nullptr && __ldg(g.img_skip + b) != 0) continue;
+      if (MODE == MODE_STATS && g.dpart != nullptr && image_dmax(g.dpart, g.n_dpart, b) <= kSafeDiagMax) continue;
 
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -289,10 +347,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       } else if constexpr (MODE == MODE_PROBS) {
         float m2 = 0.f, inv_l = 0.f, la_i = 0.f, lnz_i = 0.f, log2_l = 0.f;
         const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
-        {
+        if (g.unnorm) {
+          // Cauchy-Schwarz shift (see diag_kernel); images above the safe bound take the exact row maximum the fallback
+          // statistics pass left in `part` (same tile width, so the same 2 * n_tiles partials per row)
+          inv_l = 1.0f;
+          const float dmax = b < kDmaxSlots ? dmax_s[b] : image_dmax(g.dpart, g.n_dpart, b);
+          if (dmax <= kSafeDiagMax) {
+            m2 = sqrtf(g.diag[brow] * dmax) - kShiftHeadroom;
+          } else {
+            m2 = -INFINITY;
+            const float2* pp = g.part + static_cast<size_t>(b) * (2 * g.n_tiles) * g.m_rows + (row_ok ? row : 0);
+            for (int t = 0; t < 2 * g.n_tiles; ++t) m2 = fmaxf(m2, pp[static_cast<size_t>(t) * g.m_rows].x);
+          }
+          if (row_ok && nt == 0 && group == 0) {
+            g.stats_w[brow].x = m2;
+            if (g.stats_w2) g.stats_w2[brow].x = m2;
+          }
+        } else {
           const float2 st = g.stats[brow];
           m2 = st.x;
-          if (g.unnorm) { inv_l = 1.0f; } else { inv_l = 1.0f / st.y; log2_l = lg2_approx(st.y); }
+          inv_l = 1.0f / st.y;
+          log2_l = lg2_approx(st.y);
         }
         float l_acc = 0.f;                               // un-normalised mode: sum of the fp16-rounded p~ this group wrote
         const bool kl = g.logbin != nullptr;
@@ -301,6 +376,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         float kl_acc = 0.f, klw_acc = 0.f;
         const float* la_cols = kl ? g.logbin + static_cast<size_t>(b) * g.n_cols + col0 : nullptr;
         float* srow = g.sim_out ? g.sim_out + (brow * g.n_cols + col0) : nullptr;
+        if (g.unnorm) {
+          // inference path: both halves of a 64-column chunk are fetched from TMEM before the staging buffer is even free
+          for (int ch = 2 * group; ch < chunks; ch += 4) {
+            float v0[32], v1[32];
+            const bool two = ch + 1 < chunks;                 // warp-uniform (an odd tail half lies beyond N: the store clips it)
+            tmem_ld_32x32(taddr + ch * 32, v0);
+            if (two) tmem_ld_32x32(taddr + (ch + 1) * 32, v1);
+            if (store_leader) tma_store_wait_read<0>();       // this group's previous store has drained `buf`
+            tmem_ld_wait();
+            named_bar_sync(bar_id, 128);
+            l_acc += probs_unnorm_half(v0, nvalid - ch * 32, g.c, m2, buf, row_in_tile, 0);
+            if (two) l_acc += probs_unnorm_half(v1, nvalid - (ch + 1) * 32, g.c, m2, buf, row_in_tile, 1);
+            fence_proxy_async();                              // generic-proxy smem writes -> visible to the TMA engine
+            named_bar_sync(bar_id, 128);
+            if (store_leader && g.skip_epilogue != 2) {       // rows / columns beyond N are clipped by the tensor map
+              tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
+              tma_store_commit();
+            }
+          }
+        } else
         // 64 columns (= 128 B of fp16) per staged TMA store; this group takes every other 64-column chunk
         for (int ch = 2 * group; ch < chunks; ch += 4) {
           if (g.store_p) {
@@ -331,23 +426,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     klw_acc += (w > 0.f && fabsf(lnw - lnq) < 18.420680744f) ? w : 0.f;
                   }
                 }
-              }
-              if (g.unnorm) {
-                if (nv < 32) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) if (j >= nv) v[j] = -INFINITY;   // columns beyond N: p~ = 0
-                }
-                uint32_t h[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  h[j] = pack_half2(ex2_approx(v[2 * j]), ex2_approx(v[2 * j + 1]));
-                  const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-                  l_acc += r.x + r.y;          // the ROUNDED values: sum_j P_ij == 1 for what the aggregation pass reads (measurably more accurate)
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  *staged_chunk(buf, row_in_tile, half * 4 + q) = make_uint4(h[q * 4 + 0], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
-                continue;
               }
               if (g.skip_epilogue != 3) {
 #pragma unroll
@@ -446,23 +524,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       } else if constexpr (MODE == MODE_PVT) {   // rows = query positions, columns = value channels; 64 fp16 columns per staged store
-        const float rs = g.inv_l ? __ldg(g.inv_l + static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0)) : 1.0f;
+        float rs = 1.0f;
+        if (g.l_in) {      // l_i = sum (fixed order) of the partial sums of the rounded p~ the probability pass wrote
+          const float* lp = g.l_in + static_cast<size_t>(b) * g.l_parts * g.m_rows + (row_ok ? row : 0);
+          float l = 0.f;
+          for (int t = 0; t < g.l_parts; ++t) l += __ldg(lp + static_cast<size_t>(t) * g.m_rows);
+          rs = 1.0f / l;
+          if (row_ok && nt == 0 && group == 0) {
+            const size_t brow = static_cast<size_t>(b) * g.m_rows + row;
+            g.stats_w[brow].y = l;
+            if (g.stats_w2) g.stats_w2[brow].y = l;
+          }
+        }
         for (int ch = 2 * group; ch < chunks; ch += 4) {
+          float v[2][32];
+          const bool two = ch + 1 < chunks;                   // warp-uniform
+          tmem_ld_32x32(taddr + ch * 32, v[0]);
+          if (two) tmem_ld_32x32(taddr + (ch + 1) * 32, v[1]);
           if (store_leader) tma_store_wait_read<0>();
+          tmem_ld_wait();
           named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            if (ch + half < chunks) {
-              float v[32];
-              tmem_ld_32x32(taddr + (ch + half) * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= rs;
+            if (half == 0 || two) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *staged_chunk(buf, row_in_tile, half * 4 + q) =
-                    make_uint4(pack_half2(v[q * 8 + 0], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
-                               pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+                    make_uint4(pack_half2(v[half][q * 8 + 0] * rs, v[half][q * 8 + 1] * rs), pack_half2(v[half][q * 8 + 2] * rs, v[half][q * 8 + 3] * rs),
+                               pack_half2(v[half][q * 8 + 4] * rs, v[half][q * 8 + 5] * rs), pack_half2(v[half][q * 8 + 6] * rs, v[half][q * 8 + 7] * rs));
             }
           }
           fence_proxy_async();
@@ -559,7 +648,8 @@ __global__ void __launch_bounds__(256) pack_value_kernel(const float4* __restric
 }
 
 // (m2, l) partials over key tiles -> final row statistics
-__global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int n_tiles, int N, int B) {
+__global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __restrict__ part, float2* __restrict__ stats, float2* __restrict__ stats2,
+                                                             int n_tiles, int N, int B) {
   const int64_t total = static_cast<int64_t>(B) * N;
   for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
     const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
@@ -569,6 +659,7 @@ __global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __rest
     float l = 0.f;
     for (int t = 0; t < n_tiles; ++t) { const float2 v = p[static_cast<size_t>(t) * N]; l += v.y * ex2_approx(v.x - m); }
     stats[q] = make_float2(m, l);
+    if (stats2) stats2[q] = make_float2(m, l);
   }
 }
 
@@ -577,77 +668,71 @@ __global__ void __launch_bounds__(256) combine_stats_kernel(const float2* __rest
 // so shift_i = sqrt(d_i * d_max) - 14 keeps p~ = exp2(S_ij*c - shift_i) <= 2^14 (no fp16 overflow) and every entry within
 // 2^-10 of the row maximum a normal fp16 as long as sqrt(d_i d_max) - d_i <= d_max / 4 <= 18, i.e. d_max <= 72 (S up to
 // ~50 in natural units; random-init / BN'd features give ~16).  Images above that limit take the exact max instead.
-constexpr float kShiftHeadroom = 14.0f, kSafeDiagMax = 72.0f;
-
-// grid (ceil(N/32), B): each CTA computes d_i for 32 rows (one warp per row, 4 rows per warp in flight); the CTA that
-// finishes an image last (counter in global memory, self-resetting) derives d_max, the row shifts and the image's flag.
-__global__ void __launch_bounds__(256) diag_shift_kernel(const __half* __restrict__ fh, float* __restrict__ diag, float2* __restrict__ stats,
-                                                          int* __restrict__ img_skip, int* __restrict__ counters, int N, int dk, float c) {
-  __shared__ float red[8];
-  __shared__ int is_last;
-  const int lane = threadIdx.x & 31, b = blockIdx.y;
-  const int i0 = blockIdx.x * 32 + (threadIdx.x >> 5) * 4;
+//
+// grid (ceil(N/128), B), 1024 threads: each warp computes d_i for 4 rows; the CTA leaves the maximum of its 128 rows in
+// dpart[b, blockIdx.x].  The consumers (probability-pass epilogue, fallback statistics pass) reduce those <= 13 values per
+// image themselves: no atomics, no counters to reset, no second kernel.
+constexpr int kDiagRows = 128, kDiagThreads = 512;
+__global__ void __launch_bounds__(kDiagThreads, 2) diag_kernel(const __half* __restrict__ fh, float* __restrict__ diag, float* __restrict__ dpart,
+                                                             int N, int dk, float c) {
+  __shared__ float red[kDiagThreads / 32];
+  griddep_launch_dependents();
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5, b = blockIdx.y;
   const __half* base = fh + static_cast<size_t>(b) * N * dk;
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = lane; k < dk / 8; k += 32) {
-    uint4 u[4];
+  float* d = diag + static_cast<size_t>(b) * N;
+  const int k8 = dk / 8;                                   // 16-byte chunks per row; dk % 64 == 0 so k8 % 8 == 0
+  float wm = 0.f;
+#pragma unroll 1
+  for (int r = 0; r < kDiagRows / (kDiagThreads / 32); r += 4) {          // 8 rows per warp, 4 at a time
+    const int i0 = blockIdx.x * kDiagRows + wv * (kDiagRows / (kDiagThreads / 32)) + r;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < k8; k += 64) {                  // 8 independent, unconditional 16 B loads in flight per lane
+      const bool second = k + 32 < k8;
+      uint4 u[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) u[q] = (i0 + q < N) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(i0 + q) * dk) + k) : make_uint4(0, 0, 0, 0);
+      for (int q = 0; q < 4; ++q) {
+        const uint4* rowp = reinterpret_cast<const uint4*>(base + static_cast<size_t>(min(i0 + q, N - 1)) * dk);
+        u[2 * q] = ldg_nc_u4(rowp + k);
+        u[2 * q + 1] = ldg_nc_u4(rowp + (second ? k + 32 : k));
+      }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-        s[q] = fmaf(t.x, t.x, fmaf(t.y, t.y, s[q]));
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+          a0 = fmaf(t.x, t.x, a0);
+          a1 = fmaf(t.y, t.y, a1);
+        }
+        if ((q & 1) == 0 || second) s[q >> 1] += a0 + a1;
       }
     }
-  }
-  float* d = diag + static_cast<size_t>(b) * N;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float t = warp_sum(s[q]) * c;
-    if (lane == 0 && i0 + q < N) d[i0 + q] = t;
+    for (int q = 0; q < 4; ++q) {
+      const float t = warp_sum(s[q]) * c;
+      if (i0 + q < N) { wm = fmaxf(wm, t); if (lane == 0) d[i0 + q] = t; }
+    }
   }
-  __threadfence();
+  if (lane == 0) red[wv] = wm;
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(counters + b, 1) == static_cast<int>(gridDim.x) - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  float m = 0.f;
-  for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, __ldcg(d + i));
-  m = warp_max(m);
-  if (lane == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  float dm = 0.f;
-  for (int i = 0; i < 8; ++i) dm = fmaxf(dm, red[i]);
-  for (int i = threadIdx.x; i < N; i += 256) stats[static_cast<size_t>(b) * N + i] = make_float2(sqrtf(__ldcg(d + i) * dm) - kShiftHeadroom, 0.f);
-  if (threadIdx.x == 0) { img_skip[b] = (dm <= kSafeDiagMax) ? 1 : 0; counters[b] = 0; }
-}
-
-// images the bound is not safe for: shift_i = exact row maximum from the statistics-pass partials
-__global__ void __launch_bounds__(256) combine_max_kernel(const float2* __restrict__ part, const int* __restrict__ img_skip, float2* __restrict__ stats,
-                                                           int n_parts, int N, int64_t total) {
-  for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
-    const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
-    if (img_skip[b] != 0) continue;
-    const float2* p = part + static_cast<size_t>(b) * n_parts * N + i;
-    float m = -INFINITY;
-    for (int t = 0; t < n_parts; ++t) m = fmaxf(m, p[static_cast<size_t>(t) * N].x);
-    stats[q].x = m;
+  if (wv == 0) {
+    const float m = warp_max(lane < kDiagThreads / 32 ? red[lane] : 0.f);
+    if (lane == 0) dpart[static_cast<size_t>(b) * gridDim.x + blockIdx.x] = m;
   }
 }
 
-// l_i = sum of the partial sums of the rounded p~; stats <- (shift_i, l_i), inv_l <- 1 / l_i
-__global__ void __launch_bounds__(256) combine_l_kernel(const float* __restrict__ lpart, float2* __restrict__ stats, float* __restrict__ inv_l,
-                                                         int n_parts, int N, int64_t total) {
+// l_i = sum of the partial sums of the rounded p~; stats <- (shift_i, l_i), inv_l <- 1 / l_i   (fp32-NCHW aggregation pass only:
+// the channels-last pass, whose accumulator rows are the queries, does this in its epilogue)
+__global__ void __launch_bounds__(256) combine_l_kernel(const float* __restrict__ lpart, float2* __restrict__ stats, float2* __restrict__ stats2,
+                                                         float* __restrict__ inv_l, int n_parts, int N, int64_t total) {
   for (int64_t q = blockIdx.x * 256LL + threadIdx.x; q < total; q += static_cast<int64_t>(gridDim.x) * 256) {
     const int b = static_cast<int>(q / N), i = static_cast<int>(q - static_cast<int64_t>(b) * N);
     const float* p = lpart + static_cast<size_t>(b) * n_parts * N + i;
     float l = 0.f;
     for (int t = 0; t < n_parts; ++t) l += p[static_cast<size_t>(t) * N];
     stats[q].y = l;
+    if (stats2) stats2[q].y = l;
     inv_l[q] = 1.0f / l;
   }
 }
@@ -845,6 +930,13 @@ int env_int(const char* name, int dflt) {
   return (e && *e) ? atoi(e) : dflt;
 }
 
+// ACAN_PDL=0 launches every pass the ordinary way (A/B measurements)
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) v = env_int("ACAN_PDL", 1) ? 1 : 0;
+  return v == 1;
+}
+
 int cta_group() {
   static int cg = 0;
   if (cg == 0) {
@@ -886,8 +978,7 @@ struct Workspace {
   float* kl_part;  // [B, 2*ceil(N/kMinBN), N]   (also the l partials of the un-normalised probability pass)
   float* diag;     // [B, N]  S_ii * c
   float* inv_l;    // [B, N]
-  int* dmax_bits;  // [B]  arrival counters of diag_shift_kernel (zero between calls: the last CTA of an image resets its counter)
-  int* img_skip;   // [B]
+  float* dpart;    // [B, ceil(N/128)]  per-CTA maxima of the diagonal (diag_kernel)
   size_t bytes;
 };
 
@@ -909,8 +1000,7 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   w.kl_part = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
   w.diag = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.inv_l = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
-  w.dmax_bits = reinterpret_cast<int*>(take(static_cast<size_t>(B) * 4));
-  w.img_skip = reinterpret_cast<int*>(take(static_cast<size_t>(B) * 4));
+  w.dpart = reinterpret_cast<float*>(take(static_cast<size_t>(B) * ((N + kDiagRows - 1) / kDiagRows) * 4));
   w.bytes = off;
   return w;
 }
@@ -934,11 +1024,13 @@ int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g.pdl && use_pdl()) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG, AMN, BMN>, ta, tb, tout, g);
   if (e != cudaSuccess) return fail((int)e, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return launch_status("acan gemm_kernel");
@@ -976,7 +1068,7 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
     ProfScope ps(PROF_STATS, st);
     g.part = w.part;
     if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;
-    combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, 2 * g.n_tiles, N, B);
+    combine_stats_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(w.part, stats, stats != w.stats ? w.stats : nullptr, 2 * g.n_tiles, N, B);
     if (int e = launch_status("combine_stats_kernel")) return e;
   }
   if (want_p || sim_map || kl) {
@@ -1009,11 +1101,13 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
   return 0;
 }
 
-// Inference fast path over S = Fh Fh^T: no statistics pass.  Row shifts come from the Cauchy-Schwarz bound (diag_kernel,
-// shift_kernel); the probability pass writes un-normalised fp16 p~ and per-row sums of exactly those rounded values; the
-// aggregation pass divides by them.  Images whose diagonal is too large for the bound (img_skip == 0) still get the exact
-// row maximum: the statistics kernel is launched for them alone (its tiles for the other images are skipped on device).
-int run_affinity_fast(const Workspace& w, const __half* fh, float2* stats, int B, int N, int dk, float scale, cudaStream_t st) {
+// Inference fast path over S = Fh Fh^T: no statistics pass.  Row shifts come from the Cauchy-Schwarz bound (diag_kernel);
+// the probability pass writes un-normalised fp16 p~ and per-row partial sums of exactly those rounded values; the
+// aggregation pass adds them up and divides (combine_l: by a separate kernel, for the fp32-NCHW aggregation pass whose
+// accumulator columns are the queries).  Images whose diagonal is too large for the bound still get the exact row maximum:
+// the statistics kernel is always launched, skips the tiles of safe images on the device and exits in its first
+// instructions when every image is safe -- no host synchronisation either way.
+int run_affinity_fast(const Workspace& w, const __half* fh, float2* stats, int B, int N, int dk, float scale, cudaStream_t st, bool combine_l, int* l_parts) {
   const int cg = cta_group();
   const int m_tiles = (N + BM * cg - 1) / (BM * cg);
   const int bn = env_int("ACAN_BN_QK", choose_bn(N, B * m_tiles, cg, 64));
@@ -1026,30 +1120,32 @@ int run_affinity_fast(const Workspace& w, const __half* fh, float2* stats, int B
   g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (N + bn - 1) / bn; g.k_steps = dk / BK;
   g.m_rows = N; g.n_cols = N; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg); g.c = scale * kLog2e;
   g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
-  const int64_t rows = static_cast<int64_t>(B) * N;
-  const int grid_rows = static_cast<int>((rows + 255) / 256);
+  g.part = w.part;
+  g.dpart = w.dpart;
+  g.n_dpart = (N + kDiagRows - 1) / kDiagRows;
   {
     ProfScope ps(PROF_STATS, st);
-    ACAN_CUDA(cudaMemsetAsync(w.dmax_bits, 0, static_cast<size_t>(B) * 4, st));
-    diag_shift_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(fh, w.diag, stats, w.img_skip, w.dmax_bits, N, dk, g.c);
-    if (int e = launch_status("diag_shift_kernel")) return e;
-    g.part = w.part;
-    g.img_skip = w.img_skip;
-    if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;
-    combine_max_kernel<<<grid_rows, 256, 0, st>>>(w.part, w.img_skip, stats, 2 * g.n_tiles, N, rows);
-    if (int e = launch_status("combine_max_kernel")) return e;
+    diag_kernel<<<dim3(g.n_dpart, B), kDiagThreads, 0, st>>>(fh, w.diag, w.dpart, N, dk, g.c);
+    if (int e = launch_status("diag_kernel")) return e;
+    g.pdl = 1;
+    if (int e = launch_gemm<MODE_STATS>(ta, tb, tp, g, st, cg)) return e;     // exits at once unless an image is above the safe bound
   }
   {
     ProfScope ps(PROF_PROBS, st);
-    g.img_skip = nullptr;
-    g.stats = stats;
+    g.diag = w.diag;
+    g.stats_w = stats;
+    g.stats_w2 = stats != w.stats ? w.stats : nullptr;
     g.store_p = 1;
     g.unnorm = 1;
     g.lpart = w.kl_part;
     if (int e = launch_gemm<MODE_PROBS>(ta, tb, tp, g, st, cg)) return e;
-    combine_l_kernel<<<grid_rows, 256, 0, st>>>(w.kl_part, stats, w.inv_l, 2 * g.n_tiles, N, rows);
-    if (int e = launch_status("combine_l_kernel")) return e;
+    if (combine_l) {
+      const int64_t rows = static_cast<int64_t>(B) * N;
+      combine_l_kernel<<<static_cast<int>((rows + 255) / 256), 256, 0, st>>>(w.kl_part, stats, g.stats_w2, w.inv_l, 2 * g.n_tiles, N, rows);
+      if (int e = launch_status("combine_l_kernel")) return e;
+    }
   }
+  *l_parts = 2 * g.n_tiles;
   return 0;
 }
 
@@ -1102,12 +1198,12 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
 
   int nt = 0;
   const bool fast = value && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  int l_parts = 0;
   if (fast) {
-    if (int e = run_affinity_fast(w, w.fh, stats, B, N, dk, scale, st)) return e;
+    if (int e = run_affinity_fast(w, w.fh, stats, B, N, dk, scale, st, true, &l_parts)) return e;
   } else {
     if (int e = run_affinity(w, w.fh, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
   }
-  ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
   if (dis_label) {
     ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
     if (int e = launch_status("ordered_sum_kernel")) return e;
@@ -1166,12 +1262,12 @@ extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, v
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
   int nt = 0;
   const bool fast = value_h && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  int l_parts = 0;
   if (fast) {
-    if (int e = run_affinity_fast(w, fh, stats, B, N, dk, scale, st)) return e;
+    if (int e = run_affinity_fast(w, fh, stats, B, N, dk, scale, st, false, &l_parts)) return e;
   } else {
     if (int e = run_affinity(w, fh, stats, value_h != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
   }
-  ACAN_CUDA(cudaMemcpyAsync(w.stats, stats, static_cast<size_t>(B) * N * 8, cudaMemcpyDeviceToDevice, st));
   if (dis_label) {
     ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
     if (int e = launch_status("ordered_sum_kernel")) return e;
@@ -1191,7 +1287,11 @@ extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, v
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (dv + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
     g.m_rows = N; g.n_cols = dv; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg, true); g.c = 0.f;
     g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
-    g.inv_l = fast ? w.inv_l : nullptr;
+    if (fast) {
+      g.l_in = w.kl_part; g.l_parts = l_parts;
+      g.stats_w = stats; g.stats_w2 = stats != w.stats ? w.stats : nullptr;
+      g.pdl = 1;                         // directly behind the probability pass
+    }
     ProfScope ps(PROF_PV, st);
     if (int e = launch_gemm<MODE_PVT>(ta, tb, to, g, st, cg)) return e;
   }
