@@ -34,6 +34,9 @@ SIGNATURES = {
     "acan_ordinal_loss_ws_floats": (c_int, []),
     "acan_ordinal_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_void_p]),
     "acan_ordinal_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_void_p]),
+    "acan_tail_loss_ws_floats": (c_size_t, [c_int, c_int, c_int]),
+    "acan_tail_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "acan_tail_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "acan_continuous2discrete": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int, c_void_p]),
     "acan_pool_branch_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "acan_pool_nhwc_scratch_floats": (c_size_t, [c_int, c_int, c_int]),

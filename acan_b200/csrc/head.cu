@@ -476,6 +476,187 @@ __global__ void __launch_bounds__(kThreads) ord_loss_bwd_kernel(const float4* __
 }  // namespace
 }  // namespace acan
 
+// ---------------------------------------------------------------- fused classifier tail + ordinal loss (training; rows f-1 x f-2)
+// loss = OrdinalRegression2d(decode_ord(upsample_x8(z)), label) straight from the stride-8 pair logits z [B,h,w,2K]
+// (model.py:123-125, 228-230, 40-45; losses.py:103-158).  The full-resolution logits [B,2K,H,W] (58 MB / NYU image), their
+// gradient and both upsampling passes of the unfused step never touch HBM: forward reads 0.9 MB / image + the labels,
+// backward writes the 0.9 MB gradient of z.
+//   forward : tail_kernel's tiling (8 x 32 output pixels per CTA, <= 3 x 6 source pixels staged in shared memory).
+//   backward: dL/dz[sr,sc,2k+1] = sum over the <= 18 x 18 output pixels whose bilinear taps touch (sr,sc) of
+//             wy wx dL/dy1(Y,X,k); a thread owns one (source pixel, k), recomputes the interpolated pair from its 3 x 3
+//             source neighbourhood held in registers and gathers in a fixed order (deterministic, no atomics);
+//             dL/dz[..,2k] = -dL/dz[..,2k+1].
+namespace acan {
+namespace {
+
+__global__ void __launch_bounds__(kTailRows * kTailCols)
+tail_loss_fwd_kernel(const float* __restrict__ z, const int64_t* __restrict__ label, float2* __restrict__ partial,
+                     int h, int w, int K, int ignore_index) {
+  extern __shared__ float patch[];                       // [kTailSrcR][kTailSrcC][2K + 2]
+  __shared__ float red_s[kTailRows], red_c[kTailRows];
+  const int C = 2 * K, CP = C + 2;
+  const int H = 8 * h, W = 8 * w;
+  const int b = blockIdx.z, Y0 = blockIdx.y * kTailRows, X0 = blockIdx.x * kTailCols;
+  const float rh = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float rw = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const int r0 = (int)(rh * (float)Y0), c0 = (int)(rw * (float)X0);
+  const float* zb = z + (int64_t)b * h * w * C;
+  for (int i = threadIdx.x; i < kTailSrcR * kTailSrcC * C; i += kTailRows * kTailCols) {
+    const int c = i % C, rc = i / C, cc = rc % kTailSrcC, rr = rc / kTailSrcC;
+    const int sr = min(r0 + rr, h - 1), sc = min(c0 + cc, w - 1);
+    patch[(rr * kTailSrcC + cc) * CP + c] = __ldg(zb + ((int64_t)sr * w + sc) * C + c);
+  }
+  __syncthreads();
+  const int Y = Y0 + (threadIdx.x >> 5), X = X0 + (threadIdx.x & 31);
+  float sum = 0.f, cnt = 0.f;
+  if (X < W && Y < H) {
+    const int l = (int)label[((int64_t)b * H + Y) * W + X];
+    if (l != ignore_index) {
+      const float h1r = rh * (float)Y, w1r = rw * (float)X;
+      const int h1 = (int)h1r, w1 = (int)w1r;
+      const int h1p = (h1 < h - 1) ? 1 : 0, w1p = (w1 < w - 1) ? 1 : 0;
+      const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+      const float* p00 = patch + ((h1 - r0) * kTailSrcC + (w1 - c0)) * CP;
+      const float* p01 = p00 + w1p * CP;
+      const float* p10 = p00 + h1p * kTailSrcC * CP;
+      const float* p11 = p10 + w1p * CP;
+      for (int k = 0; k < K; ++k) {
+        const float2 a = *reinterpret_cast<const float2*>(p00 + 2 * k), bq = *reinterpret_cast<const float2*>(p01 + 2 * k);
+        const float2 c = *reinterpret_cast<const float2*>(p10 + 2 * k), d = *reinterpret_cast<const float2*>(p11 + 2 * k);
+        const float y0 = h0l * (w0l * a.x + w1l * bq.x) + h1l * (w0l * c.x + w1l * d.x);
+        const float y1 = h0l * (w0l * a.y + w1l * bq.y) + h1l * (w0l * c.y + w1l * d.y);
+        sum += ord_term(ord_prob(y0, y1), k < l);
+      }
+      cnt = 1.f;
+    }
+  }
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = sum; red_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f, c = 0.f;
+    for (int i = 0; i < kTailRows; ++i) { s += red_s[i]; c += red_c[i]; }
+    partial[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = make_float2(s, c);
+  }
+}
+
+// one thread per (b, sr, sc, k), k fastest: z loads / gradient stores of a warp are contiguous, label loads broadcast.
+// An output pixel (Y,X) touches source row sr either as its upper tap row (h1 == sr) or as its lower one (h1 == sr - 1); the
+// vertical blend of the three source columns is formed once per Y, the horizontal one per X with the two tap columns fixed by
+// the case -- no register-array indexing.  The lanes of a warp share (sr,sc) (a warp spans <= 2 source pixels), so the case
+// branches are uniform.  p is evaluated as 1 / (1 + exp(y0 - y1)) with the fast intrinsics: the gradient needs ~1e-6, not the
+// bit pattern of the reference's e1 / (e0 + e1) that the forward / inference kernels reproduce.
+__global__ void __launch_bounds__(kThreads)
+tail_loss_bwd_kernel(const float* __restrict__ z, const int64_t* __restrict__ label, const float* __restrict__ count,
+                     const float* __restrict__ grad_out, float* __restrict__ gz, int h, int w, int K, int64_t total, int ignore_index) {
+  const int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (t >= total) return;
+  const int k = (int)(t % K);
+  const int64_t pix = t / K;
+  const int sc = (int)(pix % w), sr = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+  const int C = 2 * K, H = 8 * h, W = 8 * w;
+  const float g = __ldg(grad_out) / __ldg(count);
+  const float rh = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float rw = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  float2 zt[3][3];                                        // rows sr-1..sr+1, columns sc-1..sc+1 (clamped; clamped taps are never selected)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int rr = min(max(sr - 1 + i, 0), h - 1), cc = min(max(sc - 1 + j, 0), w - 1);
+      zt[i][j] = __ldg(reinterpret_cast<const float2*>(z + (((int64_t)b * h + rr) * w + cc) * C) + k);
+    }
+  // candidate output rows / columns: rh * Y in [sr - 1, sr + 1); membership is re-checked with the forward's own arithmetic
+  const int Ylo = (h > 1) ? max(0, (int)((float)(sr - 1) / rh) - 1) : 0, Yhi = (h > 1) ? min(H - 1, (int)((float)(sr + 1) / rh) + 1) : H - 1;
+  const int Xlo = (w > 1) ? max(0, (int)((float)(sc - 1) / rw) - 1) : 0, Xhi = (w > 1) ? min(W - 1, (int)((float)(sc + 1) / rw) + 1) : W - 1;
+  const bool last_r = sr == h - 1, last_c = sc == w - 1;   // both taps of the last row / column coincide
+  const int64_t* lab_b = label + (int64_t)b * H * W;
+  float acc = 0.f;
+  for (int Y = Ylo; Y <= Yhi; ++Y) {
+    const float h1r = rh * (float)Y;
+    const int h1 = (int)h1r;
+    const float h1l = h1r - (float)h1, h0l = 1.f - h1l;
+    float2 v[3];
+    float wy;
+    if (h1 == sr - 1) {                                    // (sr - 1 < h - 1 always: the lower tap is row sr)
+      wy = h1l;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[j] = make_float2(h0l * zt[0][j].x + h1l * zt[1][j].x, h0l * zt[0][j].y + h1l * zt[1][j].y);
+    } else if (h1 == sr) {
+      wy = last_r ? 1.f : h0l;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float2 lo = last_r ? zt[1][j] : zt[2][j];
+        v[j] = make_float2(h0l * zt[1][j].x + h1l * lo.x, h0l * zt[1][j].y + h1l * lo.y);
+      }
+    } else {
+      continue;
+    }
+    const float2 vr = last_c ? v[1] : v[2];
+    const int64_t* lab_y = lab_b + (int64_t)Y * W;
+    float rowacc = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      const float w1r = rw * (float)X;
+      const int w1 = (int)w1r;
+      const float w1l = w1r - (float)w1, w0l = 1.f - w1l;
+      float dyl, wx;                                       // y0 - y1 at (Y,X), weight of column sc in it
+      if (w1 == sc - 1) {
+        wx = w1l;
+        dyl = (w0l * v[0].x + w1l * v[1].x) - (w0l * v[0].y + w1l * v[1].y);
+      } else if (w1 == sc) {
+        wx = last_c ? 1.f : w0l;
+        dyl = (w0l * v[1].x + w1l * vr.x) - (w0l * v[1].y + w1l * vr.y);
+      } else {
+        continue;
+      }
+      const int l = (int)__ldg(lab_y + X);
+      if (l == ignore_index) continue;
+      const float p = __fdividef(1.0f, 1.0f + __expf(dyl)), q = 1.0f - p;
+      const float dy1 = (k < l) ? ((p > 1e-8f) ? -q : 0.f) : ((q > 1e-8f) ? p : 0.f);      // clamp windows of log(p) / log(1 - p)
+      rowacc = fmaf(wx, dy1, rowacc);
+    }
+    acc = fmaf(wy, rowacc, acc);
+  }
+  acc *= g;
+  *reinterpret_cast<float2*>(gz + pix * C + 2 * k) = make_float2(-acc, acc);
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" size_t acan_tail_loss_ws_floats(int B, int h, int w) {
+  if (B <= 0 || h <= 0 || w <= 0) return 0;
+  return 2 * (size_t)B * h * ((8 * (size_t)w + acan::kTailCols - 1) / acan::kTailCols) + 8;
+}
+
+extern "C" int acan_tail_loss_fwd(const float* z_nhwc, const int64_t* label, float* loss_out, float* count_out, float* ws,
+                                  int B, int h, int w, int K, int ignore_index, void* stream) {
+  ACAN_CHECK_ARG(z_nhwc && label && loss_out && count_out && ws, "acan_tail_loss_fwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && h > 0 && w > 0 && K > 0 && K <= 2048, "acan_tail_loss_fwd: B=%d h=%d w=%d K=%d invalid", B, h, w, K);
+  ACAN_CHECK_ARG(B <= 65535 && h <= 65535, "acan_tail_loss_fwd: grid too large");
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(z_nhwc) % 8 == 0 && reinterpret_cast<uintptr_t>(ws) % 8 == 0, "acan_tail_loss_fwd: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((8 * w + kTailCols - 1) / kTailCols, h, B);
+  const size_t smem = (size_t)kTailSrcR * kTailSrcC * (2 * K + 2) * sizeof(float);
+  tail_loss_fwd_kernel<<<grid, kTailRows * kTailCols, smem, st>>>(z_nhwc, label, reinterpret_cast<float2*>(ws), h, w, K, ignore_index);
+  if (int e = launch_status("acan_tail_loss_fwd")) return e;
+  ord_loss_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float2*>(ws), (int)(grid.x * grid.y * grid.z), loss_out, count_out);
+  return launch_status("acan_tail_loss_fwd/final");
+}
+
+extern "C" int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, const float* count, const float* grad_out, float* grad_z_nhwc,
+                                  int B, int h, int w, int K, int ignore_index, void* stream) {
+  ACAN_CHECK_ARG(z_nhwc && label && count && grad_out && grad_z_nhwc, "acan_tail_loss_bwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && h > 0 && w > 0 && K > 0, "acan_tail_loss_bwd: sizes must be positive");
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(z_nhwc) % 8 == 0 && reinterpret_cast<uintptr_t>(grad_z_nhwc) % 8 == 0, "acan_tail_loss_bwd: alignment");
+  const int64_t total = (int64_t)B * h * w * K;
+  const int64_t blocks = (total + kThreads - 1) / kThreads;
+  ACAN_CHECK_ARG(blocks <= 0x7fffffffLL, "acan_tail_loss_bwd: problem too large");
+  tail_loss_bwd_kernel<<<(unsigned)blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(z_nhwc, label, count, grad_out, grad_z_nhwc, h, w, K, total,
+                                                                                            ignore_index);
+  return launch_status("acan_tail_loss_bwd");
+}
+
 extern "C" int acan_ordinal_loss_ws_floats(void) { return 2 * acan::kNumSMs * acan::kBlocksPerSM + 8; }
 
 extern "C" int acan_ordinal_loss_fwd(const float* logits, const int64_t* label, float* loss_out, float* count_out, float* ws,

@@ -50,6 +50,24 @@ class FusedOrdinalLoss(torch.autograd.Function):
         return ops.ordinal_loss_backward(y, lab, count, grad_out, ctx.ignore_index), None, None
 
 
+class FusedTailLoss(torch.autograd.Function):
+    """OrdinalRegression2d o decode_ord o Upsample(x8, bilinear, align_corners) on the STRIDE-8 pair logits (model.py:123-125,
+    40-45; losses.py:103-158): the full-resolution logits and their gradient never exist (SURVEY §8f rows f-1 x f-2)."""
+
+    @staticmethod
+    def forward(ctx, z, label, ignore_index):
+        loss, count, z_nhwc, lab = ops.tail_loss_forward(z, label, ignore_index)
+        ctx.save_for_backward(z_nhwc, lab, count)
+        ctx.ignore_index = ignore_index
+        ctx.z_dtype = z.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        z_nhwc, lab, count = ctx.saved_tensors
+        return ops.tail_loss_backward(z_nhwc, lab, count, grad_out, ctx.ignore_index).to(ctx.z_dtype), None, None
+
+
 class PoolBranch(torch.autograd.Function):
     """SADecoder.image_context without the broadcast (sadecoder.py:97-106) -> g [B,H2]."""
 

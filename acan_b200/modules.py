@@ -207,15 +207,27 @@ class LazyLogitsProb:
     ``inference`` through the from-logits head, so the probability tensor and its gradient are never materialised.  Any
     other consumer (e.g. the reference's own loss classes) gets ``decode_ord(logits)`` with the usual autograd."""
 
-    def __init__(self, logits: torch.Tensor, n_c: int):
-        self._logits, self._k, self._dense = logits, n_c, None
+    def __init__(self, logits: Optional[torch.Tensor], n_c: int, z: Optional[torch.Tensor] = None, upsample=None):
+        # either the full-resolution pair logits, or the stride-8 logits `z` plus the module that upsamples them: the drop-in
+        # loss / inference then work from z directly (fused tail kernels) and the full-resolution tensor is built on demand only
+        self._logits, self._k, self._dense, self._z, self._up = logits, n_c, None, z, upsample
+
+    @property
+    def z(self):
+        """stride-8 pair logits [B,2K,h,w] (None when the handle was built from full-resolution logits)."""
+        return self._z
 
     @property
     def logits(self):
+        if self._logits is None:
+            self._logits = self._up(self._z).float()
         return self._logits
 
     @property
     def shape(self):
+        if self._logits is None:
+            b, _, h, w = self._z.shape
+            return torch.Size((b, self._k, 8 * h, 8 * w))
         b, _, h, w = self._logits.shape
         return torch.Size((b, self._k, h, w))
 
@@ -227,7 +239,7 @@ class LazyLogitsProb:
 
     @property
     def device(self):
-        return self._logits.device
+        return (self._z if self._logits is None else self._logits).device
 
     @property
     def dtype(self):
@@ -235,11 +247,11 @@ class LazyLogitsProb:
 
     @property
     def requires_grad(self):
-        return self._logits.requires_grad
+        return (self._z if self._logits is None else self._logits).requires_grad
 
     def materialize(self) -> torch.Tensor:
         if self._dense is None:
-            self._dense = fn.DecodeOrd.apply(self._logits.float())
+            self._dense = fn.DecodeOrd.apply(self.logits.float())
         return self._dense
 
     def __getitem__(self, key):

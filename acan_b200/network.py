@@ -66,7 +66,9 @@ class BaseClassificationModel_(nn.Module):
         mode = "soft" if self.inferenceType == "soft" else "hard"
         if isinstance(y, LazyProb):                      # eval: fused upsample + decode_ord + head on the stride-8 logits
             return y.depth(mode)
-        if isinstance(y, LazyLogitsProb):                # training-mode handle: decode_ord fused into the head
+        if isinstance(y, LazyLogitsProb):                # training-mode handle: decode_ord (and the upsampling) fused into the head
+            if y.z is not None:
+                return ops.tail_inference(y.z.detach(), cls, mode, self.min_depth, self.max_depth, self.num_classes)
             return ops.head_inference(y.logits.detach(), cls, mode, self.min_depth, self.max_depth, self.num_classes, from_logits=True)
         return ops.head_inference(y, cls, mode, self.min_depth, self.max_depth, self.num_classes)
 
@@ -179,12 +181,16 @@ class ResNet(BaseClassificationModel_):
             if self.use_inter and self.classifierType == "OR":
                 inter_y = self.decode_ord(inter_y)
             return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
-        y = self.classifier(x)
-        if self.classifierType == "OR":
-            # lazy_head: 'y' keeps the pair logits; the drop-in ordinal loss / inference fuse decode_ord
-            y = LazyLogitsProb(y.float(), self.num_classes) if self.lazy_head else self.decode_ord(y)
-            if self.use_inter:
-                inter_y = self.decode_ord(inter_y)
+        if self.classifierType == "OR" and self.lazy_head:
+            # 'y' keeps the STRIDE-8 pair logits; the drop-in ordinal loss / inference fuse the x8 upsampling and decode_ord
+            # (SURVEY §8f rows f-1, f-2); any other consumer gets decode_ord(upsample(z)) with the usual autograd
+            y = LazyLogitsProb(None, self.num_classes, z=self.classifier.conv(x), upsample=self.classifier.upsample)
+        else:
+            y = self.classifier(x)
+            if self.classifierType == "OR":
+                y = self.decode_ord(y)
+        if self.classifierType == "OR" and self.use_inter:
+            inter_y = self.decode_ord(inter_y)
         return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
 
     @torch.no_grad()
@@ -240,6 +246,8 @@ class OrdinalRegression2d(nn.Module):
         self.ignore_index = ignore_index
 
     def forward(self, pred, label):
+        if isinstance(pred, LazyLogitsProb) and pred.z is not None:
+            return fn.FusedTailLoss.apply(pred.z, label, self.ignore_index)              # fused with the x8 upsampling and decode_ord
         if isinstance(pred, LazyLogitsProb) and pred.shape[2] * pred.shape[3] % 4 == 0:
             return fn.FusedOrdinalLoss.apply(pred.logits, label, self.ignore_index)      # fused with decode_ord, one pass
         b, c, h, w = pred.shape

@@ -107,6 +107,37 @@ def ordinal_loss_backward(logits: torch.Tensor, label: torch.Tensor, count: torc
     return out
 
 
+def tail_loss_forward(z: torch.Tensor, label: torch.Tensor, ignore_index: int = 0):
+    """(loss, count, z_nhwc, label): OrdinalRegression2d(decode_ord(upsample_x8(z))) from the stride-8 pair logits z [B,2K,h,w]
+    (any float dtype / layout); label [B,8h,8w] bin indices."""
+    if not z.is_cuda:
+        raise _lib.AcanLibraryError("z must be a CUDA tensor: acan_b200 has no CPU path")
+    zz = z.detach().permute(0, 2, 3, 1).float().contiguous()        # [B,h,w,2K] fp32: 0.9 MB per NYU image
+    b, h, w, c2 = zz.shape
+    lab = label.to(device=zz.device, dtype=torch.int64).contiguous()
+    if lab.numel() != b * 64 * h * w:
+        raise _lib.AcanLibraryError(f"label {tuple(lab.shape)} does not match stride-8 logits {tuple(z.shape)}")
+    lib = _lib.load()
+    loss = torch.empty((), device=zz.device, dtype=torch.float32)
+    count = torch.empty((), device=zz.device, dtype=torch.float32)
+    ws = torch.empty(int(lib.acan_tail_loss_ws_floats(b, h, w)), device=zz.device, dtype=torch.float32)
+    with torch.cuda.device(zz.device):
+        _lib.check(lib.acan_tail_loss_fwd(zz.data_ptr(), lab.data_ptr(), loss.data_ptr(), count.data_ptr(), ws.data_ptr(), b, h, w, c2 // 2,
+                                          int(ignore_index), _lib.current_stream()), "acan_tail_loss_fwd")
+    return loss, count, zz, lab
+
+
+def tail_loss_backward(z_nhwc: torch.Tensor, label: torch.Tensor, count: torch.Tensor, grad_out: torch.Tensor, ignore_index: int = 0):
+    """grad of the fused tail loss w.r.t. z, returned as a [B,2K,h,w] view of a channels-last buffer."""
+    b, h, w, c2 = z_nhwc.shape
+    g = grad_out.detach().to(device=z_nhwc.device, dtype=torch.float32).reshape(1).contiguous()
+    out = torch.empty_like(z_nhwc)
+    with torch.cuda.device(z_nhwc.device):
+        _lib.check(_lib.load().acan_tail_loss_bwd(z_nhwc.data_ptr(), label.data_ptr(), count.data_ptr(), g.data_ptr(), out.data_ptr(), b, h, w, c2 // 2,
+                                                  int(ignore_index), _lib.current_stream()), "acan_tail_loss_bwd")
+    return out.permute(0, 3, 1, 2)
+
+
 def continuous2discrete(depth: torch.Tensor, d_min: float, d_max: float, n_c: int) -> torch.Tensor:
     d = _cuda_f32(depth, "depth")
     out = torch.empty_like(d)

@@ -95,6 +95,19 @@ int acan_ordinal_loss_fwd(const float* logits, const int64_t* label, float* loss
 int acan_ordinal_loss_bwd(const float* logits, const int64_t* label, const float* count, const float* grad_out, float* grad_logits,
                           int B, int K, int64_t HW, int ignore_index, void* stream);
 
+/* Training-mode classifier tail fused with the ordinal loss (SURVEY.md §8f rows f-1 x f-2): replaces
+ * nn.Upsample(x8, bilinear, align_corners=True) (model.py:123-125, 228-230) -> decode_ord (model.py:40-45) ->
+ * OrdinalRegression2d (losses.py:103-158) and their three backward passes.  Works from the STRIDE-8 pair logits; the
+ * [B,2K,8h,8w] tensor and its gradient never exist.
+ *   z_nhwc  [B,h,w,2K] fp32 (output of classifier.conv, channels last), label [B,8h,8w] int64 bin indices
+ *   loss_out / count_out: 1 float each (mean over pixels whose label != ignore_index; their number, kept for backward)
+ *   ws: acan_tail_loss_ws_floats(B,h,w) floats.   backward: grad_z_nhwc [B,h,w,2K] = grad_out * dloss/dz (deterministic). */
+size_t acan_tail_loss_ws_floats(int B, int h, int w);
+int acan_tail_loss_fwd(const float* z_nhwc, const int64_t* label, float* loss_out, float* count_out, float* ws,
+                       int B, int h, int w, int K, int ignore_index, void* stream);
+int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, const float* count, const float* grad_out, float* grad_z_nhwc,
+                       int B, int h, int w, int K, int ignore_index, void* stream);
+
 /* continuous2discrete (model.py:19-23, torch-0.4 semantics): metres -> bin index as float, 0 outside (d_min,d_max). */
 int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream);
 

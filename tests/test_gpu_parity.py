@@ -162,6 +162,60 @@ def test_fused_ordinal_loss_against_oracle(b, h, w):
     close(yd.grad, yc.grad, 1e-5)
 
 
+@pytest.mark.parametrize("b,h,w", [(2, 4, 6), (2, 8, 12), (1, 1, 3), (1, 5, 1), (2, 28, 38)])
+def test_fused_tail_loss_against_oracle(b, h, w):
+    """acan_tail_loss_fwd / _bwd (OrdinalRegression2d o decode_ord o x8 bilinear upsampling, from the stride-8 logits) vs
+    autograd through F.interpolate + the oracle in fp64; ragged tile edges (8w % 32 != 0), 1-pixel-high / -wide maps,
+    ignored pixels and saturated pairs included."""
+    from acan_b200 import functions as fn
+    K = 80
+    z = 1.5 * synth.randn(f"tl.z.{h}.{w}", b, 2 * K, h, w)
+    z[0, 0:2, 0, 0] = torch.tensor([60.0, -60.0])          # p -> 0 around the first source pixel
+    z[0, 2:4, h - 1, w - 1] = torch.tensor([-60.0, 60.0])  # p -> 1 around the last one
+    lab = O.continuous2discrete(synth.depth_label(f"tl.lab.{h}.{w}", b, 8 * h, 8 * w, 0.5, 10.5), *NYU).squeeze(1).long()
+    lab[0, 0, 0], lab[0, 0, 1], lab[0, 0, 2], lab[0, 0, 3] = 5, 1, 79, 0
+    zd = z.to(DEV).requires_grad_(True)
+    loss = fn.FusedTailLoss.apply(zd, lab.to(DEV), 0)
+    (2.5 * loss).backward()
+    zc = z.double().requires_grad_(True)
+    up = torch.nn.functional.interpolate(zc, scale_factor=8, mode="bilinear", align_corners=True)
+    want = O.ordinal_regression_loss(O.decode_ord(up), lab)
+    (2.5 * want).backward()
+    assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+    close(zd.grad, zc.grad, 1e-4)
+    # channels-last half-precision logits (what the autocast training step hands over) take the same kernels
+    zh = z.half().to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    loss_h = fn.FusedTailLoss.apply(zh, lab.to(DEV), 0)
+    loss_h.backward()
+    zc2 = z.half().double().requires_grad_(True)
+    want_h = O.ordinal_regression_loss(O.decode_ord(torch.nn.functional.interpolate(zc2, scale_factor=8, mode="bilinear", align_corners=True)), lab)
+    want_h.backward()
+    assert zh.grad.dtype == torch.float16 and abs(float(loss_h) - float(want_h)) <= 1e-5 * abs(float(want_h))
+    close(zh.grad.float(), zc2.grad, 2e-3)
+
+
+def test_fused_tail_loss_full_size_matches_unfused_kernels():
+    """C4 shape (B=8, 256x352): the stride-8 kernels == upsample (ATen) + acan_ordinal_loss_fwd/bwd on the full-resolution
+    logits, loss to 1e-5 and the gradient of z to 1e-4 -- and bit-reproducible run to run (fixed summation order)."""
+    from acan_b200 import functions as fn
+    b, h, w, K = 8, 32, 44, 80
+    torch.manual_seed(synth.SEED)
+    z = (2.0 * torch.randn(b, 2 * K, h, w, device=DEV))
+    lab = torch.randint(0, K, (b, 8 * h, 8 * w), device=DEV)
+    z1 = z.clone().requires_grad_(True)
+    l1 = fn.FusedTailLoss.apply(z1, lab, 0)
+    l1.backward()
+    z2 = z.clone().requires_grad_(True)
+    l2 = fn.FusedOrdinalLoss.apply(torch.nn.functional.interpolate(z2, scale_factor=8, mode="bilinear", align_corners=True), lab, 0)
+    l2.backward()
+    assert abs(float(l1) - float(l2)) <= 1e-5 * abs(float(l2))
+    close(z1.grad, z2.grad, 1e-4)
+    z3 = z.clone().requires_grad_(True)
+    l3 = fn.FusedTailLoss.apply(z3, lab, 0)
+    l3.backward()
+    assert torch.equal(l1, l3) and torch.equal(z1.grad, z3.grad)
+
+
 def test_decode_ord_backward_matches_autograd():
     from acan_b200 import functions as fn
     y = (2 * torch.randn(2, 160, 8, 12, device=DEV)).requires_grad_(True)
