@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libacan_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class AcanLibraryError(RuntimeError):
@@ -37,6 +37,9 @@ SIGNATURES = {
     "acan_tail_loss_ws_floats": (c_size_t, [c_int, c_int, c_int]),
     "acan_tail_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "acan_tail_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "acan_bn_ws_floats": (c_size_t, [c_int]),
+    "acan_bn_train_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_float, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "acan_bn_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_int64, c_int, c_void_p]),
     "acan_continuous2discrete": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int, c_void_p]),
     "acan_pool_branch_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "acan_pool_nhwc_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
@@ -45,7 +48,7 @@ SIGNATURES = {
     "acan_attn_fwd": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_loss": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "acan_attn_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
+    "acan_attn_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_nhwc_f16": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attention_loss": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_int, c_void_p]),

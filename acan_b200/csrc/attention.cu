@@ -83,7 +83,8 @@ struct GemmArgs {
   const float* ds_delta; // MODE_DS: [B, N] delta_i = sum_c dO[c,i] O[c,i]
   const __half* ds_p;    //   [B, N, N] fp16 probabilities
   const float* ds_klT;   //   [B, N] in-window target mass T_i (attention-loss term), with logbin / lnz above
-  float ds_gk;           //   dLoss/dloss3 / (B N)
+  const float* ds_gl;    //   device scalar dLoss/dloss3 (null = no attention-loss term);  gk = *ds_gl * ds_inv_bn
+  float ds_inv_bn;       //   1 / (B N)
   const float* gscale; // backward: device pair (s, 1/s), the power-of-two gradient scale that keeps fp16 dO / dS in range
   const float* inv_l;  // MODE_PV / MODE_PVT: [B, N] 1 / l_i applied per query while the accumulator leaves TMEM (null = already normalised)
   int pdl;             // host only: launch as a programmatic dependent of the previous kernel in the stream (one of ours, see griddep_wait)
@@ -463,7 +464,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
         const float gs = g.gscale ? __ldg(g.gscale) : 1.0f;          // dP already carries the scale (dO was packed scaled)
         const float delta_i = g.ds_delta[brow] * gs;
-        const float gks = g.ds_gk * gs;
+        const float gks = (g.ds_gl ? __ldg(g.ds_gl) * g.ds_inv_bn : 0.f) * gs;
         const bool kl = g.logbin != nullptr;
         float la_i = 0.f, lnz_i = 0.f, t_i = 0.f;
         if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; t_i = g.ds_klT[brow]; }
@@ -803,12 +804,17 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const float* __restrict_
   }
 }
 
-// (s, 1/s): power of two that brings amax |dO| to 2^-2, or a host-chosen value when amax_bits is null
-__global__ void gscale_kernel(const int* __restrict__ amax_bits, float host_scale, float* __restrict__ sc) {
-  float s = host_scale;
+// (s, 1/s): power of two that brings amax |dO| to 2^-2 -- or, without an aggregation gradient, the attention-loss gradient scale to ~1;
+// chosen on the device: the loss gradient arrives as a device scalar, the step never synchronises with the host
+__global__ void gscale_kernel(const int* __restrict__ amax_bits, const float* __restrict__ grad_loss, float inv_bn, float* __restrict__ sc) {
+  float s = 1.0f;
   if (amax_bits != nullptr) {
     const float am = __int_as_float(*amax_bits);
     s = (am > 0.f && am < INFINITY) ? exp2f(-2.0f - ceilf(log2f(am))) : 1.0f;
+  } else if (grad_loss != nullptr) {
+    // loss-only backward: |dS| <= gk = |dLoss/dloss3| / (B N); bring it to ~1
+    const float gk = fabsf(*grad_loss * inv_bn);
+    s = (gk > 0.f && gk < INFINITY) ? exp2f(-ceilf(log2f(gk))) : 1.0f;
   }
   sc[0] = s;
   sc[1] = 1.0f / s;
@@ -825,7 +831,9 @@ __global__ void __launch_bounds__(256) scaled_sum_kernel(const float4* __restric
 
 // attention-loss-only dS (no aggregation gradient): dS_ij = -gk (W_ij [in window] - P_ij T_i), one CTA per row, scaled fp16 out
 __global__ void __launch_bounds__(256) kl_ds_kernel(const __half* __restrict__ p, const float* __restrict__ logbin, const float* __restrict__ lnz,
-                                                     const float* __restrict__ klT, __half* __restrict__ ds, float gk, int N) {
+                                                     const float* __restrict__ klT, __half* __restrict__ ds, const float* __restrict__ grad_loss,
+                                                     float inv_bn, const float* __restrict__ gscale, int N) {
+  const float gk = __ldg(grad_loss) * inv_bn * __ldg(gscale);
   const int64_t row = blockIdx.x;
   const int b = static_cast<int>(row / N);
   const float la_i = logbin[row], lnz_i = lnz[row], t_i = klT[row];
@@ -1390,7 +1398,7 @@ extern "C" size_t acan_attn_bwd_workspace_bytes(int B, int N, int dk, int dv) {
 // Gradients of ctx = aggregate(softmax(F^T F scale), V) (+ grad_loss * attention loss) w.r.t. F and V, on tcgen05.
 //   dV = dO P        dP = dO^T V        dS = P o (dP - delta) [+ loss term]        dF = scale * F (dS + dS^T)
 extern "C" int acan_attn_bwd(const float* feat, const float* value, const float* ctx, const float* row_stats, const float* grad_ctx,
-                             const float* dis_label, int H, int Wd, float grad_loss,
+                             const float* dis_label, int H, int Wd, const float* grad_loss,
                              float* grad_feat, float* grad_value, void* workspace, size_t workspace_bytes,
                              int B, int N, int dk, int dv, float scale, void* stream) {
   ACAN_CHECK_ARG(feat && row_stats && grad_feat && workspace, "acan_attn_bwd: null pointer");
@@ -1413,19 +1421,19 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
   pack_feat_kernel<<<dim3((N + 63) / 64, dk / 64, B), 256, 0, st>>>(feat, w.f.fh, dk, N);
   if (int e = launch_status("pack_feat_kernel")) return e;
   if (int e = cast_launch(feat, w.fb, static_cast<int64_t>(B) * dk * N, nullptr, st, "pack F (NCHW fp16)")) return e;
-  const float gk = dis_label ? grad_loss / (static_cast<float>(B) * static_cast<float>(N)) : 0.f;
+  ACAN_CHECK_ARG(!dis_label || grad_loss, "acan_attn_bwd: a label needs grad_loss (device scalar)");
+  const float inv_bn = 1.0f / (static_cast<float>(B) * static_cast<float>(N));
   if (agg) {
     // delta_i and max |dO| in one pass over dO; the power-of-two scale s keeps fp16 dO and dS in range whatever the loss scale
     ACAN_CUDA(cudaMemsetAsync(w.amax_bits, 0, 4, st));
     delta_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(grad_ctx, ctx, w.delta, w.amax_bits, dv, N);
     if (int e = launch_status("delta_kernel")) return e;
-    gscale_kernel<<<1, 1, 0, st>>>(w.amax_bits, 1.0f, w.gscale);
+    gscale_kernel<<<1, 1, 0, st>>>(w.amax_bits, nullptr, inv_bn, w.gscale);
     if (int e = launch_status("gscale_kernel")) return e;
     if (int e = cast_launch(value, w.f.vh, static_cast<int64_t>(B) * dv * N, nullptr, st, "pack V")) return e;
     if (int e = cast_launch(grad_ctx, w.doh, static_cast<int64_t>(B) * dv * N, w.gscale, st, "pack dO")) return e;
   } else {
-    // loss-only: |dS| <= gk, bring it to ~1
-    gscale_kernel<<<1, 1, 0, st>>>(nullptr, std::exp2(-std::ceil(std::log2(std::fabs(gk) > 0.f ? std::fabs(gk) : 1.0f))), w.gscale);
+    gscale_kernel<<<1, 1, 0, st>>>(nullptr, grad_loss, inv_bn, w.gscale);
     if (int e = launch_status("gscale_kernel")) return e;
   }
   // normalised P from the saved statistics (+ in-window target mass T_i for the loss term)
@@ -1458,13 +1466,12 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
       if (int e = make_tmap(&tb, w.f.vh, 2, N, dv, B, static_cast<size_t>(N) * 2, static_cast<size_t>(dv) * N * 2, 64)) return e;
       if (int e = make_tmap(&to, w.ds, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
       GemmArgs g = gemm_args(B, N, N, dv, bn, cg, umma_idesc_f16(bn, BM * cg, true, true, false));
-      g.ds_delta = w.delta; g.ds_p = w.f.p; g.ds_klT = w.klT; g.ds_gk = gk; g.gscale = w.gscale;
+      g.ds_delta = w.delta; g.ds_p = w.f.p; g.ds_klT = w.klT; g.ds_gl = dis_label ? grad_loss : nullptr; g.ds_inv_bn = inv_bn; g.gscale = w.gscale;
       g.logbin = dis_label ? w.f.logbin : nullptr; g.lnz = w.f.lnz;
       if (int e = launch_gemm<MODE_DS, true, true>(ta, tb, to, g, st, cg)) return e;
     }
   } else {
-    kl_ds_kernel<<<static_cast<int>(rows), 256, 0, st>>>(w.f.p, w.f.logbin, w.f.lnz, w.klT, w.ds,
-                                                         gk * std::exp2(-std::ceil(std::log2(std::fabs(gk) > 0.f ? std::fabs(gk) : 1.0f))), N);
+    kl_ds_kernel<<<static_cast<int>(rows), 256, 0, st>>>(w.f.p, w.f.logbin, w.f.lnz, w.klT, w.ds, grad_loss, inv_bn, w.gscale, N);
     if (int e = launch_status("kl_ds_kernel")) return e;
   }
   {  // dF[c, i] = scale / s * sum_j (dS[i, j] + dS[j, i]) F[c, j]: two fp16 GEMMs over the same (scaled) dS buffer

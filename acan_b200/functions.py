@@ -68,6 +68,58 @@ class FusedTailLoss(torch.autograd.Function):
         return ops.tail_loss_backward(z_nhwc, lab, count, grad_out, ctx.ignore_index).to(ctx.z_dtype), None, None
 
 
+class BatchNormAct(torch.autograd.Function):
+    """nn.BatchNorm2d in train() (+ residual add, + ReLU) on channels_last half-precision activations: two HBM-bound kernels
+    forward, two backward (acan_bn_train_fwd / _bwd) instead of the framework's generic statistics / transform / clamp / add
+    passes.  Running statistics are updated in place inside the forward kernel, like F.batch_norm does."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu):
+        y, mean, invstd = ops.bn_train_forward(x, weight, bias, running_mean, running_var, momentum, eps, relu, residual)
+        ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+        ctx.has_residual = residual is not None
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        gx, gres, gw, gb = ops.bn_train_backward(x, y, grad_y, weight, mean, invstd, ctx.has_residual and ctx.needs_input_grad[3])
+        if gres is not None and gres.dtype != ctx.res_dtype:
+            gres = gres.to(ctx.res_dtype)
+        return gx, gw.to(weight.dtype), gb.to(weight.dtype), gres, None, None, None, None, None
+
+
+FUSED_BN = True          # A/B switch: False routes every BatchNorm through the framework's own kernels
+
+
+def bn_act(bn, x, relu: bool, residual=None, momentum=None):
+    """``[relu](bn(x) [+ residual])`` for an ``nn.BatchNorm2d``: the fused kernels when ``bn`` is in train() on channels_last
+    half-precision CUDA activations (the autocast training step), the framework's own ops otherwise (fp32 / NCHW / eval)."""
+    if FUSED_BN and bn.training and bn.affine and ops.bn_supported(x):
+        m = bn.momentum if momentum is None else momentum
+        if bn.track_running_stats:
+            if m is None:                                     # cumulative moving average (momentum=None)
+                m = 1.0 / float(bn.num_batches_tracked + 1)
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            rm, rv = bn.running_mean, bn.running_var
+        else:
+            rm, rv, m = None, None, 0.0
+        return BatchNormAct.apply(x, bn.weight.float(), bn.bias.float(), residual, rm, rv, float(m), float(bn.eps), bool(relu))
+    if momentum is not None and bn.training:
+        keep, bn.momentum = bn.momentum, momentum
+        try:
+            y = bn(x)
+        finally:
+            bn.momentum = keep
+    else:
+        y = bn(x)
+    if residual is not None:
+        y = y + residual
+    return torch.relu(y) if relu else y
+
+
 class PoolBranch(torch.autograd.Function):
     """SADecoder.image_context without the broadcast (sadecoder.py:97-106) -> g [B,H2]."""
 
@@ -125,7 +177,7 @@ class Attention(torch.autograd.Function):
     def backward(ctx, grad_ctx, grad_loss):
         feat, value, out, row_stats, dis_label = ctx.saved_tensors
         lab = dis_label if dis_label.numel() else None
-        g_feat, g_value = ops.attention_backward(feat, row_stats, value, out, grad_ctx, lab, float(grad_loss) if lab is not None else 0.0)
+        g_feat, g_value = ops.attention_backward(feat, row_stats, value, out, grad_ctx, lab, grad_loss if lab is not None else 0.0)
         return g_feat.view_as(feat), g_value.view_as(value), None, None
 
 

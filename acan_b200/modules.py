@@ -332,16 +332,12 @@ class PixelAttentionBlock_(nn.Module):
         momentum (nothing is modified in place after the forward, so autograd's saved buffers stay valid)."""
         bn = self.f_key.bn
         twice = self.training and bn.track_running_stats and bn.momentum is not None
-        if not twice:
-            return self.f_key(x)
-        m = bn.momentum
-        bn.momentum = m * (2.0 - m)
-        try:
-            feat = self.f_key(x)
-        finally:
-            bn.momentum = m
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
+        # conv -> BN -> ReLU; on channels_last half-precision activations in train() the BN + ReLU run as the fused
+        # batch-statistics kernels (fn.bn_act, SURVEY §8 rows a1 / f-3), otherwise as the framework's own ops
+        feat = fn.bn_act(bn, self.f_key.conv(x), relu=True, momentum=bn.momentum * (2.0 - bn.momentum) if twice else None)
+        if twice:
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
         return feat
 
     def forward_att(self, x):
@@ -516,5 +512,5 @@ class FusedAttentionLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         feat, dis_label = ctx.saved_tensors
-        g, _ = ops.attention_backward(feat, ctx.row_stats, dis_label=dis_label, grad_loss=float(grad_out))   # loss-only branch of acan_attn_bwd
+        g, _ = ops.attention_backward(feat, ctx.row_stats, dis_label=dis_label, grad_loss=grad_out)   # loss-only branch of acan_attn_bwd
         return g.view_as(feat), None, None

@@ -119,11 +119,12 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        skip = x if self.downsample is None else self.downsample(x)
-        t = self.relu(self.bn1(self.conv1(x)))
-        t = self.relu(self.bn2(self.conv2(t)))
-        t = self.bn3(self.conv3(t))
-        return self.relu(t.add_(skip))
+        # fn.bn_act: BN (+ residual add) (+ ReLU) -- the fused batch-statistics kernels in train() on channels_last
+        # half-precision activations (the autocast training step), the framework's own ops otherwise
+        skip = x if self.downsample is None else fn.bn_act(self.downsample[1], self.downsample[0](x), relu=False)
+        t = fn.bn_act(self.bn1, self.conv1(x), relu=True)
+        t = fn.bn_act(self.bn2, self.conv2(t), relu=True)
+        return fn.bn_act(self.bn3, self.conv3(t), relu=True, residual=skip)
 
 
 # (planes, stride, dilation) of the four stages: output stride 8, layer3 dilated x2, layer4 x4 (model.py:177-180)
@@ -164,7 +165,7 @@ class ResNet(BaseClassificationModel_):
         return nn.Sequential(*units)
 
     def encode(self, x):
-        x = self.maxpool(self.relu1(self.bn1(self.conv1(x))))
+        x = self.maxpool(fn.bn_act(self.bn1, self.conv1(x), relu=True))
         x = self.layer3(self.layer2(self.layer1(x)))
         return x, self.layer4(x)
 

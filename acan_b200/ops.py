@@ -138,6 +138,61 @@ def tail_loss_backward(z_nhwc: torch.Tensor, label: torch.Tensor, count: torch.T
     return out.permute(0, 3, 1, 2)
 
 
+# ------------------------------------------------------------------------------------ training-mode BN (+ ReLU, + residual)
+
+_BN_WS = {}          # (device index, stream) -> zero-initialised scratch (arrival counters + partials), grown on demand
+
+
+def _bn_ws(device: torch.device, c: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    need = int(_lib.load().acan_bn_ws_floats(c))
+    t = _BN_WS.get(key)
+    if t is None or t.numel() < need:
+        t = torch.zeros(max(need, int(_lib.load().acan_bn_ws_floats(2048))), device=device, dtype=torch.float32)
+        _BN_WS[key] = t
+    return t
+
+
+def bn_supported(x: torch.Tensor) -> bool:
+    """channels-last (or 1x1-spatial) CUDA fp16 / bf16 activations with C % 8 == 0: what the fused BN kernels take."""
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0
+            and x.numel() > 0 and x.permute(0, 2, 3, 1).is_contiguous())
+
+
+def bn_train_forward(x, weight, bias, running_mean, running_var, momentum, eps, relu, residual=None):
+    """(y, save_mean, save_invstd).  x [B,C,H,W] channels_last half; running statistics updated in place (may be None)."""
+    b, c, h, w = x.shape
+    y = torch.empty_like(x)                                  # preserves the channels_last strides
+    mean = torch.empty(c, device=x.device, dtype=torch.float32)
+    invstd = torch.empty(c, device=x.device, dtype=torch.float32)
+    if residual is not None and not (residual.dtype == x.dtype and residual.shape == x.shape and residual.permute(0, 2, 3, 1).is_contiguous()):
+        residual = residual.to(x.dtype).contiguous(memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().acan_bn_train_fwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, weight.data_ptr(), bias.data_ptr(), _lib.ptr(residual),
+                                                 y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                                 float(momentum), float(eps), int(bool(relu)), _bn_ws(x.device, c).data_ptr(), b * h * w, c,
+                                                 _lib.current_stream()), "acan_bn_train_fwd")
+    return y, mean, invstd
+
+
+def bn_train_backward(x, y, grad_y, weight, mean, invstd, want_residual_grad):
+    """(grad_x, grad_residual | None, grad_weight, grad_bias); y = forward output when a ReLU was fused, else None."""
+    b, c, h, w = x.shape
+    if not (grad_y.dtype == x.dtype and grad_y.permute(0, 2, 3, 1).is_contiguous()):
+        grad_y = grad_y.to(x.dtype).contiguous(memory_format=torch.channels_last)
+    gx = torch.empty_like(x)
+    gres = torch.empty_like(x) if (want_residual_grad and y is not None) else None
+    gw = torch.empty(c, device=x.device, dtype=torch.float32)
+    gb = torch.empty(c, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().acan_bn_train_bwd(x.data_ptr(), _lib.ptr(y), grad_y.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, weight.data_ptr(),
+                                                 mean.data_ptr(), invstd.data_ptr(), gx.data_ptr(), _lib.ptr(gres), gw.data_ptr(), gb.data_ptr(),
+                                                 _bn_ws(x.device, c).data_ptr(), b * h * w, c, _lib.current_stream()), "acan_bn_train_bwd")
+    if want_residual_grad and gres is None:
+        gres = grad_y                                        # no ReLU in between: the upstream gradient passes through unchanged
+    return gx, gres, gw, gb
+
+
 def continuous2discrete(depth: torch.Tensor, d_min: float, d_max: float, n_c: int) -> torch.Tensor:
     d = _cuda_f32(depth, "depth")
     out = torch.empty_like(d)
@@ -278,8 +333,9 @@ _bwd_scratch = {}
 
 def attention_backward(feat: torch.Tensor, row_stats: torch.Tensor, value: Optional[torch.Tensor] = None,
                        ctx: Optional[torch.Tensor] = None, grad_ctx: Optional[torch.Tensor] = None,
-                       dis_label: Optional[torch.Tensor] = None, grad_loss: float = 0.0):
-    """(grad_feat, grad_value | None) from the tcgen05 backward (acan_attn_bwd)."""
+                       dis_label: Optional[torch.Tensor] = None, grad_loss=0.0):
+    """(grad_feat, grad_value | None) from the tcgen05 backward (acan_attn_bwd).  ``grad_loss``: the upstream gradient of the
+    attention loss, a 0-dim CUDA tensor (no host synchronisation: the C ABI takes a device scalar) or a python float."""
     f = _cuda_f32(feat, "feat")
     b, dk, h, w = f.shape
     n = h * w
@@ -301,8 +357,14 @@ def attention_backward(feat: torch.Tensor, row_stats: torch.Tensor, value: Optio
     ptr = (buf.data_ptr() + 1023) // 1024 * 1024
     gf = torch.empty_like(f)
     gv = torch.empty_like(v) if agg else None
+    if lab is None:
+        gl = None
+    elif isinstance(grad_loss, torch.Tensor):
+        gl = grad_loss.detach().to(device=f.device, dtype=torch.float32).reshape(1)
+    else:
+        gl = torch.full((1,), float(grad_loss), device=f.device, dtype=torch.float32)
     with torch.cuda.device(f.device):
-        _lib.check(lib.acan_attn_bwd(f.data_ptr(), _lib.ptr(v), _lib.ptr(o), st.data_ptr(), _lib.ptr(go), _lib.ptr(lab), hh, ww, float(grad_loss),
+        _lib.check(lib.acan_attn_bwd(f.data_ptr(), _lib.ptr(v), _lib.ptr(o), st.data_ptr(), _lib.ptr(go), _lib.ptr(lab), hh, ww, _lib.ptr(gl),
                                      gf.data_ptr(), _lib.ptr(gv), ptr, nbytes, b, n, dk, dv, float(dk) ** -0.5, _lib.current_stream()), "acan_attn_bwd")
     return gf, gv
 

@@ -1,0 +1,76 @@
+"""Training-step driver for the drop-in network: the whole step -- forward, the two fused losses, backward, the gradient
+all-reduce and the optimizer -- captured ONCE into a CUDA graph and replayed.
+
+Why: the step is ~2500 kernel launches (cuDNN convolutions, the fused BN / attention / loss kernels of this package, the
+optimizer); launched eagerly from Python the host cannot stay ahead of a B200 and the GPU idles for a quarter of the step
+(profiles/r01_notes.md).  Nothing on the path synchronises with the host (the attention backward takes its upstream loss
+gradient as a device scalar), so the step is capturable as is.  The reference's trainer (depthest_trainer.py:118-131) calls
+``net(images)``, ``criterion(...)``, ``loss.backward()``, ``optimizer.step()`` every iteration; ``GraphedTrainStep(...)(images,
+labels)`` is that sequence with static input buffers.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(net, criterion, optimizer, images_example, labels_example);  loss = step(images, labels)
+
+    ``criterion(preds, labels, epoch) -> (loss1, loss2, loss3, total)`` as ``ResNet.LossFunc``.  ``reducer`` (optional): a
+    ``parallel.GradAllReducer`` whose bucketed NCCL all-reduces are captured with the backward pass they overlap.
+    ``amp_dtype=None`` runs the step in fp32.  ``graph=False`` keeps the same interface on the eager path (A/B measurements).
+    Shapes are fixed at construction (the network is shape-specialised anyway)."""
+
+    def __init__(self, net, criterion, optimizer, images: torch.Tensor, labels: torch.Tensor, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
+                 reducer=None, epoch: int = 1, warmup: int = 3, graph: bool = True, after_backward: Optional[Callable[[], None]] = None):
+        if not images.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors: acan_b200 has no CPU path")
+        self.net, self.criterion, self.optimizer, self.reducer = net, criterion, optimizer, reducer
+        self.amp_dtype, self.epoch, self.after_backward = amp_dtype, epoch, after_backward
+        self.static_x = images.clone()
+        self.static_y = labels.clone()
+        self.graph = None
+        self.losses = None
+        self.library_launches_per_step = None
+        if not graph:
+            return
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream(images.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):                  # cuDNN autotuning, workspace allocations, optimizer state
+                optimizer.zero_grad(set_to_none=True)
+                self._body()
+        torch.cuda.current_stream(images.device).wait_stream(side)
+        torch.cuda.synchronize(images.device)
+        optimizer.zero_grad(set_to_none=True)                # captured backward re-creates the .grad tensors in the graph's pool
+        self.graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.load().acan_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.losses = self._body()
+        self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0)    # kernels of libacan_b200 in one replay
+
+    def _body(self):
+        with torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
+            preds = self.net(self.static_x)
+            l1, l2, l3, total = self.criterion(preds, self.static_y, self.epoch)
+        total.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        if self.after_backward is not None:
+            self.after_backward()
+        self.optimizer.step()
+        return l1, l2, l3, total
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """one training step; returns the total loss (a device scalar; static across steps when graphed)."""
+        self.static_x.copy_(images, non_blocking=True)
+        self.static_y.copy_(labels, non_blocking=True)
+        if self.graph is None:
+            self.optimizer.zero_grad(set_to_none=True)
+            self.losses = self._body()
+        else:
+            self.graph.replay()
+        return self.losses[3]

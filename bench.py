@@ -158,6 +158,119 @@ def run_reference(args, rank):
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+TRAIN_BATCH = 8
+TRAIN_WORKLOAD = "configs[3]: ACAN training step with attention loss (beta=1, alpha=0), fwd + loss + bwd + SGD, NYU 256x352, batch 8 per GPU"
+
+
+def run_train(args, rank, world, device, lib):
+    """--workload train: BASELINE.json configs[3] (and configs[4] under torchrun): ResNet-101 + CAM + fused ordinal tail loss +
+    fused attention loss, forward + backward + SGD(momentum) step; N > 1 averages gradients with the bucketed NCCL all-reduce
+    of acan_b200.parallel (overlapped with backward).  bf16 autocast, channels_last; the hand-written kernels run in fp16
+    operands / fp32 accumulate (attention) and fp32 (losses)."""
+    import torch.distributed as dist
+    from acan_b200 import ops
+    from acan_b200.modules import AttentionLoss2d
+    from acan_b200.network import OrdinalRegression2d, ResNet
+    from acan_b200.parallel import GradAllReducer
+    B = TRAIN_BATCH
+    torch.manual_seed(2019)
+    net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=1.0, layers=LAYERS101).to(device)
+    net = net.to(memory_format=torch.channels_last).train()
+    crit = net.LossFunc(DMIN, DMAX, K, AppearanceLoss=OrdinalRegression2d(ignore_index=0), AttentionLoss=AttentionLoss2d(scale=1), alpha=0.0, beta=1.0)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9, weight_decay=5e-4)
+    reducer = GradAllReducer(net.parameters(), bucket_mb=32.0)
+    n_rot = 8
+    torch.manual_seed(2019 + rank)
+    host_x = [torch.rand(B, 3, H, W).contiguous(memory_format=torch.channels_last).pin_memory() for _ in range(n_rot)]
+    host_y = [(torch.rand(B, 1, H, W) * 10 + 0.5).mul_((torch.rand(B, 1, H, W) > 0.1).float()).pin_memory() for _ in range(n_rot)]   # ~10 % invalid (0)
+    dev_x = [t.to(device, non_blocking=True) for t in host_x]
+    dev_y = [t.to(device, non_blocking=True) for t in host_y]
+
+    from acan_b200.training import GraphedTrainStep
+    step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
+                            graph=not args.no_graph)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(dev_x[i % n_rot], dev_y[i % n_rot])
+    barrier()
+    launches0 = lib.acan_launch_count()
+    sampler = ClockSampler(device.index)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(dev_x[i % n_rot], dev_y[i % n_rot])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed = e0.elapsed_time(e1) * 1e-3
+    launches = lib.acan_launch_count() - launches0
+    if step.graph is not None:                       # replays do not pass through the library's host-side launch counter
+        launches = step.library_launches_per_step * args.steps
+    assert bool(torch.isfinite(loss)), "training loss is not finite"
+    # end to end: pinned host images + labels in, the loss value out, every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss_host = float(step(host_x[i % n_rot], host_y[i % n_rot]))     # pinned host -> the step's static device buffers, loss -> host
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    t = torch.tensor([elapsed, e2e_elapsed], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed, e2e_elapsed = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # roofline of the dominant hand-written group of the step: attention forward (+ fused loss) and backward, stand-alone, same shape
+    pk = peaks()
+    n = (H // 8) * (W // 8)
+    f = torch.relu(torch.randn(B, 512, H // 8, W // 8, device=device))
+    v = torch.relu(torch.randn(B, 2048, H // 8, W // 8, device=device))
+    lab = torch.randint(0, K, (B, 1, H, W), device=device).float()
+    go = torch.randn(B, 2048, H // 8, W // 8, device=device) * 1e-3
+    o = ops.attention_forward(f, v, dis_label=lab)
+
+    def ev(fn_, iters=10):
+        for _ in range(3):
+            fn_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn_()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / iters
+    t_f = ev(lambda: ops.attention_forward(f, v, dis_label=lab, ws=o["ws"]))
+    t_b = ev(lambda: ops.attention_backward(f, o["row_stats"], v, o["ctx"], go, lab, 1.0))
+    bwd_flops = B * 10240.0 * n * n
+    out = {
+        "metric": "ACAN NYU-shape training images/sec", "value": world * B * args.steps / elapsed, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": TRAIN_WORKLOAD, "parallelism": f"dp{world} (batch-sharded replicas; bucketed NCCL gradient all-reduce overlapped with backward)" if world > 1 else "dp1",
+                   "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd fp16 operands / fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
+                   "launch": "eager" if args.no_graph else "whole step (fwd + losses + bwd + all-reduce + SGD) replayed from one CUDA graph (acan_b200.training.GraphedTrainStep)",
+                   "l2": f"{n_rot} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_elapsed / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "acan_attn_bwd (P recompute, dV, dP -> dS with fused attention-loss term, dF: five tcgen05 GEMMs + packs), fp32-NCHW ABI, stand-alone at the step's shape",
+                     "achieved": bwd_flops / t_b / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": bwd_flops / t_b / 1e12 / pk["tensor"], "traffic": None,
+                     "peak_source": pk["src"] + " (bf16 burst)", "launch_us": t_b * 1e6},
+        "attention_fwd_loss_us": t_f * 1e6, "loss": loss_host, "cpu_baseline": None,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +278,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train workload: launch the step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer (default): BASELINE.json configs[1], the headline.  train: configs[3]/[4], the beta=1 training step, B=8 per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -185,6 +301,9 @@ def main():
     lib = _lib.load()
     _lib.check(lib.acan_device_check(), "acan_device_check")
     torch.backends.cudnn.benchmark = True                 # as depthest_main.py:65
+    if args.workload == "train":
+        run_train(args, rank, world, device, lib)
+        return
 
     net = build_net(device)
     n_rot = 8                                             # 8 distinct input batches = 138 MB > 126 MB L2
@@ -270,6 +389,21 @@ def main():
     torch.cuda.synchronize()
     t_head = h0.elapsed_time(h1) * 1e-4
     del prob
+    # the whole attention core as the step runs it (one acan_attn_fwd_nhwc_f16 call: diagonal, fallback statistics, probability
+    # and aggregation passes chained by programmatic dependent launch), stand-alone at the same shape, no event hooks in between
+    # (the in-step per-pass brackets below record events between the passes, which serialises them)
+    fcl = torch.relu(torch.randn(BATCH, 512, H // 8, W // 8, device=device)).half().contiguous(memory_format=torch.channels_last)
+    vcl = torch.relu(torch.randn(BATCH, 2048, H // 8, W // 8, device=device)).half().contiguous(memory_format=torch.channels_last)
+    ws_core = ops.attention_forward_cl(fcl, vcl)["ws"]
+    for _ in range(3):
+        ops.attention_forward_cl(fcl, vcl, ws=ws_core)
+    h0.record()
+    for _ in range(20):
+        ops.attention_forward_cl(fcl, vcl, ws=ws_core)
+    h1.record()
+    torch.cuda.synchronize()
+    t_core_call = h0.elapsed_time(h1) * 1e-3 / 20
+    del fcl, vcl, ws_core
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
     # profiles/r01_attn_final_channels_last.ncu-rep (155.8 MB + 64.9 MB; algorithmic V 92 + P 63 MB read, O 92 MB fp16 written)
     roof = {"bound": "tensor", "kernel": "gemm_kernel<MODE_PVT, CG=2> (aggregation O = P V on tcgen05, CTA pairs, V read in place MN-major)",
@@ -277,9 +411,12 @@ def main():
             "peak": pk["tensor"], "unit": "TFLOP/s", "frac": pv_flops / t_pv / 1e12 / pk["tensor"], "traffic": 220.7e6,
             "peak_source": pk["src"] + " (bf16 burst)", "launch_us": t_pv * 1e6, "launches_timed": cnt[3]}
     extra = {
-        "attention_core": {"bound": "tensor", "what": "operand pack + stats + probability + aggregation passes, algorithmic 5120*N^2 FLOP/img",
-                           "achieved": core_flops / t_core / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": core_flops / t_core / 1e12 / pk["tensor"],
-                           "us": {"pack": per_launch(0) * 1e6, "stats": per_launch(1) * 1e6, "probs": per_launch(2) * 1e6, "pv": t_pv * 1e6}},
+        "attention_core": {"bound": "tensor", "what": "whole CAM core call (diagonal + fallback statistics + probability + aggregation passes), algorithmic "
+                                   "5120*N^2 FLOP/img, CUDA events around 20 stand-alone calls at the step's shape; `us_in_step` = the per-pass event "
+                                   "brackets inside the timed steps (events between the passes disable their launch overlap)",
+                           "achieved": core_flops / t_core_call / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": core_flops / t_core_call / 1e12 / pk["tensor"],
+                           "call_us": t_core_call * 1e6, "frac_in_step": core_flops / t_core / 1e12 / pk["tensor"],
+                           "us_in_step": {"pack": per_launch(0) * 1e6, "stats": per_launch(1) * 1e6, "probs": per_launch(2) * 1e6, "pv": t_pv * 1e6}},
         "head": {"bound": "hbm", "what": "OR soft inference prob -> depth kernel, 324*HW B/img, measured stand-alone at the same shape", "achieved": head_bytes / t_head / 1e9 if t_head > 0 else None,
                  "peak": pk["hbm"], "unit": "GB/s", "frac": head_bytes / t_head / 1e9 / pk["hbm"] if t_head > 0 else None, "launch_us": t_head * 1e6},
         "tail": {"what": "fused classifier tail in the step: x8 bilinear + decode_ord + OR soft head from stride-8 logits (expf/div-bound; "

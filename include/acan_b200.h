@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ACAN_ABI_VERSION 1
+#define ACAN_ABI_VERSION 2
 
 #define ACAN_ERR_BAD_ARG     10001   /* null pointer, non-positive size, unsupported shape */
 #define ACAN_ERR_WORKSPACE   10002   /* workspace smaller than *_workspace_bytes() */
@@ -108,6 +108,25 @@ int acan_tail_loss_fwd(const float* z_nhwc, const int64_t* label, float* loss_ou
 int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, const float* count, const float* grad_out, float* grad_z_nhwc,
                        int B, int h, int w, int K, int ignore_index, void* stream);
 
+/* Training-mode BatchNorm2d over channels-last half-precision activations fused with the ReLU (and residual add) behind it:
+ * the Q/K projection's BN + ReLU (sadecoder.py:25-30) and, same arithmetic, every
+ * conv -> BN -> ReLU of the backbone (model.py:128-160).  Semantics of nn.BatchNorm2d in train(): batch statistics (biased
+ * variance) normalise, running statistics take the unbiased variance with `momentum`.
+ *   x, y, residual, grad_*: [M, C] (M = B*H*W, channels contiguous), dtype 0 = fp16 / 1 = bf16, C % 8 == 0, 16-byte aligned
+ *   y = [relu]( (x - mean) * invstd * weight + bias [+ residual] );   save_mean / save_invstd [C] fp32 are kept for backward
+ *   running_mean / running_var: NULL (track_running_stats = False) or [C] fp32, updated in place
+ *   ws: acan_bn_ws_floats(C) floats, ZERO-INITIALISED ONCE by the caller (it holds self-resetting arrival counters) and not shared
+ *       between streams.
+ *   backward: y = the forward output when a ReLU was fused (its sign is the mask), else NULL; grad_residual: NULL, or receives the
+ *       masked upstream gradient (what flows into the residual branch); grad_weight / grad_bias [C] fp32. */
+size_t acan_bn_ws_floats(int C);
+int acan_bn_train_fwd(const void* x, int dtype, const float* weight, const float* bias, const void* residual, void* y,
+                      float* save_mean, float* save_invstd, float* running_mean, float* running_var,
+                      float momentum, float eps, int relu, float* ws, int64_t M, int C, void* stream);
+int acan_bn_train_bwd(const void* x, const void* y, const void* grad_y, int dtype, const float* weight,
+                      const float* save_mean, const float* save_invstd, void* grad_x, void* grad_residual,
+                      float* grad_weight, float* grad_bias, float* ws, int64_t M, int C, void* stream);
+
 /* continuous2discrete (model.py:19-23, torch-0.4 semantics): metres -> bin index as float, 0 outside (d_min,d_max). */
 int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream);
 
@@ -165,13 +184,15 @@ int acan_attn_fwd_loss(const float* feat, const float* value, float* ctx, float*
  *   dV = dO P      dP = dO^T V      dS = P o (dP - delta_i) - g/(B N) (W o [clamp window] - P T_i)      dF = scale F (dS + dS^T)
  *   feat, value, ctx (the forward output), row_stats: as given to / returned by the forward call (fp32 NCHW)
  *   grad_ctx   [B,dv,N] fp32, or NULL when only the attention loss is differentiated (value / ctx / grad_value unused)
- *   dis_label  NULL, or the forward's label: adds grad_loss * d(attention loss)/dF
+ *   dis_label  NULL, or the forward's label: adds *grad_loss * d(attention loss)/dF;  grad_loss is a DEVICE scalar (the upstream
+ *              gradient of the loss as autograd hands it over): the call never synchronises with the host and can be captured
+ *              in a CUDA graph
  *   grad_feat  [B,dk,N] fp32, grad_value [B,dv,N] fp32.   workspace: acan_attn_bwd_workspace_bytes(), 1024-byte aligned.
  * P is recomputed from row_stats; every tensor-core operand is fp16 with fp32 accumulation, dO and dS pre-multiplied by a
  * power of two chosen on the device from max|dO| (so the loss scale cannot push them out of the fp16 range). */
 size_t acan_attn_bwd_workspace_bytes(int B, int N, int dk, int dv);
 int acan_attn_bwd(const float* feat, const float* value, const float* ctx, const float* row_stats, const float* grad_ctx,
-                  const float* dis_label, int H, int W, float grad_loss,
+                  const float* dis_label, int H, int W, const float* grad_loss,
                   float* grad_feat, float* grad_value, void* workspace, size_t workspace_bytes,
                   int B, int N, int dk, int dv, float scale, void* stream);
 

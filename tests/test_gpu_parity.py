@@ -226,6 +226,126 @@ def test_decode_ord_backward_matches_autograd():
     close(y.grad, yc.grad, 1e-5)
 
 
+# ------------------------------------------------------------------------------------ training-mode BN (+ ReLU, + residual)
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,c,h,w", [(2, 64, 16, 24), (2, 128, 8, 12), (3, 256, 8, 12), (2, 512, 4, 6), (2, 2048, 4, 6), (1, 24, 5, 7), (2, 320, 4, 4), (8, 64, 128, 176)])
+def test_fused_batchnorm_against_torch_fp64(b, c, h, w, dtype):
+    """acan_bn_train_fwd / _bwd (nn.BatchNorm2d in train() + residual + ReLU on channels_last half activations) vs
+    F.batch_norm + autograd in fp64 on the same (half-rounded) inputs: outputs and dx to half-precision rounding,
+    dgamma / dbeta / running statistics to fp32 accuracy.  Widths cover 8-channel groups that fill a warp (>= 256), that
+    tile it (64, 128), that do not (24) and a ragged last slab (320)."""
+    from acan_b200 import functions as fn
+    tol_half = 2e-3 if dtype == torch.float16 else 1.2e-2
+    for relu, with_res in ((True, False), (False, False), (True, True)):
+        tag = f"bn.{c}.{h}.{relu}.{with_res}"
+        x = (1.5 * synth.randn(tag + ".x", b, c, h, w) + 0.7).to(dtype)
+        res = synth.randn(tag + ".r", b, c, h, w).to(dtype) if with_res else None
+        go = synth.randn(tag + ".g", b, c, h, w).to(dtype)
+        bn = torch.nn.BatchNorm2d(c).to(DEV).train()
+        with torch.no_grad():
+            bn.weight.copy_(1.0 + 0.3 * synth.randn(tag + ".w", c)); bn.bias.copy_(0.2 * synth.randn(tag + ".b", c))
+            bn.running_mean.copy_(synth.randn(tag + ".rm", c)); bn.running_var.copy_(1.0 + synth.rand(tag + ".rv", c))
+        rm0, rv0 = bn.running_mean.double().cpu().clone(), bn.running_var.double().cpu().clone()
+        xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        rd = res.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) if with_res else None
+        y = fn.bn_act(bn, xd, relu=relu, residual=rd)
+        assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last) and int(bn.num_batches_tracked) == 1
+        y.backward(go.to(DEV).contiguous(memory_format=torch.channels_last))
+        # fp64 reference
+        xc = x.double().requires_grad_(True)
+        rc = res.double().requires_grad_(True) if with_res else None
+        wc, bc = bn.weight.detach().double().cpu().requires_grad_(True), bn.bias.detach().double().cpu().requires_grad_(True)
+        rm, rv = rm0.clone(), rv0.clone()
+        yc = torch.nn.functional.batch_norm(xc, rm, rv, wc, bc, True, 0.1, bn.eps)
+        if with_res:
+            yc = yc + rc
+        if relu:
+            yc = torch.relu(yc)
+        yc.backward(go.double())
+        close(y.float(), yc, tol_half)
+        close(xd.grad.float(), xc.grad, tol_half)
+        if with_res:
+            close(rd.grad.float(), rc.grad, tol_half)
+        close(bn.weight.grad, wc.grad, 2e-3 if dtype == torch.float16 else 1e-2)       # the ReLU mask is taken from the ROUNDED output
+        close(bn.bias.grad, bc.grad, 2e-3 if dtype == torch.float16 else 1e-2)
+        close(bn.running_mean, rm, 1e-5)
+        close(bn.running_var, rv, 1e-5)
+
+
+def test_fused_batchnorm_training_step_matches_framework_bn():
+    """tiny ResNet + CAM, bf16 autocast channels_last training step: fused BN kernels vs the framework's BN kernels on the same
+    weights and batch -- losses and BN running statistics (incl. f_key's double update) agree to bf16 noise, and measured against
+    the fp32 step the gradients of the fused pipeline are as accurate as those of the framework's bf16 pipeline."""
+    from acan_b200 import functions as fn
+    from acan_b200.network import ResNet, OrdinalRegression2d
+    from acan_b200.modules import AttentionLoss2d
+    hh, ww, b = 64, 96, 4
+    x = synth.rand("bnstep.x", b, 3, hh, ww).to(DEV).contiguous(memory_format=torch.channels_last)
+    label = synth.depth_label("bnstep.label", b, hh, ww, 0.5, 10.5).to(DEV)
+    res = {}
+    try:
+        for arm in ("fused", "framework", "fp32"):
+            fn.FUSED_BN = arm == "fused"
+            torch.manual_seed(synth.SEED)
+            net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=1.0, layers=[1, 1, 1, 1]).to(DEV).to(memory_format=torch.channels_last).train()
+            for m in net.modules():
+                if isinstance(m, torch.nn.Dropout2d):
+                    m.eval()
+            crit = net.LossFunc(*NYU, AppearanceLoss=OrdinalRegression2d(ignore_index=0), AttentionLoss=AttentionLoss2d(scale=1), alpha=0.0, beta=1.0)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=arm != "fp32"):
+                l1, _, l3, tot = crit(net(x), label, 1)
+            tot.backward()
+            res[arm] = (float(l1), float(l3), {k: v.detach().float().clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k},
+                        {k: p.grad.detach().float().clone() for k, p in net.named_parameters() if p.grad is not None})
+    finally:
+        fn.FUSED_BN = True
+    (a1, a3, sa, ga), (b1, b3, sb, gb), (r1, r3, sr, gr) = res["fused"], res["framework"], res["fp32"]
+    assert abs(a1 - b1) <= 2e-2 * abs(b1) and abs(a3 - b3) <= 5e-2 * abs(b3), (a1, b1, a3, b3)
+    assert abs(a1 - r1) <= 2e-2 * abs(r1) and abs(a3 - r3) <= 5e-2 * abs(r3), (a1, r1, a3, r3)
+    assert set(sa) == set(sb) and set(ga) == set(gb) == set(gr)
+    for k in sa:
+        if "num_batches" in k:
+            assert torch.equal(sa[k], sb[k]), k
+        else:
+            close(sa[k], sr[k], 3e-2)
+    # tensors whose gradient is analytically ~0 (conv biases in front of a BN) are rounding noise in every arm and are left out
+    big = max(float(v.norm()) for v in gr.values())
+    keys = [k for k in gr if float(gr[k].norm()) > 1e-2 * big]
+    ea = {k: float((ga[k] - gr[k]).norm() / gr[k].norm()) for k in keys}
+    eb = {k: float((gb[k] - gr[k]).norm() / gr[k].norm()) for k in keys}
+    bad = {k: (round(ea[k], 3), round(eb[k], 3)) for k in keys if ea[k] > max(2.0 * eb[k], 0.05)}
+    assert len(keys) > 10 and not bad, bad
+    assert sum(ea.values()) <= 1.5 * sum(eb.values()) + 0.02 * len(keys), (sum(ea.values()) / len(keys), sum(eb.values()) / len(keys))
+
+
+def test_graphed_train_step_matches_eager():
+    """acan_b200.training.GraphedTrainStep: the whole step (fwd + fused losses + bwd + SGD) replayed from one CUDA graph gives the
+    same losses as launching it eagerly, step after step (dropout off; same seeds) -- and nothing on the path syncs with the host."""
+    from acan_b200.training import GraphedTrainStep
+    from acan_b200.network import ResNet, OrdinalRegression2d
+    from acan_b200.modules import AttentionLoss2d
+    hh, ww, b = 64, 96, 4
+    xs = [synth.rand(f"gts.x{i}", b, 3, hh, ww).to(DEV).contiguous(memory_format=torch.channels_last) for i in range(3)]
+    ys = [synth.depth_label(f"gts.y{i}", b, hh, ww, 0.5, 10.5).to(DEV) for i in range(3)]
+    out = {}
+    for graph in (True, False):
+        torch.manual_seed(synth.SEED)
+        net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=1.0, layers=[1, 1, 1, 1]).to(DEV).to(memory_format=torch.channels_last).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.eval()
+        crit = net.LossFunc(*NYU, AppearanceLoss=OrdinalRegression2d(ignore_index=0), AttentionLoss=AttentionLoss2d(scale=1), alpha=0.0, beta=1.0)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        step = GraphedTrainStep(net, crit, opt, xs[0], ys[0], amp_dtype=torch.bfloat16, graph=graph, warmup=2)
+        net.load_state_dict(sd0)                              # the capture warm-up stepped the weights: start both arms from the same point
+        opt.state.clear() if not graph else [buf.zero_() for st_ in opt.state.values() for buf in st_.values() if torch.is_tensor(buf)]
+        out[graph] = [float(step(x, y)) for x, y in zip(xs, ys)]
+    for a, e in zip(out[True], out[False]):
+        assert abs(a - e) <= 2e-2 * abs(e), (out[True], out[False])
+
+
 # ------------------------------------------------------------------------------------ pooling branch
 
 def test_pool_branch_against_oracle():
