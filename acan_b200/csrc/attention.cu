@@ -1405,6 +1405,7 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
   const bool agg = grad_ctx != nullptr;           // aggregation gradient present (else: attention-loss gradient only)
   ACAN_CHECK_ARG(!agg || (value && ctx && grad_value), "acan_attn_bwd: value, ctx and grad_value are required with grad_ctx");
   ACAN_CHECK_ARG(agg || dis_label, "acan_attn_bwd: nothing to differentiate (no grad_ctx, no label)");
+  ACAN_CHECK_ARG(!dis_label || grad_loss, "acan_attn_bwd: a label needs grad_loss (device scalar)");
   if (int e = check_attn_shape("acan_attn_bwd", B, N, dk, dv)) return e;
   ACAN_CHECK_ARG(N % 8 == 0 && (static_cast<int64_t>(dk) * N) % 8 == 0, "acan_attn_bwd: N must be a multiple of 8");
   ACAN_CHECK_ARG(!dis_label || (H / 8) * (Wd / 8) == N, "acan_attn_bwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
@@ -1421,7 +1422,6 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
   pack_feat_kernel<<<dim3((N + 63) / 64, dk / 64, B), 256, 0, st>>>(feat, w.f.fh, dk, N);
   if (int e = launch_status("pack_feat_kernel")) return e;
   if (int e = cast_launch(feat, w.fb, static_cast<int64_t>(B) * dk * N, nullptr, st, "pack F (NCHW fp16)")) return e;
-  ACAN_CHECK_ARG(!dis_label || grad_loss, "acan_attn_bwd: a label needs grad_loss (device scalar)");
   const float inv_bn = 1.0f / (static_cast<float>(B) * static_cast<float>(N));
   if (agg) {
     // delta_i and max |dO| in one pass over dO; the power-of-two scale s keeps fp16 dO and dS in range whatever the loss scale

@@ -64,6 +64,7 @@ class GradAllReducer:
         self._pending = [len(b) for b in self.buckets]
         self._work = []
         self._hooks = []
+        self.enabled = True          # False: the hooks stay quiet (backward being captured into a CUDA graph); use reduce_now() after it
         if self.world > 1:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -77,6 +78,8 @@ class GradAllReducer:
         self._work.append((work, flat, ps))
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not self.enabled:
+            return
         bi = self._bucket_of[id(p)]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
@@ -99,6 +102,25 @@ class GradAllReducer:
                     off += n
         self._work = []
         self._pending = [len(b) for b in self.buckets]
+
+    def reduce_now(self) -> None:
+        """average the gradients that are in ``.grad`` right now, bucket by bucket, without the hooks: for a backward pass that
+        ran inside a CUDA graph (a replay is asynchronous, so these launches are queued behind it while it still runs; the
+        all-reduce itself then follows the backward instead of overlapping it: ~1 ms of NVLink time on a ~20 ms step)."""
+        if self.world == 1:
+            return
+        inflight = []
+        for bucket in self.buckets:
+            ps = [p for p in bucket if p.grad is not None]
+            if not ps:
+                continue
+            flat = torch.cat([p.grad.reshape(-1) for p in ps])
+            inflight.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat, ps))
+        for work, flat, ps in inflight:
+            work.wait()
+            flat.div_(self.world)
+            # (.grad of a channels_last weight is not contiguous in logical order: copy through shaped views, never reshape(-1))
+            torch._foreach_copy_([p.grad for p in ps], [c.view(p.grad.shape) for c, p in zip(flat.split([p.numel() for p in ps]), ps)])
 
     def remove(self) -> None:
         for h in self._hooks:

@@ -19,7 +19,9 @@ class GraphedTrainStep:
     """step = GraphedTrainStep(net, criterion, optimizer, images_example, labels_example);  loss = step(images, labels)
 
     ``criterion(preds, labels, epoch) -> (loss1, loss2, loss3, total)`` as ``ResNet.LossFunc``.  ``reducer`` (optional): a
-    ``parallel.GradAllReducer`` whose bucketed NCCL all-reduces are captured with the backward pass they overlap.
+    ``parallel.GradAllReducer``.  With a reducer of world size > 1 the step is two graphs -- forward + losses + backward, then
+    the optimizer -- with the bucketed NCCL all-reduce launched eagerly between the replays (``reducer.reduce_now()``; the
+    replays are asynchronous, so the host queues the collectives while the backward graph still runs).
     ``amp_dtype=None`` runs the step in fp32.  ``graph=False`` keeps the same interface on the eager path (A/B measurements).
     Shapes are fixed at construction (the network is shape-specialised anyway)."""
 
@@ -32,14 +34,18 @@ class GraphedTrainStep:
         self.static_x = images.clone()
         self.static_y = labels.clone()
         self.graph = None
+        self.opt_graph = None
         self.losses = None
         self.library_launches_per_step = None
+        self._split = reducer is not None and getattr(reducer, "world", 1) > 1       # NCCL stays outside the graphs
         if not graph:
             return
+        if self._split:
+            reducer.enabled = False
         side = torch.cuda.Stream(device=images.device)
         side.wait_stream(torch.cuda.current_stream(images.device))
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):                  # cuDNN autotuning, workspace allocations, optimizer state
+            for _ in range(max(warmup, 1)):                  # cuDNN autotuning, workspace allocations, optimizer state, NCCL communicator
                 optimizer.zero_grad(set_to_none=True)
                 self._body()
         torch.cuda.current_stream(images.device).wait_stream(side)
@@ -49,20 +55,31 @@ class GraphedTrainStep:
         from . import _lib
         n0 = _lib.load().acan_launch_count()
         with torch.cuda.graph(self.graph):
-            self.losses = self._body()
+            self.losses = self._body(capture_part=1 if self._split else 0)
         self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0)    # kernels of libacan_b200 in one replay
+        if self._split:
+            self.opt_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.opt_graph, pool=self.graph.pool()):
+                self._body(capture_part=2)
 
-    def _body(self):
-        with torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
-            preds = self.net(self.static_x)
-            l1, l2, l3, total = self.criterion(preds, self.static_y, self.epoch)
-        total.backward()
-        if self.reducer is not None:
-            self.reducer.finish()
-        if self.after_backward is not None:
-            self.after_backward()
-        self.optimizer.step()
-        return l1, l2, l3, total
+    def _body(self, capture_part: int = 0):
+        """capture_part 0: the whole step; 1: forward + losses + backward only; 2: what follows the gradient all-reduce."""
+        out = None
+        if capture_part in (0, 1):
+            with torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
+                preds = self.net(self.static_x)
+                out = self.criterion(preds, self.static_y, self.epoch)
+            out[3].backward()
+        if capture_part == 0 and self.reducer is not None:
+            if self._split and not self.reducer.enabled:
+                self.reducer.reduce_now()                    # warm-up passes of the split mode: hooks are off
+            else:
+                self.reducer.finish()
+        if capture_part in (0, 2):
+            if self.after_backward is not None:
+                self.after_backward()
+            self.optimizer.step()
+        return out
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """one training step; returns the total loss (a device scalar; static across steps when graphed)."""
@@ -73,4 +90,7 @@ class GraphedTrainStep:
             self.losses = self._body()
         else:
             self.graph.replay()
+            if self.opt_graph is not None:
+                self.reducer.reduce_now()
+                self.opt_graph.replay()
         return self.losses[3]

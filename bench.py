@@ -253,7 +253,8 @@ def run_train(args, rank, world, device, lib):
         "metric": "ACAN NYU-shape training images/sec", "value": world * B * args.steps / elapsed, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": TRAIN_WORKLOAD, "parallelism": f"dp{world} (batch-sharded replicas; bucketed NCCL gradient all-reduce overlapped with backward)" if world > 1 else "dp1",
+        "config": {"workload": TRAIN_WORKLOAD, "parallelism": (f"dp{world} (batch-sharded replicas; bucketed NCCL gradient all-reduce " +
+                                   ("overlapped with backward from grad hooks)" if args.no_graph else "between the backward graph and the optimizer graph)")) if world > 1 else "dp1",
                    "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd fp16 operands / fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
                    "launch": "eager" if args.no_graph else "whole step (fwd + losses + bwd + all-reduce + SGD) replayed from one CUDA graph (acan_b200.training.GraphedTrainStep)",
                    "l2": f"{n_rot} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},

@@ -1,5 +1,3 @@
 set -x
-python scripts/bn_time.py
-python -m pytest tests -m gpu -x -q -k batchnorm 2>&1 | tail -3
-python bench.py --workload train --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_train_graph.json
-head -c 400 gpurun_out/bench_train_graph.json; echo
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload train --steps 10 --warmup 3 2>&1 | tail -4 > gpurun_out/bench_train_n2.log
+tail -c 1800 gpurun_out/bench_train_n2.log

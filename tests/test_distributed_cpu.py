@@ -43,6 +43,15 @@ def _worker(rank, world, port, out):
     reducer.finish()
     got2 = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     out[rank + world] = float((got2 - want).abs().max())
+    # third step: hooks quiet (the mode used when backward runs inside a CUDA graph), gradients averaged afterwards by reduce_now()
+    net.zero_grad()
+    reducer.enabled = False
+    torch.nn.functional.mse_loss(net(xs), ys).backward()
+    local = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    reducer.reduce_now()
+    got3 = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    out[rank + 2 * world] = float((got3 - want).abs().max())
+    out[rank + 3 * world] = 0.0 if float((local - want).abs().max()) > 1e-4 else 1.0      # the local gradient alone must differ from the mean
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,5 +62,5 @@ def test_grad_allreduce_world2_gloo():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-    assert len(out) == 2 * world
+    assert len(out) == 4 * world
     assert all(v < 1e-6 for v in out.values()), dict(out)

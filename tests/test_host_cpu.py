@@ -112,3 +112,55 @@ def test_shard_bounds_cover_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bn_act_host_semantics_off_gpu():
+    """fn.bn_act on tensors the fused kernels do not take (CPU / fp32 / NCHW) is exactly the framework's
+    relu(bn(x) + residual), including the running-statistics update and an overridden momentum (f_key's double step)."""
+    from acan_b200 import functions as fn
+    torch.manual_seed(3)
+    x, r = torch.randn(2, 8, 5, 7), torch.randn(2, 8, 5, 7)
+    a, b = torch.nn.BatchNorm2d(8).train(), torch.nn.BatchNorm2d(8).train()
+    b.load_state_dict(a.state_dict())
+    got = fn.bn_act(a, x, relu=True, residual=r)
+    want = torch.relu(b(x) + r)
+    assert torch.equal(got, want) and torch.equal(a.running_var, b.running_var) and int(a.num_batches_tracked) == 1
+    fn.bn_act(a, x, relu=False, momentum=0.19)
+    b.momentum = 0.19
+    b(x)
+    assert torch.allclose(a.running_mean, b.running_mean) and a.momentum == 0.1
+    a.eval(), b.eval()
+    assert torch.equal(fn.bn_act(a, x, relu=True), torch.relu(b(x)))
+
+
+def test_lazy_training_handle_shapes_and_materialisation():
+    """the training-mode 'y' handle built from stride-8 logits reports the reference's [B,K,H,W] shape and, for any consumer
+    other than the drop-in loss / inference, upsamples and decodes lazily (CPU: shape logic only, decode_ord needs the GPU)."""
+    from acan_b200.modules import LazyLogitsProb
+    z = torch.randn(2, 160, 4, 6, requires_grad=True)
+    up = torch.nn.Upsample(scale_factor=8, mode="bilinear", align_corners=True)
+    y = LazyLogitsProb(None, 80, z=z, upsample=up)
+    assert tuple(y.shape) == (2, 80, 32, 48) and y.size(1) == 80 and y.dim() == 4 and y.requires_grad and y.z is z
+    assert tuple(y.logits.shape) == (2, 160, 32, 48) and y.logits.requires_grad
+    full = LazyLogitsProb(torch.randn(2, 160, 32, 48), 80)
+    assert full.z is None and tuple(full.shape) == (2, 80, 32, 48)
+
+
+def test_graphed_train_step_refuses_cpu():
+    from acan_b200.training import GraphedTrainStep
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GraphedTrainStep(None, None, None, torch.zeros(1, 3, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    from acan_b200 import _lib
+    lib = _lib.load()
+    BAD = 10001
+    assert lib.acan_bn_train_fwd(16, 1, 16, 16, None, 16, 16, 16, None, None, 0.1, 1e-5, 1, 16, 128, 12, None) == BAD      # C % 8 != 0
+    assert lib.acan_bn_train_fwd(16, 3, 16, 16, None, 16, 16, 16, None, None, 0.1, 1e-5, 1, 16, 128, 16, None) == BAD      # unknown dtype
+    assert lib.acan_bn_train_fwd(16, 1, 16, 16, None, 16, 16, 16, 16, None, 0.1, 1e-5, 1, 16, 128, 16, None) == BAD        # running_var missing
+    assert lib.acan_bn_train_bwd(16, None, 16, 1, 16, 16, 16, 16, 16, 16, 16, 16, 128, 16, None) == BAD                    # grad_residual without y
+    assert lib.acan_tail_loss_fwd(8, 8, 8, 8, 8, 0, 4, 6, 80, 0, None) == BAD                                             # B = 0
+    assert lib.acan_tail_loss_bwd(8, 8, 8, 8, None, 1, 4, 6, 80, 0, None) == BAD                                          # null output
+    assert lib.acan_attn_bwd(1024, None, None, 1024, None, 1024, 64, 96, None, 1024, None, 1024, 1 << 30, 1, 96, 512, 2048, 0.044, None) == BAD   # label without grad_loss
+    assert lib.acan_bn_ws_floats(2048) > 128 * 2048 * 2 and lib.acan_tail_loss_ws_floats(8, 32, 44) >= 2 * 8 * 32 * 11
