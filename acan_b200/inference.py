@@ -184,3 +184,93 @@ class StreamedPredictor:
 
     def flush(self):
         return self._collect()
+
+
+class GraphedPredictor:
+    """The eval call pattern ``net.inference(net(images))`` (depthest_trainer.py:184-185) captured once into CUDA graphs and
+    replayed: ~250 launches per step (cuDNN convolutions + the kernels of this package) stop costing host time, and the host
+    copies ride on their own streams.  Two slots (static device input + static depth output + one graph each) let the upload
+    of batch i+1 and the download of depth i-1 overlap the replay of batch i.
+
+        pred = GraphedPredictor(fast_net, example_images_on_device)
+        depth = pred.predict(images_on_device)                       # device in, device out (valid until the next-but-one call)
+        prev = pred.submit(pinned_host_images) ... pred.flush()      # host in, host out, as StreamedPredictor
+    """
+
+    def __init__(self, net, example: torch.Tensor, warmup: int = 3):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedPredictor needs a CUDA example batch: acan_b200 has no CPU path")
+        self.net, self.device = net, example.device
+        self.h2d, self.d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.x = [example.clone(), example.clone()]
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):                  # cuDNN autotuning + workspace allocations happen outside the capture
+                net.inference(net(self.x[0]))
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        from . import _lib
+        self.graphs, self.depth = [], []
+        n0 = _lib.load().acan_launch_count()
+        for slot in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.graphs[0].pool() if self.graphs else None), torch.no_grad():
+                d = net.inference(net(self.x[slot]))
+            self.graphs.append(g)
+            self.depth.append(d)
+        self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0) // 2
+        self.host_out = [torch.empty(self.depth[0].shape, dtype=self.depth[0].dtype, pin_memory=True) for _ in range(2)]
+        self._done = [None, None]         # compute of the slot's last replay finished
+        self._down = [None, None]         # download of the slot's last depth finished
+        self._pending = None              # slot whose download has not been handed to the caller yet
+        self._i = 0
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        """device-resident images -> depth on the device (the static output of the slot: consume before the next-but-one call)."""
+        slot = self._i & 1
+        self._i += 1
+        cur = torch.cuda.current_stream(self.device)
+        if self._down[slot] is not None:
+            cur.wait_event(self._down[slot])
+        self.x[slot].copy_(images, non_blocking=True)
+        self.graphs[slot].replay()
+        return self.depth[slot]
+
+    def submit(self, host_images: torch.Tensor):
+        """pinned host images in; returns the host depth of the PREVIOUS submission (None the first time)."""
+        slot = self._i & 1
+        self._i += 1
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.h2d):
+            if self._done[slot] is not None:
+                self.h2d.wait_event(self._done[slot])         # the replay that last read this slot's input (two steps ago)
+            self.x[slot].copy_(host_images, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(self.h2d)
+        cur.wait_event(up)
+        if self._down[slot] is not None:
+            cur.wait_event(self._down[slot])                  # this slot's previous depth has left the device
+        self.graphs[slot].replay()
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._done[slot] = done
+        prev = self._collect()
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(done)
+            self.host_out[slot].copy_(self.depth[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.d2h)
+        self._down[slot] = ev
+        self._pending = slot
+        return prev
+
+    def _collect(self):
+        if self._pending is None:
+            return None
+        slot, self._pending = self._pending, None
+        self._down[slot].synchronize()
+        return self.host_out[slot]
+
+    def flush(self):
+        return self._collect()

@@ -701,3 +701,36 @@ def test_optimize_for_inference_matches_unfused_network():
     close(fast.predict_depth(x), got, 1e-6)
     n = out["sim_map"].shape[1]
     close(out["sim_map"].rows([n // 2]), net(x)["sim_map"].materialize()[:, [n // 2]], 2e-2)
+
+
+def test_graphed_predictor_matches_eager_inference():
+    """acan_b200.inference.GraphedPredictor (the eval step replayed from CUDA graphs, double-buffered host copies) returns
+    exactly what the eager call pattern net.inference(net(x)) returns, for device and for host inputs, across slot reuse."""
+    from acan_b200.inference import GraphedPredictor, optimize_for_inference
+    from acan_b200.network import ResNet
+    hh, ww, b = 64, 96, 2
+    torch.manual_seed(synth.SEED)
+    net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=0, layers=[1, 1, 1, 1]).to(DEV)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()
+    net.train()
+    with torch.no_grad():
+        net(synth.rand("gp.cal", b, 3, hh, ww).to(DEV))
+    fast = optimize_for_inference(net.eval())
+    xs = [synth.rand(f"gp.x{i}", b, 3, hh, ww) for i in range(5)]
+    want = [fast.inference(fast(x.to(DEV))).cpu() for x in xs]
+    pred = GraphedPredictor(fast, xs[0].to(DEV))
+    for x, w_ in zip(xs, want):
+        close(pred.predict(x.to(DEV)).cpu(), w_, 2e-3)      # (library convolutions may pick split-K variants: not bit-stable run to run)
+    outs = []
+    for x in xs:
+        o = pred.submit(x.pin_memory())
+        if o is not None:
+            outs.append(o.clone())
+    outs.append(pred.flush().clone())
+    assert len(outs) == len(want)
+    for o, w_ in zip(outs, want):
+        close(o, w_, 2e-3)
