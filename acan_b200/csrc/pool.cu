@@ -9,6 +9,7 @@
 //           shuffle reduction, optional keep-mask * 2.  Kernel 2/3: one warp per output neuron, the
 //           weight row is read once (coalesced 16 B loads) and dotted with all B inputs.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace acan {
 namespace {
@@ -236,4 +237,70 @@ extern "C" int acan_pool_branch_fwd_nhwc(const void* x, int x_dtype, const float
   if (int e = launch_status("acan_pool_branch_fwd_nhwc/reduce")) return e;
   if (int e = launch_linear(mean_out, w1, b1, hidden_out, B, C, H1, st, "acan_pool_branch_fwd_nhwc/linear1")) return e;
   return launch_linear(hidden_out, w2, b2, g_out, B, H1, H2, st, "acan_pool_branch_fwd_nhwc/linear2");
+}
+
+
+// ---------------------------------------------------------------- merge epilogue (sadecoder.py:107-111, 120-121)
+// The pooled branch g is spatially constant, so its share of the merge convolution ReLU(conv1x1(cat(context, g))) is a per-image
+// bias  W[:, dv:] g + b  added to the GEMM over the context channels.  This kernel applies that [B, C] bias and the ReLU in place
+// on the channels-last half-precision GEMM output: one read + one write of y (the framework's broadcast add + ReLU took two
+// passes, the add through a non-vectorised kernel: 154 us -> one HBM pass at C2).
+namespace acan {
+namespace {
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) bias_relu_nhwc_kernel(uint4* __restrict__ y, const float* __restrict__ bias, int64_t n8_per_image, int C) {
+  const int c8 = C >> 3;
+  const float* bb = bias + static_cast<size_t>(blockIdx.y) * C;
+  uint4* yb = y + static_cast<size_t>(blockIdx.y) * n8_per_image;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n8_per_image; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int c = static_cast<int>(i % c8) * 8;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + c)), b1 = __ldg(reinterpret_cast<const float4*>(bb + c) + 1);
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint4 u = yb[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float lo, hi;
+      if (BF16) {
+        lo = __uint_as_float(w[e] << 16);
+        hi = __uint_as_float(w[e] & 0xffff0000u);
+      } else {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+        lo = t.x;
+        hi = t.y;
+      }
+      lo = fmaxf(lo + bv[2 * e], 0.f);
+      hi = fmaxf(hi + bv[2 * e + 1], 0.f);
+      if (BF16) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        o[e] = *reinterpret_cast<const uint32_t*>(&h);
+      } else {
+        const __half2 h = __floats2half2_rn(lo, hi);
+        o[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    yb[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" int acan_bias_relu_nhwc(void* y, int dtype, const float* bias, int B, int N, int C, void* stream) {
+  ACAN_CHECK_ARG(y && bias, "acan_bias_relu_nhwc: null pointer");
+  ACAN_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && C > 0 && (C % 8) == 0, "acan_bias_relu_nhwc: B=%d N=%d C=%d invalid (C %% 8 == 0)", B, N, C);
+  ACAN_CHECK_ARG(dtype == 1 || dtype == 2, "acan_bias_relu_nhwc: dtype %d (1 = fp16, 2 = bf16)", dtype);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(y) % 16 == 0 && reinterpret_cast<uintptr_t>(bias) % 16 == 0, "acan_bias_relu_nhwc: 16-byte alignment");
+  const int64_t n8 = static_cast<int64_t>(N) * (C / 8);
+  int64_t gx = (n8 + 255) / 256;
+  const int64_t cap = (static_cast<int64_t>(acan::kNumSMs) * 16 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const dim3 grid(static_cast<unsigned>(gx), B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == 2) acan::bias_relu_nhwc_kernel<true><<<grid, 256, 0, st>>>(static_cast<uint4*>(y), bias, n8, C);
+  else            acan::bias_relu_nhwc_kernel<false><<<grid, 256, 0, st>>>(static_cast<uint4*>(y), bias, n8, C);
+  return acan::launch_status("acan_bias_relu_nhwc");
 }

@@ -49,7 +49,7 @@ class FusedConv(nn.Module):
                 return torch.cudnn_convolution_add_relu(x, self.weight, residual, 1.0, self.bias, self.stride, self.padding, self.dilation, 1)
             except RuntimeError:
                 self._fused_ok = False          # configuration the fused-epilogue path does not support: plain calls from now on
-        y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation)
+        y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation)       # bias None: moved into the consumer (FusedBottleneck)
         if residual is not None:
             y = y + residual
         return torch.relu_(y) if self.relu else y
@@ -61,8 +61,17 @@ class FusedBottleneck(nn.Module):
         def fc(conv, bn, relu):
             w, b = fold_conv_bn(conv, bn)
             return FusedConv(w, b, conv.stride, conv.padding, conv.dilation, relu)
-        self.c1, self.c2, self.c3 = fc(blk.conv1, blk.bn1, True), fc(blk.conv2, blk.bn2, True), fc(blk.conv3, blk.bn3, True)
-        self.project = fc(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
+        self.c1, self.c2 = fc(blk.conv1, blk.bn1, True), fc(blk.conv2, blk.bn2, True)
+        w3, b3 = fold_conv_bn(blk.conv3, blk.bn3)
+        self.project = None
+        if blk.downsample is not None:
+            # out = relu(c3(.) + b3 + project(x) + bp): the projection's folded bias moves into c3's (added in fp32), the projection
+            # itself runs bias-free -- a convolution without a fused activation would otherwise pay a separate broadcast-add pass
+            wp, bp = fold_conv_bn(blk.downsample[0], blk.downsample[1])
+            b3 = b3 + bp
+            self.project = FusedConv(wp, bp, blk.downsample[0].stride, blk.downsample[0].padding, blk.downsample[0].dilation, False)
+            self.project.bias = None
+        self.c3 = FusedConv(w3, b3, blk.conv3.stride, blk.conv3.padding, blk.conv3.dilation, True)
 
     def forward(self, x):
         skip = x if self.project is None else self.project(x)

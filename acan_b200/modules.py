@@ -435,8 +435,10 @@ class SADecoder(nn.Module):
         _, _, g = ops.pool_branch_cl(x, ic.linear1.weight, ic.linear1.bias, ic.linear2.weight, ic.linear2.bias, None)
         w = mg.conv1.weight.view(mg.conv1.out_channels, -1)
         bias = F.linear(g, w[:, dv:].float(), mg.conv1.bias.float())
-        y = F.conv2d(out["ctx"], self._ctx_weight_half(w, dv)) + bias.to(out["ctx"].dtype).view(b, -1, 1, 1)
-        return torch.relu_(y), self.sim_map
+        y = F.conv2d(out["ctx"], self._ctx_weight_half(w, dv))
+        if y.shape[1] % 8 == 0 and y.permute(0, 2, 3, 1).is_contiguous():
+            return ops.bias_relu_cl_(y, bias), self.sim_map                  # per-image bias + ReLU in one in-place pass
+        return torch.relu_(y + bias.to(y.dtype).view(b, -1, 1, 1)), self.sim_map
 
     def _ctx_weight_half(self, w2d: torch.Tensor, dv: int) -> torch.Tensor:
         """fp16 channels_last copy of W[:, :dv], cached until the parameter changes."""

@@ -243,6 +243,18 @@ def pool_branch_cl(x: torch.Tensor, w1, b1, w2, b2, keep_mask: Optional[torch.Te
     return mean, hid, g
 
 
+def bias_relu_cl_(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """y <- relu(y + bias[:, :, None, None]) in place; y [B,C,h,w] fp16 / bf16 in channels_last memory, bias [B,C]."""
+    if not y.is_cuda or y.dtype not in (torch.float16, torch.bfloat16) or not y.permute(0, 2, 3, 1).is_contiguous():
+        raise _lib.AcanLibraryError("bias_relu_cl_ wants a CUDA fp16 / bf16 channels_last tensor")
+    b, c, h, w = y.shape
+    bb = _cuda_f32(bias, "bias").reshape(b, c)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().acan_bias_relu_nhwc(y.data_ptr(), 1 if y.dtype == torch.float16 else 2, bb.data_ptr(), b, h * w, c, _lib.current_stream()),
+                   "acan_bias_relu_nhwc")
+    return y
+
+
 # ------------------------------------------------------------------------------------ attention
 
 class AttnWorkspace:

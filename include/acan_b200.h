@@ -108,6 +108,10 @@ int acan_tail_loss_fwd(const float* z_nhwc, const int64_t* label, float* loss_ou
 int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, const float* count, const float* grad_out, float* grad_z_nhwc,
                        int B, int h, int w, int K, int ignore_index, void* stream);
 
+/* Epilogue of the merge convolution (sadecoder.py:107-111): y <- ReLU(y + bias[b, :]) in place, y [B,N,C] channels-last fp16
+ * (dtype 1) / bf16 (dtype 2), bias [B,C] fp32 = W[:, dv:] g + b, the spatially constant share of conv1x1(cat(context, g)). */
+int acan_bias_relu_nhwc(void* y, int dtype, const float* bias, int B, int N, int C, void* stream);
+
 /* Training-mode BatchNorm2d over channels-last half-precision activations fused with the ReLU (and residual add) behind it:
  * the Q/K projection's BN + ReLU (sadecoder.py:25-30) and, same arithmetic, every
  * conv -> BN -> ReLU of the backbone (model.py:128-160).  Semantics of nn.BatchNorm2d in train(): batch statistics (biased

@@ -723,8 +723,13 @@ def test_graphed_predictor_matches_eager_inference():
     xs = [synth.rand(f"gp.x{i}", b, 3, hh, ww) for i in range(5)]
     want = [fast.inference(fast(x.to(DEV))).cpu() for x in xs]
     pred = GraphedPredictor(fast, xs[0].to(DEV))
+    # eager vs captured: the library convolutions may be autotuned to different fp16 kernels in the two settings (cudnn.benchmark
+    # state is inherited from whatever ran before), so the comparison is to fp16-pipeline noise; replays themselves are exact
     for x, w_ in zip(xs, want):
-        close(pred.predict(x.to(DEV)).cpu(), w_, 2e-3)      # (library convolutions may pick split-K variants: not bit-stable run to run)
+        close(pred.predict(x.to(DEV)).cpu(), w_, 1e-2)
+    first = [pred.predict(x.to(DEV)).cpu() for x in xs[:2]]      # one input per slot
+    again = [pred.predict(x.to(DEV)).cpu() for x in xs[:2]]
+    assert all(torch.equal(a, b_) for a, b_ in zip(first, again))
     outs = []
     for x in xs:
         o = pred.submit(x.pin_memory())
@@ -733,4 +738,17 @@ def test_graphed_predictor_matches_eager_inference():
     outs.append(pred.flush().clone())
     assert len(outs) == len(want)
     for o, w_ in zip(outs, want):
-        close(o, w_, 2e-3)
+        close(o, w_, 1e-2)
+    assert torch.equal(outs[0], first[0]) and torch.equal(outs[1], first[1])      # host path == device path, bit for bit
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_merge_bias_relu_epilogue(dtype):
+    """acan_bias_relu_nhwc: y <- relu(y + bias[b, :]) in place on a channels_last half tensor == the framework's two passes."""
+    from acan_b200 import ops
+    for b, c, h, w in ((2, 2048, 4, 6), (3, 64, 5, 7), (16, 2048, 32, 44)):
+        y = synth.randn(f"br.y.{c}.{h}", b, c, h, w).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        bias = synth.randn(f"br.b.{c}.{h}", b, c).to(DEV)
+        want = torch.relu(y.float() + bias.view(b, c, 1, 1)).to(dtype)
+        got = ops.bias_relu_cl_(y.clone(memory_format=torch.preserve_format), bias)
+        assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
