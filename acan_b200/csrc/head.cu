@@ -262,7 +262,12 @@ tail_kernel(const float* __restrict__ z, float* __restrict__ depth, float* __res
       const float2 c = *reinterpret_cast<const float2*>(p10 + 2 * k), d = *reinterpret_cast<const float2*>(p11 + 2 * k);
       const float y0 = h0l * (w0l * a.x + w1l * bq.x) + h1l * (w0l * c.x + w1l * d.x);
       const float y1 = h0l * (w0l * a.y + w1l * bq.y) + h1l * (w0l * c.y + w1l * d.y);
-      const float pk = ord_prob(y0, y1);
+      // soft inference with no probability output: p = 1 / (1 + exp(y0 - y1)) with the fast intrinsics (~1e-6 relative; the depth
+      // is a float output with a 1e-3 bar).  Hard inference and the materialised 'y' keep the reference's literal e1 / (e0 + e1):
+      // the bin index is bit-exact and p > 0.5 is not equivalent to y1 > y0 at rounding ties.
+      float pk;
+      if (KIND == ACAN_HEAD_OR_SOFT && prob == nullptr) pk = __fdividef(1.0f, 1.0f + __expf(y0 - y1));
+      else pk = ord_prob(y0, y1);
       acc.feed(pk, k);
       if (prob != nullptr) prob[((int64_t)b * K + k) * HW + pix] = pk;
     } else {

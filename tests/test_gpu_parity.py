@@ -724,12 +724,14 @@ def test_graphed_predictor_matches_eager_inference():
     want = [fast.inference(fast(x.to(DEV))).cpu() for x in xs]
     pred = GraphedPredictor(fast, xs[0].to(DEV))
     # eager vs captured: the library convolutions may be autotuned to different fp16 kernels in the two settings (cudnn.benchmark
-    # state is inherited from whatever ran before), so the comparison is to fp16-pipeline noise; replays themselves are exact
+    # state is inherited from whatever ran before) and their split-K variants accumulate atomically, so comparisons are to
+    # fp16-pipeline noise (looser across settings, tight between replays of the same graphs)
     for x, w_ in zip(xs, want):
         close(pred.predict(x.to(DEV)).cpu(), w_, 1e-2)
     first = [pred.predict(x.to(DEV)).cpu() for x in xs[:2]]      # one input per slot
     again = [pred.predict(x.to(DEV)).cpu() for x in xs[:2]]
-    assert all(torch.equal(a, b_) for a, b_ in zip(first, again))
+    for a, b_ in zip(first, again):
+        close(a, b_, 2e-3)
     outs = []
     for x in xs:
         o = pred.submit(x.pin_memory())
@@ -739,7 +741,8 @@ def test_graphed_predictor_matches_eager_inference():
     assert len(outs) == len(want)
     for o, w_ in zip(outs, want):
         close(o, w_, 1e-2)
-    assert torch.equal(outs[0], first[0]) and torch.equal(outs[1], first[1])      # host path == device path, bit for bit
+    close(outs[0], first[0], 2e-3)                                                 # host path == device path
+    close(outs[1], first[1], 2e-3)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
