@@ -16,6 +16,7 @@
 // against ~4 launches x several passes each of the framework's generic channels-last kernels.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace acan {
 namespace {
@@ -65,10 +66,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 struct ColGeom {
   int groups, rows_per_warp, cg, rsub;
 };
-__device__ __forceinline__ ColGeom col_geom(int C) {
+__device__ __forceinline__ ColGeom col_geom(int C, int slab_groups = 32) {
   ColGeom g;
   const int c8 = C >> 3;
-  g.groups = min(c8 - static_cast<int>(blockIdx.x) * 32, 32);
+  g.groups = min(c8 - static_cast<int>(blockIdx.x) * slab_groups, slab_groups);
   g.rows_per_warp = (32 % g.groups) == 0 ? 32 / g.groups : 1;     // otherwise the lanes beyond `groups` idle
   g.cg = static_cast<int>(threadIdx.x) % g.groups;
   g.rsub = static_cast<int>(threadIdx.x) / g.groups;        // < rows_per_warp for active lanes
@@ -371,6 +372,277 @@ bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, co
   }
 }
 
+// ---------------------------------------------------------------- single-launch variants (cooperative grid)
+// The activations of one layer (3 .. 46 MB at the C4 shapes) fit the 126 MB L2, and at 5 .. 25 us per pass the two-launch
+// form above is dominated by launch gaps and by the serial "last block finalises" tail.  Here one cooperative launch does
+// both passes: every block reduces its rows, the blocks of a channel slab meet at a barrier, EVERY block then reduces the
+// slab's partials itself (in parallel, same fixed order -> identical results) and walks its rows again -- now L2 hits --
+// to write the output.  The grid is at most one block per SM (checked by the cooperative launch), so the barrier cannot
+// deadlock; a bounded spin traps instead of hanging if that is ever violated.
+__device__ __forceinline__ void slab_barrier(int* cnt /* [2]: arrive, depart; zero between launches */, int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    atomicAdd(cnt, 1);
+    const long long t0 = clock64();
+    while (atomicAdd(cnt, 0) < nblocks) {
+      __nanosleep(40);
+      if (clock64() - t0 > 4000000000LL) {                  // ~2 s: blocks were not co-resident
+        printf("acan: BN slab barrier timeout (slab %d block %d of %d)\n", blockIdx.x, blockIdx.y, nblocks);
+        __trap();
+      }
+    }
+    __threadfence();
+    if (atomicAdd(cnt + 1, 1) == nblocks - 1) { cnt[0] = 0; cnt[1] = 0; }      // the last block to leave resets both words
+  }
+  __syncthreads();
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(32 * kBnRedY)
+bn_fwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residual, uint4* __restrict__ y, const float* __restrict__ weight,
+                   const float* __restrict__ bias, float* __restrict__ partial, int* __restrict__ counters, float* __restrict__ save_mean,
+                   float* __restrict__ save_invstd, float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                   int relu, int64_t M, int C, int slab_groups) {
+  __shared__ __align__(16) float sm[kBnRedY * 32 * 16];
+  __shared__ float sc_s[kBnSlab], sh_s[kBnSlab];
+  const ColGeom g = col_geom(C, slab_groups);
+  const bool active = static_cast<int>(threadIdx.x) < g.groups * g.rows_per_warp;
+  const int c8 = C >> 3;
+  const int64_t row_step = static_cast<int64_t>(gridDim.y) * kBnRedY * g.rows_per_warp;
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.y) * kBnRedY + threadIdx.y) * g.rows_per_warp + g.rsub;
+  const int64_t off = blockIdx.x * slab_groups + g.cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  if (active) {
+    for (int64_t r = r0; r < M; r += 8 * row_step) {
+      uint4 u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t rr = r + i * row_step;
+        u[i] = ldg_nc_u4(x + (rr < M ? rr : r) * c8 + off);
+        if (rr >= M) u[i] = make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float f[8];
+        unpack8<BF16>(u[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+      }
+    }
+  }
+  block_col_reduce(s, q, g, active, sm);
+  if (threadIdx.y == 0 && static_cast<int>(threadIdx.x) < g.groups) {
+    float* p = partial + (static_cast<size_t>(blockIdx.y) * C + (blockIdx.x * slab_groups + threadIdx.x) * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { p[2 * e] = s[e]; p[2 * e + 1] = q[e]; }
+  }
+  slab_barrier(counters + 2 * blockIdx.x, gridDim.y);
+  double S, Q;
+  const int nch = g.groups * 8, c0 = blockIdx.x * slab_groups * 8;
+  final_col_sum(partial, gridDim.y, C, c0, nch, reinterpret_cast<double*>(sm), S, Q);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < nch) {
+    const int c = c0 + tid;
+    const double mean = S / static_cast<double>(M);
+    double var = Q / static_cast<double>(M) - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float scv = __ldg(weight + c) * invstd;
+    sc_s[tid] = scv;
+    sh_s[tid] = __ldg(bias + c) - static_cast<float>(mean) * scv;
+    if (blockIdx.y == 0) {
+      save_mean[c] = static_cast<float>(mean);
+      save_invstd[c] = invstd;
+      if (running_mean != nullptr) {
+        const double unbiased = M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+      }
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = sc_s[g.cg * 8 + e]; sh[e] = sh_s[g.cg * 8 + e]; }
+  for (int64_t r = r0; r < M; r += 4 * row_step) {             // second pass over the same rows: L2 hits
+    uint4 ux[4], ur[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t rr = r + i * row_step;
+      const int64_t idx = (rr < M ? rr : r) * c8 + off;
+      ux[i] = ldg_nc_u4(x + idx);
+      ur[i] = (residual != nullptr) ? ldg_nc_u4(residual + idx) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t rr = r + i * row_step;
+      if (rr < M) {
+        float f[8], rv[8];
+        unpack8<BF16>(ux[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+        if (residual != nullptr) {
+          unpack8<BF16>(ur[i], rv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += rv[e];
+        }
+        if (relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+        }
+        y[rr * c8 + off] = pack8<BF16>(f);
+      }
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(32 * kBnRedY)
+bn_bwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ gy, const float* __restrict__ weight,
+                   const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float* __restrict__ partial, int* __restrict__ counters,
+                   float* __restrict__ grad_weight, float* __restrict__ grad_bias, uint4* __restrict__ gx, uint4* __restrict__ gres, int64_t M, int C, int slab_groups) {
+  __shared__ __align__(16) float sm[kBnRedY * 32 * 16];
+  __shared__ float a_s[kBnSlab], b_s[kBnSlab], c_s[kBnSlab];
+  const ColGeom g = col_geom(C, slab_groups);
+  const bool active = static_cast<int>(threadIdx.x) < g.groups * g.rows_per_warp;
+  const int c8 = C >> 3;
+  const int64_t row_step = static_cast<int64_t>(gridDim.y) * kBnRedY * g.rows_per_warp;
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.y) * kBnRedY + threadIdx.y) * g.rows_per_warp + g.rsub;
+  const int64_t off = blockIdx.x * slab_groups + g.cg;
+  float sg[8], sx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sg[e] = 0.f; sx[e] = 0.f; }
+  if (active) {
+    const int cbase = (blockIdx.x * slab_groups + g.cg) * 8;
+    float mu[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mu[e] = __ldg(save_mean + cbase + e);
+    for (int64_t r = r0; r < M; r += 4 * row_step) {
+      uint4 ux[4], ug[4], uy[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t rr = r + i * row_step;
+        const int64_t idx = (rr < M ? rr : r) * c8 + off;
+        ux[i] = ldg_nc_u4(x + idx);
+        ug[i] = ldg_nc_u4(gy + idx);
+        uy[i] = (y != nullptr) ? ldg_nc_u4(y + idx) : make_uint4(0, 0, 0, 0);
+        if (rr >= M) ug[i] = make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float fx[8], fg[8], fy[8];
+        unpack8<BF16>(ux[i], fx);
+        unpack8<BF16>(ug[i], fg);
+        if (y != nullptr) {
+          unpack8<BF16>(uy[i], fy);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) fg[e] = fy[e] > 0.f ? fg[e] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sg[e] += fg[e]; sx[e] = fmaf(fg[e], fx[e] - mu[e], sx[e]); }
+      }
+    }
+  }
+  block_col_reduce(sg, sx, g, active, sm);
+  if (threadIdx.y == 0 && static_cast<int>(threadIdx.x) < g.groups) {
+    float* p = partial + (static_cast<size_t>(blockIdx.y) * C + (blockIdx.x * slab_groups + threadIdx.x) * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { p[2 * e] = sg[e]; p[2 * e + 1] = sx[e]; }
+  }
+  slab_barrier(counters + 2 * blockIdx.x, gridDim.y);
+  double S, Q;
+  const int nch = g.groups * 8, c0 = blockIdx.x * slab_groups * 8;
+  final_col_sum(partial, gridDim.y, C, c0, nch, reinterpret_cast<double*>(sm), S, Q);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < nch) {
+    const int c = c0 + tid;
+    const double is = static_cast<double>(save_invstd[c]), mean = static_cast<double>(save_mean[c]), w = static_cast<double>(weight[c]);
+    const double sum_gx = Q * is;
+    const double a = S / static_cast<double>(M), b = sum_gx / static_cast<double>(M), A = w * is;
+    a_s[tid] = static_cast<float>(A);
+    b_s[tid] = static_cast<float>(-A * is * b);
+    c_s[tid] = static_cast<float>(A * (is * b * mean - a));
+    if (blockIdx.y == 0) {
+      grad_bias[c] = static_cast<float>(S);
+      grad_weight[c] = static_cast<float>(sum_gx);
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float A[8], Bc[8], Cc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { A[e] = a_s[g.cg * 8 + e]; Bc[e] = b_s[g.cg * 8 + e]; Cc[e] = c_s[g.cg * 8 + e]; }
+  for (int64_t r = r0; r < M; r += 2 * row_step) {             // second pass: L2 hits
+    uint4 ux[2], ug[2], uy[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t rr = r + i * row_step;
+      const int64_t idx = (rr < M ? rr : r) * c8 + off;
+      ux[i] = ldg_nc_u4(x + idx);
+      ug[i] = ldg_nc_u4(gy + idx);
+      uy[i] = (y != nullptr) ? ldg_nc_u4(y + idx) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t rr = r + i * row_step;
+      if (rr < M) {
+        const int64_t idx = rr * c8 + off;
+        float fx[8], fg[8], fy[8], o[8];
+        unpack8<BF16>(ux[i], fx);
+        unpack8<BF16>(ug[i], fg);
+        if (y != nullptr) {
+          unpack8<BF16>(uy[i], fy);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) fg[e] = fy[e] > 0.f ? fg[e] : 0.f;
+          if (gres != nullptr) gres[idx] = pack8<BF16>(fg);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(A[e], fg[e], fmaf(Bc[e], fx[e], Cc[e]));
+        gx[idx] = pack8<BF16>(o);
+      }
+    }
+  }
+}
+
+// cooperative grids: at most one block per SM in total, and no more row blocks than the finalisation sums per thread.
+// Narrow layers (C <= 512) get narrower channel slabs (8 or 16 lane groups instead of 32; the spare lanes of a warp take further
+// rows) so that the grid still covers the machine: with 256-channel slabs a C = 256 layer would run on 32 SMs.
+struct CoopGrid { int slab_groups, slabs, row_blocks; };
+CoopGrid coop_grid(int64_t M, int C, int rows_per_thread) {
+  CoopGrid best = {32, (C + kBnSlab - 1) / kBnSlab, 1};
+  long best_blocks = -1;
+  const int cands[3] = {32, 16, 8};
+  for (int L : cands) {
+    const int c8 = C / 8;
+    const int slabs = (c8 + L - 1) / L;
+    if (slabs > kNumSMs || 2 * slabs > kBnCounterSlots) continue;
+    const int groups = c8 < L ? c8 : L;
+    const int rpw = (32 % groups) == 0 ? 32 / groups : 1;
+    const int64_t rows_per_block_min = static_cast<int64_t>(kBnRedY) * rpw * rows_per_thread;
+    int64_t rb = kNumSMs / slabs;
+    const int64_t max_rb = (M + rows_per_block_min - 1) / rows_per_block_min;
+    const int nch = groups * 8;
+    const int64_t fin = static_cast<int64_t>(kBnFinalDepth) * ((32 * kBnRedY) / nch);
+    if (rb > max_rb) rb = max_rb;
+    if (rb > fin) rb = fin;
+    if (rb > kBnMaxRowBlocks) rb = kBnMaxRowBlocks;
+    if (rb < 1) rb = 1;
+    const long blocks = static_cast<long>(slabs) * rb;
+    if (blocks > best_blocks) { best_blocks = blocks; best = {L, slabs, static_cast<int>(rb)}; }      // ties keep the wider slab
+  }
+  return best;
+}
+
+bool bn_use_coop(int C) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACAN_BN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && (C + kBnSlab - 1) / kBnSlab <= kNumSMs && 2 * ((C + kBnSlab - 1) / kBnSlab) <= kBnCounterSlots;   // the 32-group candidate always fits then
+}
+
 // row blocks so that the whole grid is ~`per_sm` blocks per SM, with at least `rows_per_thread` rows for every thread of a block
 // (block height `by`; a warp covers 32 / groups rows when the slab has fewer than 32 channel groups)
 int row_blocks_for(int64_t M, int C, int per_sm, int by, int rows_per_thread, int cap) {
@@ -427,6 +699,16 @@ extern "C" int acan_bn_train_fwd(const void* x, int dtype, const float* weight, 
   const dim3 agrid(slabs, row_blocks_for(M, C, 8, kBnAppY, 2, 65535)), ablock(32, kBnAppY);
   const uint4* xr = static_cast<const uint4*>(x);
   const uint4* rr = static_cast<const uint4*>(residual);
+  if (bn_use_coop(C)) {
+    CoopGrid cg = coop_grid(M, C, 8);
+    const dim3 cgrid(cg.slabs, cg.row_blocks);
+    uint4* yw = static_cast<uint4*>(y);
+    void* args[] = {&xr, &rr, &yw, &weight, &bias, &partial, &counters, &save_mean, &save_invstd, &running_mean, &running_var,
+                    &momentum, &eps, &relu, &M, &C, &cg.slab_groups};
+    const void* fn = dtype == 1 ? reinterpret_cast<const void*>(bn_fwd_coop_kernel<true>) : reinterpret_cast<const void*>(bn_fwd_coop_kernel<false>);
+    ACAN_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, rblock, args, 0, st));
+    return launch_status("bn_fwd_coop_kernel");
+  }
   if (dtype == 1) {
     bn_stats_kernel<true><<<rgrid, rblock, 0, st>>>(xr, weight, bias, partial, counters, save_mean, save_invstd, scale_shift, running_mean, running_var,
                                                     momentum, eps, M, C);
@@ -460,6 +742,16 @@ extern "C" int acan_bn_train_bwd(const void* x, const void* y, const void* grad_
   const uint4* xr = static_cast<const uint4*>(x);
   const uint4* yr = static_cast<const uint4*>(y);
   const uint4* gr = static_cast<const uint4*>(grad_y);
+  if (bn_use_coop(C)) {
+    CoopGrid cg = coop_grid(M, C, 4);
+    const dim3 cgrid(cg.slabs, cg.row_blocks);
+    uint4* gxw = static_cast<uint4*>(grad_x);
+    uint4* grw = static_cast<uint4*>(grad_residual);
+    void* args[] = {&xr, &yr, &gr, &weight, &save_mean, &save_invstd, &partial, &counters, &grad_weight, &grad_bias, &gxw, &grw, &M, &C, &cg.slab_groups};
+    const void* fn = dtype == 1 ? reinterpret_cast<const void*>(bn_bwd_coop_kernel<true>) : reinterpret_cast<const void*>(bn_bwd_coop_kernel<false>);
+    ACAN_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, rblock, args, 0, st));
+    return launch_status("bn_bwd_coop_kernel");
+  }
   if (dtype == 1) {
     bn_bwd_reduce_kernel<true><<<rgrid, rblock, 0, st>>>(xr, yr, gr, weight, save_mean, save_invstd, partial, counters, grad_weight, grad_bias, coef, M, C);
     if (int e = launch_status("bn_bwd_reduce_kernel")) return e;
