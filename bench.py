@@ -419,10 +419,10 @@ def main():
     t_core_call = h0.elapsed_time(h1) * 1e-3 / 20
     del fcl, vcl, ws_core
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
-    # profiles/r01_attn_final_channels_last.ncu-rep (155.8 MB + 64.9 MB; algorithmic V 92 + P 63 MB read, O 92 MB fp16 written)
+    # profiles/r01b_attn_cl_4launch_pdl.ncu-rep (157.2 MB + 65.0 MB; algorithmic V 92 + P 63 MB read, O 92 MB fp16 written)
     roof = {"bound": "tensor", "kernel": "gemm_kernel<MODE_PVT, CG=2> (aggregation O = P V on tcgen05, CTA pairs, V read in place MN-major)",
             "achieved": pv_flops / t_pv / 1e12,
-            "peak": pk["tensor"], "unit": "TFLOP/s", "frac": pv_flops / t_pv / 1e12 / pk["tensor"], "traffic": 220.7e6,
+            "peak": pk["tensor"], "unit": "TFLOP/s", "frac": pv_flops / t_pv / 1e12 / pk["tensor"], "traffic": 222.2e6,
             "peak_source": pk["src"] + " (bf16 burst)", "launch_us": t_pv * 1e6, "launches_timed": cnt[3]}
     extra = {
         "attention_core": {"bound": "tensor", "what": "whole CAM core call (diagonal + fallback statistics + probability + aggregation passes), algorithmic "
