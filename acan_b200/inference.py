@@ -224,7 +224,9 @@ class GraphedPredictor:
         n0 = _lib.load().acan_launch_count()
         for slot in range(2):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.graphs[0].pool() if self.graphs else None), torch.no_grad():
+            # one memory pool PER graph: with a shared pool the second capture may place its output in memory the first graph uses
+            # for temporaries, and replaying slot 0 would then corrupt depth[1] while its download is still in flight
+            with torch.cuda.graph(g), torch.no_grad():
                 d = net.inference(net(self.x[slot]))
             self.graphs.append(g)
             self.depth.append(d)

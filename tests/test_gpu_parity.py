@@ -340,6 +340,7 @@ def test_graphed_train_step_matches_eager():
         sd0 = {k: v.clone() for k, v in net.state_dict().items()}
         step = GraphedTrainStep(net, crit, opt, xs[0], ys[0], amp_dtype=torch.bfloat16, graph=graph, warmup=2)
         net.load_state_dict(sd0)                              # the capture warm-up stepped the weights: start both arms from the same point
+        step.sync_weights()                                   # (weights changed from outside the step: refresh its 16-bit shadow copies)
         opt.state.clear() if not graph else [buf.zero_() for st_ in opt.state.values() for buf in st_.values() if torch.is_tensor(buf)]
         out[graph] = [float(step(x, y)) for x, y in zip(xs, ys)]
     for a, e in zip(out[True], out[False]):
