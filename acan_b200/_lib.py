@@ -40,6 +40,8 @@ SIGNATURES = {
     "acan_bn_ws_floats": (c_size_t, [c_int]),
     "acan_bn_train_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_float, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "acan_bn_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_int64, c_int, c_void_p]),
+    "acan_depth_metrics_ws_floats": (c_int, []),
+    "acan_depth_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "acan_continuous2discrete": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int, c_void_p]),
     "acan_pool_branch_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "acan_pool_nhwc_scratch_floats": (c_size_t, [c_int, c_int, c_int]),

@@ -131,6 +131,13 @@ int acan_bn_train_bwd(const void* x, const void* y, const void* grad_y, int dtyp
                       const float* save_mean, const float* save_invstd, void* grad_x, void* grad_residual,
                       float* grad_weight, float* grad_bias, float* ws, int64_t M, int C, void* stream);
 
+/* The eight depth-error measures of the evaluation loop (utils/eval_utils.py:16-48 compute_errors) in one
+ * pass: gt, pred [n] fp32 (n = batch_size * H * W), pixels with gt <= 0 ignored; out8 (device) receives, in the reference's
+ * measure_list order, a1, a2, a3, rmse, rmse_log, log10 (a natural log in the reference, kept), abs_rel, sq_rel -- each the mean over
+ * the valid pixels of the whole batch times batch_size, as the reference returns them.  ws: acan_depth_metrics_ws_floats() floats. */
+int acan_depth_metrics_ws_floats(void);
+int acan_depth_metrics(const float* gt, const float* pred, float* out8, float* ws, int64_t n, int batch_size, void* stream);
+
 /* continuous2discrete (model.py:19-23, torch-0.4 semantics): metres -> bin index as float, 0 outside (d_min,d_max). */
 int acan_continuous2discrete(const float* depth, float* bins, int64_t n, double d_min, double d_max, int K, void* stream);
 

@@ -337,3 +337,74 @@ def ordinal_regression_loss(prob: Tensor, label: Tensor, ignore_index: int = 0) 
     lt = (k < lab).to(prob.dtype)
     ent = -(torch.log(prob.clamp(1e-8, 1e8)) * lt + torch.log((1 - prob).clamp(1e-8, 1e8)) * (1 - lt))
     return ent.sum(dim=1)[label.view(b, h, w) != ignore_index].mean()
+
+
+# ---------------------------------------------------------------- evaluation helpers
+
+def compute_errors(gt: Tensor, pred: Tensor) -> Dict[str, Tensor]:
+    """utils/eval_utils.py:16-48.  Means over the pixels with gt > 0 of the whole batch, each multiplied by the batch size; the
+    reference's 'log10' measure uses the same NATURAL log as 'rmse_log' (eval_utils.py:30-31)."""
+    n_batch = pred.shape[0]
+    keep = gt > 0
+    g, p = gt[keep], pred[keep]
+    slog = lambda t: torch.log(t.clamp(1e-6, 1e6))        # noqa: E731
+    ratio = torch.maximum(g / p, p / g)
+    dlog = slog(g) - slog(p)
+    vals = [(ratio < 1.25 ** k).to(g.dtype).mean() for k in (1, 2, 3)]
+    vals += [((g - p) ** 2).mean().sqrt(), (dlog ** 2).mean().sqrt(), dlog.abs().mean(), ((g - p).abs() / g).mean(), ((g - p) ** 2 / g).mean()]
+    return {name: v * n_batch for name, v in zip(("a1", "a2", "a3", "rmse", "rmse_log", "log10", "abs_rel", "sq_rel"), vals)}
+
+
+def _rescale(image: Tensor, scale: float) -> Tensor:
+    return image if scale == 1 else torch.nn.functional.interpolate(image, scale_factor=scale, mode="bilinear", align_corners=True)
+
+
+def _net_depth(net, x: Tensor) -> Tensor:
+    out = net(x)
+    return net.inference(out[-1] if isinstance(out, list) else out)
+
+
+def predict_whole_img(net, image: Tensor, scale: float = 1, flip: bool = False) -> Tensor:
+    """utils/eval_utils.py:131-176: one forward on the (rescaled) image, depth * scale, nearest resize back; with flip the
+    mirrored image's prediction is mirrored back and averaged in."""
+    size = image.shape[2:]
+
+    def once(img):
+        return torch.nn.functional.interpolate(_net_depth(net, _rescale(img, scale)) * scale, size=tuple(size), mode="nearest")
+    d = once(image)
+    return 0.5 * (d + once(image.flip([3])).flip([3])) if flip else d
+
+
+def predict_sliding(net, image: Tensor, tile_size, classes: int, scale: float = 1, flip: bool = False) -> Tensor:
+    """utils/eval_utils.py:68-129, 160-165: non-overlapping tiles of ``tile_size`` over the rescaled image (the last row / column of
+    tiles is shifted back inside), per-tile depth * scale, count-normalised, nearest resize by 1/scale."""
+    th, tw = tile_size
+
+    def once(img):
+        big = _rescale(img, scale)
+        n, _, hh, ww = big.shape
+        acc = torch.zeros((n, 1, hh, ww), dtype=big.dtype, device=big.device)
+        cnt = torch.zeros_like(acc)
+        rows = int(math.ceil((hh - th) / th) + 1)
+        cols = int(math.ceil((ww - tw) / tw) + 1)
+        for r in range(rows):
+            for c in range(cols):
+                x2, y2 = min(c * tw + tw, ww), min(r * th + th, hh)
+                x1, y1 = max(x2 - tw, 0), max(y2 - th, 0)
+                tile = big[:, :, y1:y2, x1:x2]
+                padded = torch.nn.functional.pad(tile, (0, tw - tile.shape[3], 0, th - tile.shape[2]))
+                d = torch.nn.functional.interpolate(_net_depth(net, padded) * scale, size=(th, tw), mode="nearest")
+                acc[:, :, y1:y2, x1:x2] += d[:, :, :tile.shape[2], :tile.shape[3]]
+                cnt[:, :, y1:y2, x1:x2] += 1
+        return torch.nn.functional.interpolate(acc / cnt, scale_factor=(1.0 / scale, 1.0 / scale), mode="nearest")
+    d = once(image)
+    return 0.5 * (d + once(image.flip([3])).flip([3])) if flip else d
+
+
+def predict_multi_scale(net, image: Tensor, scales, classes: int, flip: bool) -> Tensor:
+    """utils/eval_utils.py:178-209: mean over scales; scales <= 1 see the whole image, larger ones are tiled at the original size."""
+    total = torch.zeros((image.shape[0], 1) + tuple(image.shape[2:]), dtype=image.dtype, device=image.device)
+    for s_ in scales:
+        s_ = float(s_)
+        total += predict_whole_img(net, image, s_, flip) if s_ <= 1.0 else predict_sliding(net, image, tuple(image.shape[2:]), classes, s_, flip)
+    return total / len(scales)

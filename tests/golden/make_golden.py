@@ -200,7 +200,31 @@ def golden_resnet_tiny():
          loss1=l1, loss3=l3, total=tot)
 
 
+def golden_eval():
+    """utils/eval_utils.py (imported stand-alone: utils/__init__ pulls in matplotlib): compute_errors on a batch with invalid pixels,
+    zeros and outliers in the prediction; predict_multi_scale (whole image at scale 1, 2x2 tiles at 1.25, with flips) on the toy net."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_eval_utils", "/root/reference/code/utils/eval_utils.py")
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    gt = synth.depth_label("eval.gt", 3, 32, 48, 0.5, 10.5).squeeze(1)
+    pred = gt * (1.0 + 0.3 * synth.randn("eval.noise", 3, 32, 48)).abs() + 0.05 * synth.rand("eval.off", 3, 32, 48)
+    pred[0, 0, :4] = torch.tensor([0.0, 1e-8, 1e7, 5.0])                  # clamp windows of the safe log, division by zero in thresh
+    m = ev.compute_errors(gt.clone(), pred.clone())
+    net = synth.ToyDepthNet(4).eval()
+    img = synth.rand("eval.img", 2, 3, 16, 24)
+    with torch.no_grad():
+        tta = ev.predict_multi_scale(net, img, [1, 1.25], 4, True)
+        tta_noflip = ev.predict_multi_scale(net, img, [1.25], 4, False)
+        whole = ev.predict_whole_img(net, img, scale=0.75, flip=True)
+    save("eval_utils", measures=torch.stack([m[k] for k in ev.measure_list]), measure_list=np.array(ev.measure_list),
+         tta=tta, tta_noflip=tta_noflip, whole_075=whole)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":          # python tests/golden/make_golden.py eval  -> only the row f-4 fixtures
+        golden_eval()
+        sys.exit(0)
     torch.manual_seed(synth.SEED)
     torch.set_num_threads(os.cpu_count() or 1)
     golden_head()

@@ -77,3 +77,25 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+class ToyDepthNet(torch.nn.Module):
+    """Deterministic stand-in for the network in the test-time-augmentation tests: its output depends on the absolute position
+    inside the tile it is given and is not flip-symmetric, so a tiling, flipping or re-assembly mistake changes the result.
+    forward(x [N,3,h,w]) -> scores [N,classes,h,w];  inference(scores) -> depth [N,1,h,w]  (the two calls the reference's
+    predict_* helpers make, utils/eval_utils.py:112-118, 156-162)."""
+
+    def __init__(self, classes: int = 4):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, classes, 3, padding=1)
+        with torch.no_grad():
+            self.conv.weight.copy_(0.3 * randn("toy.w", classes, 3, 3, 3))
+            self.conv.bias.copy_(0.1 * randn("toy.b", classes))
+
+    def forward(self, x):
+        h, w = x.shape[2:]
+        ramp = 0.1 * torch.linspace(0, 1, w, device=x.device).view(1, 1, 1, w) + 0.05 * torch.linspace(0, 1, h, device=x.device).view(1, 1, h, 1) ** 2
+        return self.conv(x) + ramp
+
+    def inference(self, y):
+        return y.abs().sum(dim=1, keepdim=True) + 0.5

@@ -756,3 +756,53 @@ def test_merge_bias_relu_epilogue(dtype):
         want = torch.relu(y.float() + bias.view(b, c, 1, 1)).to(dtype)
         got = ops.bias_relu_cl_(y.clone(memory_format=torch.preserve_format), bias)
         assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
+
+
+def test_depth_metrics_kernel(golden):
+    """acan_depth_metrics (compute_errors, utils/eval_utils.py:16-48, in one pass) vs the reference's own numbers and vs the oracle on
+    a C2-sized batch with invalid pixels; an all-invalid batch gives NaN like the reference's means over an empty selection."""
+    from acan_b200 import evaluation as E
+    g = golden("eval_utils")
+    gt = synth.depth_label("eval.gt", 3, 32, 48, 0.5, 10.5).squeeze(1)
+    pred = gt * (1.0 + 0.3 * synth.randn("eval.noise", 3, 32, 48)).abs() + 0.05 * synth.rand("eval.off", 3, 32, 48)
+    pred[0, 0, :4] = torch.tensor([0.0, 1e-8, 1e7, 5.0])
+    m = E.compute_errors(gt.to(DEV), pred.to(DEV))
+    assert list(m.keys()) == [str(k) for k in g["measure_list"]] == E.measure_list
+    got = torch.stack([m[k] for k in m]).cpu()
+    assert torch.allclose(got, T(g["measures"]), rtol=2e-5, atol=0), (got, T(g["measures"]))
+    gt = synth.depth_label("eval.big", 16, 256, 352, 0.5, 10.5).squeeze(1)
+    pred = (gt * (1.0 + 0.2 * synth.randn("eval.bign", 16, 256, 352)).abs()).clamp_min(1e-3)
+    want = O.compute_errors(gt.double(), pred.double())
+    m = E.compute_errors(gt.to(DEV), pred.to(DEV)[:, None])              # [B,1,H,W] prediction against [B,H,W] ground truth, as the trainer passes them
+    for k in want:
+        assert abs(float(m[k]) - float(want[k])) <= 2e-5 * abs(float(want[k])), k
+    odd = E.compute_errors(gt.to(DEV)[:3, :7, :13].contiguous(), pred.to(DEV)[:3, :7, :13].contiguous())   # n % 4 != 0: scalar tail
+    want = O.compute_errors(gt[:3, :7, :13].double(), pred[:3, :7, :13].double())
+    assert all(abs(float(odd[k]) - float(want[k])) <= 2e-5 * abs(float(want[k])) for k in want)
+    none = E.compute_errors(torch.zeros(2, 8, 8, device=DEV), torch.ones(2, 8, 8, device=DEV))
+    assert all(bool(torch.isnan(v)) for v in none.values())
+
+
+def test_batched_tta_on_the_network():
+    """predict_multi_scale with the drop-in network in eval mode: every forward of the reference's loops (oracle restatement, run one
+    by one) in one batched call gives the same depth map."""
+    from acan_b200 import evaluation as E
+    from acan_b200.network import ResNet
+    hh, ww, b = 64, 96, 2
+    torch.manual_seed(synth.SEED)
+    net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=0, layers=[1, 1, 1, 1]).to(DEV)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()
+    net.train()
+    with torch.no_grad():
+        net(synth.rand("tta.cal", b, 3, hh, ww).to(DEV))
+    net.eval()
+    img = synth.rand("tta.img", b, 3, hh, ww).to(DEV)
+    with torch.no_grad():
+        want = O.predict_multi_scale(net, img, [1, 1.25], NYU[2], True)
+    got = E.predict_multi_scale(net, img, [1, 1.25], NYU[2], True)
+    assert got.shape == (b, 1, hh, ww)
+    close(got, want, 1e-4)

@@ -164,3 +164,29 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert lib.acan_tail_loss_bwd(8, 8, 8, 8, None, 1, 4, 6, 80, 0, None) == BAD                                          # null output
     assert lib.acan_attn_bwd(1024, None, None, 1024, None, 1024, 64, 96, None, 1024, None, 1024, 1 << 30, 1, 96, 512, 2048, 0.044, None) == BAD   # label without grad_loss
     assert lib.acan_bn_ws_floats(2048) > 128 * 2048 * 2 and lib.acan_tail_loss_ws_floats(8, 32, 44) >= 2 * 8 * 32 * 11
+
+
+def test_batched_tta_drivers_match_reference_golden(golden):
+    """acan_b200.evaluation.predict_multi_scale / predict_whole_img (every equally-sized forward of the reference's loops in ONE
+    batched call) reproduce the reference's own outputs on the toy network -- host logic, no GPU involved."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    from acan_b200 import evaluation as E
+    g = golden("eval_utils")
+    net = synth.ToyDepthNet(4).eval()
+    img = synth.rand("eval.img", 2, 3, 16, 24)
+    calls = []
+    fwd = net.forward
+    net.forward = lambda x: (calls.append(tuple(x.shape)), fwd(x))[1]
+    assert torch.allclose(E.predict_multi_scale(net, img, [1, 1.25], 4, True), torch.as_tensor(g["tta"]), rtol=1e-6, atol=1e-6)
+    assert calls == [(20, 3, 16, 24)]                                   # 2 whole views + 2 x 4 tiles, 2 images each: one forward
+    assert torch.allclose(E.predict_multi_scale(net, img, [1.25], 4, False), torch.as_tensor(g["tta_noflip"]), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(E.predict_whole_img(net, img, 0.75, True), torch.as_tensor(g["whole_075"]), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(E.predict_multi_scale(net, img, [1, 1.25], 4, True, max_batch=6), torch.as_tensor(g["tta"]), rtol=1e-6, atol=1e-6)
+    with pytest.raises(RuntimeError, match="eval"):
+        E.predict_multi_scale(net.train(), img, [1], 4, False)
+    from acan_b200 import _lib
+    with pytest.raises(_lib.AcanLibraryError, match="no CPU path"):
+        E.compute_errors(torch.ones(1, 4, 4), torch.ones(1, 4, 4))
+    assert _lib.load().acan_depth_metrics(8, 8, 8, 8, 0, 1, None) == 10001

@@ -155,3 +155,23 @@ def test_full_network_matches_reference(golden):
     assert abs(float(l3) - float(g["loss3"])) <= 1e-4 * abs(float(g["loss3"]))
     l1 = O.ordinal_regression_loss(out["y"], dis.squeeze(1).long())
     assert abs(float(l1) - float(g["loss1"])) <= 1e-4 * abs(float(g["loss1"]))
+
+
+def test_evaluation_helpers_against_reference_golden(golden):
+    """row f-4: compute_errors and the test-time-augmentation drivers (utils/eval_utils.py) restated in the oracle vs the
+    reference's own outputs on the same inputs (tests/golden/make_golden.py: golden_eval)."""
+    g = golden("eval_utils")
+    gt = synth.depth_label("eval.gt", 3, 32, 48, 0.5, 10.5).squeeze(1)
+    pred = gt * (1.0 + 0.3 * synth.randn("eval.noise", 3, 32, 48)).abs() + 0.05 * synth.rand("eval.off", 3, 32, 48)
+    pred[0, 0, :4] = torch.tensor([0.0, 1e-8, 1e7, 5.0])
+    m = O.compute_errors(gt, pred)
+    assert [str(k) for k in g["measure_list"]] == list(m.keys())
+    want = torch.as_tensor(g["measures"])
+    got = torch.stack([m[k] for k in m])
+    assert torch.allclose(got, want, rtol=1e-5, atol=0), (got, want)
+    net = synth.ToyDepthNet(4).eval()
+    img = synth.rand("eval.img", 2, 3, 16, 24)
+    with torch.no_grad():
+        assert torch.allclose(O.predict_multi_scale(net, img, [1, 1.25], 4, True), torch.as_tensor(g["tta"]), rtol=1e-6, atol=1e-6)
+        assert torch.allclose(O.predict_multi_scale(net, img, [1.25], 4, False), torch.as_tensor(g["tta_noflip"]), rtol=1e-6, atol=1e-6)
+        assert torch.allclose(O.predict_whole_img(net, img, 0.75, True), torch.as_tensor(g["whole_075"]), rtol=1e-6, atol=1e-6)
