@@ -20,8 +20,10 @@ class GraphedTrainStep:
 
     ``criterion(preds, labels, epoch) -> (loss1, loss2, loss3, total)`` as ``ResNet.LossFunc``.  ``reducer`` (optional): a
     ``parallel.GradAllReducer``.  With a reducer of world size > 1 the step is two graphs -- forward + losses + backward, then
-    the optimizer -- with the bucketed NCCL all-reduce launched eagerly between the replays (``reducer.reduce_now()``; the
-    replays are asynchronous, so the host queues the collectives while the backward graph still runs).
+    the optimizer -- with ONE NCCL all-reduce launched eagerly between the replays: every ``.grad`` is a view into a single
+    fp32 buffer: the backward graph ends by gathering the gradients into it, it is averaged in place, the optimizer graph
+    starts by scattering it back (the replays are asynchronous, so the host queues the collective while the backward graph still
+    runs).
     ``amp_dtype=None`` runs the step in fp32.  ``graph=False`` keeps the same interface on the eager path (A/B measurements).
     ``shadow_weights`` (default: on with a 16-bit ``amp_dtype``): the convolution weights are fed to the forward pass from 16-bit
     shadow copies that are refreshed from the fp32 parameters by ONE multi-tensor copy after the optimizer step, and their 16-bit
@@ -56,6 +58,7 @@ class GraphedTrainStep:
         self.losses = None
         self.library_launches_per_step = None
         self._split = reducer is not None and getattr(reducer, "world", 1) > 1       # NCCL stays outside the graphs
+        self._flat_grad = None
         if not graph:
             return
         if self._split:
@@ -69,6 +72,8 @@ class GraphedTrainStep:
         torch.cuda.current_stream(images.device).wait_stream(side)
         torch.cuda.synchronize(images.device)
         optimizer.zero_grad(set_to_none=True)                # captured backward re-creates the .grad tensors in the graph's pool
+        if self._split:
+            self._bind_flat_gradients()
         self.graph = torch.cuda.CUDAGraph()
         from . import _lib
         n0 = _lib.load().acan_launch_count()
@@ -80,13 +85,44 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.opt_graph, pool=self.graph.pool()):
                 self._body(capture_part=2)
 
+    def _bind_flat_gradients(self) -> None:
+        """multi-GPU replay mode: ONE fp32 buffer holds every gradient for the collective.  The backward graph ends with a
+        multi-tensor copy of the ``.grad`` tensors into views of it (each view has its gradient's own memory layout, so the copy is
+        the fused fast path), the gradient average is a single in-place NCCL all-reduce, and the optimizer graph starts by copying
+        the views back."""
+        self._flat_params, seen = [], set()
+        for p in self.net.parameters():
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                self._flat_params.append(p)
+        self._flat_grad = torch.zeros(sum(p.numel() for p in self._flat_params), device=self.static_x.device, dtype=torch.float32)
+        self._flat_views, self._flat_grads = None, None
+
+    def _flat_pairs(self):
+        if self._flat_views is None:                          # built once, inside the capture, from the gradients the backward produced
+            views, grads, off = [], [], 0
+            for p in self._flat_params:
+                seg = self._flat_grad[off:off + p.numel()]
+                off += p.numel()
+                g = p.grad
+                if g is None:
+                    continue
+                if g.dim() == 4 and not g.is_contiguous() and g.is_contiguous(memory_format=torch.channels_last):
+                    v = seg.view(g.shape[0], g.shape[2], g.shape[3], g.shape[1]).permute(0, 3, 1, 2)
+                else:
+                    v = seg.view(g.shape)
+                views.append(v)
+                grads.append(g)
+            self._flat_views, self._flat_grads = views, grads
+        return self._flat_views, self._flat_grads
+
     def _body(self, capture_part: int = 0):
         """capture_part 0: the whole step; 1: forward + losses + backward only; 2: what follows the gradient all-reduce."""
         out = None
         if capture_part in (0, 1):
             with torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
                 if self._shadows:
-                    preds = torch.func.functional_call(self.net, dict(zip(self._shadow_names, self._shadows)), (self.static_x,), tie_weights=True, strict=False)
+                    preds = torch.func.functional_call(self.net, dict(zip(self._shadow_names, self._shadows)), (self.static_x,), tie_weights=False, strict=False)   # (f_query IS f_key: one module object, one name suffices; tie_weights=True also hands the ORIGINAL parameter a gradient)
                 else:
                     preds = self.net(self.static_x)
                 out = self.criterion(preds, self.static_y, self.epoch)
@@ -98,12 +134,18 @@ class GraphedTrainStep:
                 torch._foreach_copy_([p.grad for p in self._shadow_params], [s_.grad for s_ in self._shadows])
                 for s_ in self._shadows:
                     s_.grad = None
+            if capture_part == 1 and self._flat_grad is not None:
+                views, grads = self._flat_pairs()
+                torch._foreach_copy_(views, grads)
         if capture_part == 0 and self.reducer is not None:
             if self._split and not self.reducer.enabled:
                 self.reducer.reduce_now()                    # warm-up passes of the split mode: hooks are off
             else:
                 self.reducer.finish()
         if capture_part in (0, 2):
+            if capture_part == 2 and self._flat_grad is not None:
+                views, grads = self._flat_pairs()
+                torch._foreach_copy_(grads, views)
             if self.after_backward is not None:
                 self.after_backward()
             self.optimizer.step()
@@ -129,6 +171,7 @@ class GraphedTrainStep:
         else:
             self.graph.replay()
             if self.opt_graph is not None:
-                self.reducer.reduce_now()
+                import torch.distributed as dist
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG, group=self.reducer.group)     # one in-place collective, queued behind the replay
                 self.opt_graph.replay()
         return self.losses[3]

@@ -220,8 +220,15 @@ def run_train(args, rank, world, device, lib):
     barrier()
     e2e_elapsed = time.perf_counter() - t0
     t = torch.tensor([elapsed, e2e_elapsed], device=device, dtype=torch.float64)
+    in_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # averaged gradients keep the replicas' weights identical: compare a checksum of all parameters across ranks
+        chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool((hi - lo).abs() <= 1e-9 * hi.abs())
     elapsed, e2e_elapsed = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
@@ -253,8 +260,8 @@ def run_train(args, rank, world, device, lib):
         "metric": "ACAN NYU-shape training images/sec", "value": world * B * args.steps / elapsed, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": TRAIN_WORKLOAD, "parallelism": (f"dp{world} (batch-sharded replicas; bucketed NCCL gradient all-reduce " +
-                                   ("overlapped with backward from grad hooks)" if args.no_graph else "between the backward graph and the optimizer graph)")) if world > 1 else "dp1",
+        "config": {"workload": TRAIN_WORKLOAD, "parallelism": (f"dp{world} (batch-sharded replicas; NCCL gradient all-reduce " +
+                                   ("bucketed, overlapped with backward from grad hooks)" if args.no_graph else "one in-place all-reduce of a flat fp32 gradient buffer between the backward graph and the optimizer graph)")) if world > 1 else "dp1",
                    "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd fp16 operands / fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
                    "launch": "eager" if args.no_graph else "whole step (fwd + losses + bwd + all-reduce + SGD) replayed from one CUDA graph (acan_b200.training.GraphedTrainStep)",
                    "l2": f"{n_rot} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},
@@ -265,7 +272,7 @@ def run_train(args, rank, world, device, lib):
         "roofline": {"bound": "tensor", "kernel": "acan_attn_bwd (P recompute, dV, dP -> dS with fused attention-loss term, dF: five tcgen05 GEMMs + packs), fp32-NCHW ABI, stand-alone at the step's shape",
                      "achieved": bwd_flops / t_b / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": bwd_flops / t_b / 1e12 / pk["tensor"], "traffic": None,
                      "peak_source": pk["src"] + " (bf16 burst)", "launch_us": t_b * 1e6},
-        "attention_fwd_loss_us": t_f * 1e6, "loss": loss_host, "cpu_baseline": None,
+        "attention_fwd_loss_us": t_f * 1e6, "loss": loss_host, "replicas_in_sync": in_sync, "cpu_baseline": None,
     }
     print(json.dumps(out))
     if world > 1:

@@ -328,7 +328,7 @@ def test_graphed_train_step_matches_eager():
     hh, ww, b = 64, 96, 4
     xs = [synth.rand(f"gts.x{i}", b, 3, hh, ww).to(DEV).contiguous(memory_format=torch.channels_last) for i in range(3)]
     ys = [synth.depth_label(f"gts.y{i}", b, hh, ww, 0.5, 10.5).to(DEV) for i in range(3)]
-    out = {}
+    out, final = {}, {}
     for graph in (True, False):
         torch.manual_seed(synth.SEED)
         net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=1.0, layers=[1, 1, 1, 1]).to(DEV).to(memory_format=torch.channels_last).train()
@@ -343,8 +343,14 @@ def test_graphed_train_step_matches_eager():
         step.sync_weights()                                   # (weights changed from outside the step: refresh its 16-bit shadow copies)
         opt.state.clear() if not graph else [buf.zero_() for st_ in opt.state.values() for buf in st_.values() if torch.is_tensor(buf)]
         out[graph] = [float(step(x, y)) for x, y in zip(xs, ys)]
+        final[graph] = {k: v.detach().float().clone() for k, v in net.named_parameters()}
+        moved = {k for k, v in final[graph].items() if float((v - sd0[k].float()).abs().max()) > 0}
+        assert moved == set(final[graph]), set(final[graph]) - moved          # every parameter receives its update (none skipped by the capture)
     for a, e in zip(out[True], out[False]):
         assert abs(a - e) <= 2e-2 * abs(e), (out[True], out[False])
+    for k in final[True]:                                                     # same weights after three steps, to bf16-pipeline noise of the updates
+        upd = (final[False][k] - sd0[k].float()).abs().max()
+        assert float((final[True][k] - final[False][k]).abs().max()) <= 0.35 * float(upd) + 1e-7, k
 
 
 # ------------------------------------------------------------------------------------ pooling branch
