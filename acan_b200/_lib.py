@@ -47,6 +47,7 @@ SIGNATURES = {
     "acan_pool_nhwc_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
     "acan_pool_branch_fwd_nhwc": (c_int, [c_void_p, c_int] + [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "acan_bias_relu_nhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "acan_maxpool3x3s2_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "acan_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "acan_attn_fwd": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_loss": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),

@@ -304,3 +304,83 @@ extern "C" int acan_bias_relu_nhwc(void* y, int dtype, const float* bias, int B,
   else            acan::bias_relu_nhwc_kernel<false><<<grid, 256, 0, st>>>(static_cast<uint4*>(y), bias, n8, C);
   return acan::launch_status("acan_bias_relu_nhwc");
 }
+
+
+// ---------------------------------------------------------------- stem max pooling (model.py:170, 218: nn.MaxPool2d(3, 2, 1))
+// 3x3 / stride 2 / pad 1 max pooling of the stem's channels-last half-precision output, inference only (no indices): a thread owns
+// 8 channels of one output pixel and reads its <= 9 taps as 16 B vectors (neighbouring outputs share taps through L1 / L2).
+// HBM-bound: 46 MB read + 11.5 MB written at configs[1]; the framework's NHWC kernel takes 113 us there.
+namespace acan {
+namespace {
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int Ho, int Wo, int c8,
+                                                                 int64_t total) {
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const int cg = static_cast<int>(i % c8);
+    int64_t t = i / c8;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int64_t b = t / Ho;
+    const int h0 = 2 * ho - 1, w0 = 2 * wo - 1;
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int hh = h0 + dy;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ww = w0 + dx;
+        if (ww < 0 || ww >= W) continue;
+        const uint4 u = __ldg(x + ((b * H + hh) * W + ww) * c8 + cg);
+        const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float lo, hi;
+          if (BF16) {
+            lo = __uint_as_float(wv[e] << 16);
+            hi = __uint_as_float(wv[e] & 0xffff0000u);
+          } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[e]));
+            lo = f.x;
+            hi = f.y;
+          }
+          m[2 * e] = fmaxf(m[2 * e], lo);              // (NaN inputs are dropped by fmaxf; the framework propagates them)
+          m[2 * e + 1] = fmaxf(m[2 * e + 1], hi);
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (BF16) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(m[2 * e], m[2 * e + 1]);
+        o[e] = *reinterpret_cast<const uint32_t*>(&h);
+      } else {
+        const __half2 h = __floats2half2_rn(m[2 * e], m[2 * e + 1]);
+        o[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" int acan_maxpool3x3s2_nhwc(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream) {
+  ACAN_CHECK_ARG(x && y, "acan_maxpool3x3s2_nhwc: null pointer");
+  ACAN_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0, "acan_maxpool3x3s2_nhwc: B=%d H=%d W=%d C=%d invalid (C %% 8 == 0)", B, H, W, C);
+  ACAN_CHECK_ARG(dtype == 1 || dtype == 2, "acan_maxpool3x3s2_nhwc: dtype %d (1 = fp16, 2 = bf16)", dtype);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0, "acan_maxpool3x3s2_nhwc: 16-byte alignment");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, c8 = C / 8;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * c8;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > acan::kNumSMs * 32) blocks = acan::kNumSMs * 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == 2) acan::maxpool3x3s2_nhwc_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), H, W, Ho, Wo, c8, total);
+  else            acan::maxpool3x3s2_nhwc_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), H, W, Ho, Wo, c8, total);
+  return acan::launch_status("acan_maxpool3x3s2_nhwc");
+}

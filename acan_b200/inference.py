@@ -106,9 +106,28 @@ class InferenceNet(nn.Module):
 
     def _features(self, x):
         x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
-        x = self.blocks(self.maxpool(self.stem(x)))
+        x = self.stem(x)
+        mp = self.maxpool
+        if (mp.kernel_size, mp.stride, mp.padding, mp.dilation, mp.ceil_mode) == (3, 2, 1, 1, False) and x.shape[1] % 8 == 0:
+            from . import ops
+            x = ops.maxpool3x3s2_cl(x)                      # 3x3 / 2 max pooling of the channels_last stem output in one HBM pass
+        else:
+            x = mp(x)
+        x = self.blocks(x)
         x, sim_map = self.decoder(x)
-        return self.classifier_conv(x), sim_map
+        return self._classify(x), sim_map
+
+    def _classify(self, x):
+        """classifier.conv (1x1, 2048 -> 2K or K channels) as a plain GEMM over the channels_last rows: for 160 output channels cuDNN
+        falls back to an sm_80 implicit-GEMM kernel (248 us at configs[1], 5 % of the step); the cuBLASLt GEMM takes ~25 us.  The
+        result is viewed back as [B,C,h,w] in channels_last memory, which is the layout the fused tail kernel reads."""
+        conv = self.classifier_conv
+        b, c, h, w = x.shape
+        rows = x.permute(0, 2, 3, 1)
+        if not rows.is_contiguous() or conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.padding != (0, 0):
+            return conv(x)
+        z = F.linear(rows.reshape(b * h * w, c), conv.weight.view(conv.out_channels, c), conv.bias)
+        return z.view(b, h, w, conv.out_channels).permute(0, 3, 1, 2)
 
     @torch.no_grad()
     def forward(self, x):

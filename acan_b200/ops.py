@@ -243,6 +243,18 @@ def pool_branch_cl(x: torch.Tensor, w1, b1, w2, b2, keep_mask: Optional[torch.Te
     return mean, hid, g
 
 
+def maxpool3x3s2_cl(x: torch.Tensor) -> torch.Tensor:
+    """nn.MaxPool2d(3, 2, 1) on a CUDA fp16 / bf16 channels_last tensor [B,C,H,W] (inference: no indices, no autograd)."""
+    if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16) or not x.permute(0, 2, 3, 1).is_contiguous() or x.shape[1] % 8:
+        raise _lib.AcanLibraryError("maxpool3x3s2_cl wants a CUDA fp16 / bf16 channels_last tensor with C % 8 == 0")
+    b, c, h, w = x.shape
+    y = torch.empty((b, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().acan_maxpool3x3s2_nhwc(x.data_ptr(), y.data_ptr(), 1 if x.dtype == torch.float16 else 2, b, h, w, c, _lib.current_stream()),
+                   "acan_maxpool3x3s2_nhwc")
+    return y
+
+
 def bias_relu_cl_(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """y <- relu(y + bias[:, :, None, None]) in place; y [B,C,h,w] fp16 / bf16 in channels_last memory, bias [B,C]."""
     if not y.is_cuda or y.dtype not in (torch.float16, torch.bfloat16) or not y.permute(0, 2, 3, 1).is_contiguous():

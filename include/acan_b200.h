@@ -112,6 +112,10 @@ int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, const float* c
  * (dtype 1) / bf16 (dtype 2), bias [B,C] fp32 = W[:, dv:] g + b, the spatially constant share of conv1x1(cat(context, g)). */
 int acan_bias_relu_nhwc(void* y, int dtype, const float* bias, int B, int N, int C, void* stream);
 
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the stem (model.py:170, 218) on a channels-last fp16 (dtype 1) / bf16
+ * (dtype 2) tensor, inference only (no indices): x [B,H,W,C] -> y [B,(H-1)/2+1,(W-1)/2+1,C], C % 8 == 0. */
+int acan_maxpool3x3s2_nhwc(const void* x, void* y, int dtype, int B, int H, int W, int C, void* stream);
+
 /* Training-mode BatchNorm2d over channels-last half-precision activations fused with the ReLU (and residual add) behind it:
  * the Q/K projection's BN + ReLU (sadecoder.py:25-30) and, same arithmetic, every
  * conv -> BN -> ReLU of the backbone (model.py:128-160).  Semantics of nn.BatchNorm2d in train(): batch statistics (biased

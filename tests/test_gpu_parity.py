@@ -812,3 +812,14 @@ def test_batched_tta_on_the_network():
     got = E.predict_multi_scale(net, img, [1, 1.25], NYU[2], True)
     assert got.shape == (b, 1, hh, ww)
     close(got, want, 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_stem_maxpool_kernel(dtype):
+    """acan_maxpool3x3s2_nhwc == nn.MaxPool2d(3, 2, 1) on channels_last half tensors, odd and even sizes, bit for bit."""
+    from acan_b200 import ops
+    for b, c, h, w in ((2, 64, 16, 24), (1, 8, 7, 9), (3, 64, 33, 50), (16, 64, 128, 176)):
+        x = synth.randn(f"mp.{c}.{h}.{w}", b, c, h, w).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        want = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+        got = ops.maxpool3x3s2_cl(x)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
