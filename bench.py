@@ -256,6 +256,42 @@ def run_train(args, rank, world, device, lib):
     t_f = ev(lambda: ops.attention_forward(f, v, dis_label=lab, ws=o["ws"]))
     t_b = ev(lambda: ops.attention_backward(f, o["row_stats"], v, o["ctx"], go, lab, 1.0))
     bwd_flops = B * 10240.0 * n * n
+    del f, v, lab, go, o
+    # the dominant hand-written kernels of the step by time are the BN (+ReLU/+residual) passes (105 layers, ~3.3 ms of the step): the
+    # backward kernel at the most common large layer shape (layer3's 1024-channel maps), operands rotated through > 2x L2, replayed from
+    # a CUDA graph so that the number is device time, not host launch rate
+    bc, bh, bw = 1024, H // 8, W // 8
+    n_rot = 14
+    xs = [torch.randn(B, bc, bh, bw, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(n_rot)]
+    gs = [torch.randn(B, bc, bh, bw, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(n_rot)]
+    wgt, bia = torch.ones(bc, device=device), torch.zeros(bc, device=device)
+    outs = [ops.bn_train_forward(xx, wgt, bia, None, None, 0.1, 1e-5, True, None) for xx in xs]
+    ys_, mean_, invstd_ = [t_[0] for t_ in outs], outs[0][1], outs[0][2]
+
+    def graph_time(calls, reps=10):
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for c_ in calls[:2]:
+                c_()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            keep = [c_() for c_ in calls]
+        for _ in range(2):
+            g_.replay()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g_.replay()
+        b_.record()
+        torch.cuda.synchronize()
+        del keep
+        return a.elapsed_time(b_) * 1e-3 / (reps * len(calls))
+    t_bn_f = graph_time([lambda xx=xx: ops.bn_train_forward(xx, wgt, bia, None, None, 0.1, 1e-5, True, None) for xx in xs])
+    t_bn_b = graph_time([lambda k=k: ops.bn_train_backward(xs[k], ys_[k], gs[k], wgt, mean_, invstd_, False) for k in range(n_rot)])
+    bn_elems = float(B * bc * bh * bw)
     out = {
         "metric": "ACAN NYU-shape training images/sec", "value": world * B * args.steps / elapsed, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -269,9 +305,16 @@ def run_train(args, rank, world, device, lib):
         "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_elapsed / args.steps * 1e3},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "acan_attn_bwd (P recompute, dV, dP -> dS with fused attention-loss term, dF: five tcgen05 GEMMs + packs), fp32-NCHW ABI, stand-alone at the step's shape",
-                     "achieved": bwd_flops / t_b / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": bwd_flops / t_b / 1e12 / pk["tensor"], "traffic": None,
-                     "peak_source": pk["src"] + " (bf16 burst)", "launch_us": t_b * 1e6},
+        "roofline": {"bound": "hbm", "kernel": "bn_bwd_coop_kernel<bf16> (BN + ReLU backward: one cooperative launch, 14 B per element algorithmic: dy, y, x read for the "
+                               "statistics, read again -- from L2 -- for dx, dx written), layer3 shape [8,1024,32,44], stand-alone, graph-replayed over 14 rotating operand sets",
+                     "achieved": 14.0 * bn_elems / t_bn_b / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": 14.0 * bn_elems / t_bn_b / 1e9 / pk["hbm"],
+                     "traffic": 76.1e6, "peak_source": pk["src"] + " (copy)", "launch_us": t_bn_b * 1e6,
+                     "note": "traffic = dram read 71.5 MB + write 4.6 MB from profiles/r01b_train_kernels_bn_tailloss.ncu-rep (the 23 MB of dx are still in L2 when the kernel ends)"},
+        "bn_forward": {"bound": "hbm", "what": "bn_fwd_coop_kernel<bf16>, same shape, 6 B per element algorithmic", "achieved": 6.0 * bn_elems / t_bn_f / 1e9, "peak": pk["hbm"],
+                       "unit": "GB/s", "frac": 6.0 * bn_elems / t_bn_f / 1e9 / pk["hbm"], "launch_us": t_bn_f * 1e6},
+        "attention_bwd": {"bound": "tensor", "what": "acan_attn_bwd (P recompute, dV, dP -> dS with fused attention-loss term, dF: five tcgen05 GEMMs + packs), fp32-NCHW ABI, "
+                                                     "stand-alone at the step's shape, algorithmic 10240*N^2 FLOP/img",
+                          "achieved": bwd_flops / t_b / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": bwd_flops / t_b / 1e12 / pk["tensor"], "launch_us": t_b * 1e6},
         "attention_fwd_loss_us": t_f * 1e6, "loss": loss_host, "replicas_in_sync": in_sync, "cpu_baseline": None,
     }
     print(json.dumps(out))
