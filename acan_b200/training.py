@@ -20,10 +20,9 @@ class GraphedTrainStep:
 
     ``criterion(preds, labels, epoch) -> (loss1, loss2, loss3, total)`` as ``ResNet.LossFunc``.  ``reducer`` (optional): a
     ``parallel.GradAllReducer``.  With a reducer of world size > 1 the step is two graphs -- forward + losses + backward, then
-    the optimizer -- with ONE NCCL all-reduce launched eagerly between the replays: every ``.grad`` is a view into a single
-    fp32 buffer: the backward graph ends by gathering the gradients into it, it is averaged in place, the optimizer graph
-    starts by scattering it back (the replays are asynchronous, so the host queues the collective while the backward graph still
-    runs).
+    the optimizer -- with ONE NCCL all-reduce launched eagerly between the replays: the backward graph ends by gathering every
+    gradient into a single fp32 buffer, the buffer is averaged in place, and the optimizer graph starts by scattering it back
+    (the replays are asynchronous, so the host queues the collective while the backward graph still runs).
     ``amp_dtype=None`` runs the step in fp32.  ``graph=False`` keeps the same interface on the eager path (A/B measurements).
     ``shadow_weights`` (default: on with a 16-bit ``amp_dtype``): the convolution weights are fed to the forward pass from 16-bit
     shadow copies that are refreshed from the fp32 parameters by ONE multi-tensor copy after the optimizer step, and their 16-bit
@@ -122,7 +121,9 @@ class GraphedTrainStep:
         if capture_part in (0, 1):
             with torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
                 if self._shadows:
-                    preds = torch.func.functional_call(self.net, dict(zip(self._shadow_names, self._shadows)), (self.static_x,), tie_weights=False, strict=False)   # (f_query IS f_key: one module object, one name suffices; tie_weights=True also hands the ORIGINAL parameter a gradient)
+                    # tie_weights=False: f_query IS f_key (one module object, so one name reaches both), and with tie_weights=True the
+                    # ORIGINAL parameter is handed a gradient as well -- under capture that left its .grad out of the optimizer graph
+                    preds = torch.func.functional_call(self.net, dict(zip(self._shadow_names, self._shadows)), (self.static_x,), tie_weights=False, strict=False)
                 else:
                     preds = self.net(self.static_x)
                 out = self.criterion(preds, self.static_y, self.epoch)
