@@ -187,8 +187,15 @@ def run_train(args, rank, world, device, lib):
     dev_y = [t.to(device, non_blocking=True) for t in host_y]
 
     from acan_b200.training import GraphedTrainStep
-    step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
-                            graph=not args.no_graph)
+    graph_note = None
+    try:
+        step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
+                                graph=not args.no_graph)
+    except Exception as e:          # same kernels either way: a failed capture must not cost the measurement
+        torch.cuda.synchronize()
+        graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        reducer.enabled = True
+        step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None, graph=False)
 
     def barrier():
         if world > 1:
@@ -299,7 +306,7 @@ def run_train(args, rank, world, device, lib):
         "config": {"workload": TRAIN_WORKLOAD, "parallelism": (f"dp{world} (batch-sharded replicas; NCCL gradient all-reduce " +
                                    ("bucketed, overlapped with backward from grad hooks)" if args.no_graph else "one in-place all-reduce of a flat fp32 gradient buffer between the backward graph and the optimizer graph)")) if world > 1 else "dp1",
                    "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd fp16 operands / fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
-                   "launch": "eager" if args.no_graph else "whole step (fwd + losses + bwd + all-reduce + SGD) replayed from one CUDA graph (acan_b200.training.GraphedTrainStep)",
+                   "launch": graph_note or ("eager" if args.no_graph else "whole step (fwd + losses + bwd + SGD) replayed from a CUDA graph; N > 1: backward graph, one NCCL all-reduce, optimizer graph (acan_b200.training.GraphedTrainStep)"),
                    "l2": f"{n_rot} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
@@ -371,7 +378,14 @@ def main():
     # ---- device-resident throughput -------------------------------------------------------------------------
     # default: the step replayed from a CUDA graph (acan_b200.inference.GraphedPredictor); --no-graph launches it eagerly
     from acan_b200.inference import GraphedPredictor, StreamedPredictor
-    pred = None if args.no_graph else GraphedPredictor(net, dev_in[0])
+    pred, launch_note = None, "eager"
+    if not args.no_graph:
+        try:
+            pred = GraphedPredictor(net, dev_in[0])
+            launch_note = "step replayed from a CUDA graph (acan_b200.inference.GraphedPredictor); roofline brackets from an eager pass over the same steps"
+        except Exception as e:      # same kernels either way: a failed capture must not cost the measurement
+            torch.cuda.synchronize()
+            launch_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:120]})"
     run = (lambda x: step_device(net, x)) if pred is None else pred.predict
     for i in range(args.warmup):
         run(dev_in[i % n_rot])
@@ -494,7 +508,7 @@ def main():
         "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (batch-sharded replicas, no collective in inference)",
                    "precision": "fp16 channels_last cuDNN convs with folded BN and fused bias/ReLU/residual epilogues (acan_b200.inference.optimize_for_inference); attention core fp16 operands / fp32 accumulate, F and V consumed in place; fused upsample+decode+head tail in fp32",
                    "l2": f"{n_rot} rotating input batches (138 MB) + ~190 MB of fp16 weights per step exceed the 126 MB L2; no explicit flush",
-                   "launch": "eager" if args.no_graph else "step replayed from a CUDA graph (acan_b200.inference.GraphedPredictor); roofline brackets from an eager pass over the same steps"},
+                   "launch": launch_note},
         "clocks": clocks,
         "e2e": {"value": world * BATCH * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
                 "d2h_bytes_per_step": BATCH * H * W * 4, "ms_per_step": e2e_elapsed / args.steps * 1e3},
