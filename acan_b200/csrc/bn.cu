@@ -637,6 +637,16 @@ CoopGrid coop_grid(int64_t M, int C, int rows_per_thread) {
   return best;
 }
 
+// ACAN_BN_PLAIN_LAUNCH=1: launch the single-pass kernels as ordinary grids (experiment).  The grid is still at most one block per SM, so
+// every block becomes resident as soon as the kernels ahead of it in the stream drain (nothing that runs later can hold an SM against it)
+// and the barrier's bounded spin still traps instead of hanging; an ordinary launch may start its first blocks under the previous
+// kernel's tail, which a cooperative launch (whole grid resident at once) cannot.
+bool bn_plain_launch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACAN_BN_PLAIN_LAUNCH"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 bool bn_use_coop(int C) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("ACAN_BN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -706,7 +716,7 @@ extern "C" int acan_bn_train_fwd(const void* x, int dtype, const float* weight, 
     void* args[] = {&xr, &rr, &yw, &weight, &bias, &partial, &counters, &save_mean, &save_invstd, &running_mean, &running_var,
                     &momentum, &eps, &relu, &M, &C, &cg.slab_groups};
     const void* fn = dtype == 1 ? reinterpret_cast<const void*>(bn_fwd_coop_kernel<true>) : reinterpret_cast<const void*>(bn_fwd_coop_kernel<false>);
-    ACAN_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, rblock, args, 0, st));
+    ACAN_CUDA(bn_plain_launch() ? cudaLaunchKernel(fn, cgrid, rblock, args, 0, st) : cudaLaunchCooperativeKernel(fn, cgrid, rblock, args, 0, st));
     return launch_status("bn_fwd_coop_kernel");
   }
   if (dtype == 1) {
@@ -749,7 +759,7 @@ extern "C" int acan_bn_train_bwd(const void* x, const void* y, const void* grad_
     uint4* grw = static_cast<uint4*>(grad_residual);
     void* args[] = {&xr, &yr, &gr, &weight, &save_mean, &save_invstd, &partial, &counters, &grad_weight, &grad_bias, &gxw, &grw, &M, &C, &cg.slab_groups};
     const void* fn = dtype == 1 ? reinterpret_cast<const void*>(bn_bwd_coop_kernel<true>) : reinterpret_cast<const void*>(bn_bwd_coop_kernel<false>);
-    ACAN_CUDA(cudaLaunchCooperativeKernel(fn, cgrid, rblock, args, 0, st));
+    ACAN_CUDA(bn_plain_launch() ? cudaLaunchKernel(fn, cgrid, rblock, args, 0, st) : cudaLaunchCooperativeKernel(fn, cgrid, rblock, args, 0, st));
     return launch_status("bn_bwd_coop_kernel");
   }
   if (dtype == 1) {
