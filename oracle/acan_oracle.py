@@ -7,8 +7,8 @@ missing instead of falling back to anything in here.
 
 What it is: a functional restatement (plain ``torch`` CPU ops, fp32 or fp64, no
 ``nn.Module``) of the algorithm the reference implements in
-``code/models/sadecoder.py``, ``code/models/losses.py:12-62`` and
-``code/models/model.py:19-99,113-126,216-272``.  Every function cites the reference
+``code/models/sadecoder.py``, ``code/models/losses.py:12-62,103-158``,
+``code/models/model.py:19-99,113-126,216-272`` and (row f-4 of the scope table) ``code/utils/eval_utils.py:16-209``.  Every function cites the reference
 lines it follows.  The reference is Python over ATen, so the oracle is Python over
 ATen too; it was written from the maths, not transcribed.
 
