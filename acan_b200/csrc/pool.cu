@@ -148,31 +148,27 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256) slab_colsum_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int N, int C8, int slabs) {
+__global__ void __launch_bounds__(256, 4) slab_colsum_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int N, int C8, int slabs) {
   const int c8 = blockIdx.x * 256 + threadIdx.x;
   const int slab = blockIdx.y, b = blockIdx.z;
   if (c8 >= C8) return;
   const int r0 = slab * kSlabRows, r1 = min(N, r0 + kSlabRows);
   const uint4* src = x + (static_cast<int64_t>(b) * N + r0) * C8 + c8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {                       // 4 independent 16 B loads in flight
-    uint4 u[4];
+  for (int r = r0; r < r1; r += 8) {                  // 8 independent 16 B loads in flight (volatile asm: ptxas keeps them batched);
+    uint4 u[8];                                       // rows beyond the slab re-read row r and are zeroed
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(src + static_cast<int64_t>(r - r0 + k) * C8);
+    for (int k = 0; k < 8; ++k) {
+      u[k] = ldg_nc_u4(src + static_cast<int64_t>((r + k < r1 ? r + k : r) - r0) * C8);
+      if (r + k >= r1) u[k] = make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       float f[8];
       unpack8<BF16>(u[k], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += f[i];
     }
-  }
-  for (; r < r1; ++r) {
-    float f[8];
-    unpack8<BF16>(__ldg(src + static_cast<int64_t>(r - r0) * C8), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += f[i];
   }
   float4* dst = reinterpret_cast<float4*>(partial + ((static_cast<int64_t>(b) * slabs + slab) * C8 + c8) * 8);
   dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);

@@ -125,8 +125,12 @@ class PoolBranch(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, keep_mask):
-        mean, hid, g = ops.pool_branch(x, w1, b1, w2, b2, keep_mask)
+        if x.dtype in (torch.float16, torch.bfloat16) and x.dim() == 4 and x.shape[1] % 8 == 0 and x.permute(0, 2, 3, 1).is_contiguous():
+            mean, hid, g = ops.pool_branch_cl(x, w1, b1, w2, b2, keep_mask)      # channels_last half activations are read in place
+        else:
+            mean, hid, g = ops.pool_branch(x, w1, b1, w2, b2, keep_mask)
         ctx.save_for_backward(mean, hid, g, w1, w2, keep_mask if keep_mask is not None else torch.empty(0, device=x.device))
+        ctx.x_dtype = x.dtype
         ctx.x_shape = x.shape
         return g
 
@@ -146,7 +150,7 @@ class PoolBranch(torch.autograd.Function):
         dmean = dz1 @ w1                                     # [B,C]
         if keep.numel():
             dmean = dmean * keep * 2.0
-        gx = (dmean / n).view(b, c, *([1] * (len(ctx.x_shape) - 2))).expand(ctx.x_shape)
+        gx = (dmean / n).to(ctx.x_dtype).view(b, c, *([1] * (len(ctx.x_shape) - 2))).expand(ctx.x_shape)
         return gx, gw1, gb1, gw2, gb2, None
 
 

@@ -460,7 +460,8 @@ class SADecoder(nn.Module):
         # image-level pooling branch: mean -> dropout -> MLP, never broadcast (sadecoder.py:97-106)
         ic = self.image_context
         keep_pool = self._channel_keep(ic.dropout, b, x.shape[1], x.device)
-        g = fn.PoolBranch.apply(x.float(), ic.linear1.weight, ic.linear1.bias, ic.linear2.weight, ic.linear2.bias, keep_pool)
+        half_cl = x.dtype in (torch.float16, torch.bfloat16) and x.permute(0, 2, 3, 1).is_contiguous()
+        g = fn.PoolBranch.apply(x if half_cl else x.float(), ic.linear1.weight, ic.linear1.bias, ic.linear2.weight, ic.linear2.bias, keep_pool)
         # merge = ReLU(W [context ; g] + b): GEMM over the dv context channels, the spatially constant pooled
         # branch folds into a per-image bias W[:, dv:] g  (sadecoder.py:107-111,120-121); no cat, no broadcast
         mg = self.merge
