@@ -34,6 +34,8 @@ SIGNATURES = {
     "acan_ordinal_loss_ws_floats": (c_int, []),
     "acan_ordinal_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_void_p]),
     "acan_ordinal_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_void_p]),
+    "acan_ce_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_float, c_int, c_void_p]),
+    "acan_ce_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_float, c_int, c_void_p]),
     "acan_tail_loss_ws_floats": (c_size_t, [c_int, c_int, c_int]),
     "acan_tail_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "acan_tail_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),

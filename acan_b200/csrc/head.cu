@@ -662,6 +662,127 @@ extern "C" int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, con
   return launch_status("acan_tail_loss_bwd");
 }
 
+// ---------------------------------------------------------------- cross-entropy loss of the CE classifier
+// CrossEntropy2d with reduction='sum', no class weights (losses.py:103-141, 164-196): per valid pixel, with p = softmax_k(y) and the
+// smoothed target s_k = (1 - eps) [k == l] + eps prior_k [k != l]  (prior: uniform 1/(K-1), or gaussian N(k - l; sigma = K/10)),
+//     loss = - sum_k ( s_k log clamp(p_k, 1e-8, 1e8) + (1 - s_k) log clamp(1 - p_k, 1e-8, 1e8) )
+// -- a per-class binary cross-entropy on the softmax outputs, not the usual -log p_l -- averaged over the pixels whose label != ignore.
+// Forward reads the scores [B,K,HW] once for the online (max, sum-exp) and once more (L2) for the terms; backward re-reads them and
+// writes dL/dy_k = p_k (a_k - sum_c a_c p_c) / count,  a_k = dloss/dp_k inside the clamp windows.  The softmax output, the one-hot /
+// smoothed label tensors and their gradients ([B,H,W,K] each in the reference) never exist.
+namespace acan {
+namespace {
+
+struct CePrior { float eps; int kind; float inv_km1; float sigma; };     // kind 0: uniform, 1: gaussian
+
+__device__ __forceinline__ float ce_target(int k, int l, const CePrior& pr) {
+  if (k == l) return 1.0f - pr.eps;
+  if (pr.eps == 0.f) return 0.f;
+  if (pr.kind == 0) return pr.eps * pr.inv_km1;
+  const float d = (float)(k - l);
+  return pr.eps * expf(-d * d / (2.0f * pr.sigma * pr.sigma)) * rsqrtf(6.283185307179586f * pr.sigma * pr.sigma);
+}
+
+// one thread per pixel (consecutive threads = consecutive pixels: coalesced 4 B loads per class plane)
+__global__ void __launch_bounds__(kThreads) ce_loss_fwd_kernel(const float* __restrict__ y, const int64_t* __restrict__ label, float2* __restrict__ partial,
+                                                                int K, int64_t HW, int64_t total, int ignore_index, CePrior pr) {
+  __shared__ float red_s[kThreads / 32], red_c[kThreads / 32];
+  float sum = 0.f, cnt = 0.f;
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int l = (int)label[q];
+    if (l == ignore_index) continue;
+    const int64_t b = q / HW, x = q - b * HW;
+    const float* src = y + b * (int64_t)K * HW + x;
+    float m = -INFINITY, z = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float v = __ldg(src + (int64_t)k * HW);
+      if (v > m) { z = z * expf(m - v) + 1.0f; m = v; } else { z += expf(v - m); }
+    }
+    const float inv_z = 1.0f / z;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float p = expf(__ldg(src + (int64_t)k * HW) - m) * inv_z;
+      const float s_k = ce_target(k, l, pr);
+      acc -= s_k * logf(fminf(fmaxf(p, 1e-8f), 1e8f)) + (1.0f - s_k) * logf(fminf(fmaxf(1.0f - p, 1e-8f), 1e8f));
+    }
+    sum += acc;
+    cnt += 1.f;
+  }
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = sum; red_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s_ = 0.f, c_ = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) { s_ += red_s[i]; c_ += red_c[i]; }
+    partial[blockIdx.x] = make_float2(s_, c_);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) ce_loss_bwd_kernel(const float* __restrict__ y, const int64_t* __restrict__ label, const float* __restrict__ count,
+                                                                const float* __restrict__ grad_out, float* __restrict__ gy, int K, int64_t HW, int64_t total,
+                                                                int ignore_index, CePrior pr) {
+  const float g = __ldg(grad_out) / __ldg(count);
+  for (int64_t q = blockIdx.x * (int64_t)kThreads + threadIdx.x; q < total; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t b = q / HW, x = q - b * HW;
+    const float* src = y + b * (int64_t)K * HW + x;
+    float* dst = gy + b * (int64_t)K * HW + x;
+    const int l = (int)label[q];
+    if (l == ignore_index) {
+      for (int k = 0; k < K; ++k) dst[(int64_t)k * HW] = 0.f;
+      continue;
+    }
+    float m = -INFINITY, z = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float v = __ldg(src + (int64_t)k * HW);
+      if (v > m) { z = z * expf(m - v) + 1.0f; m = v; } else { z += expf(v - m); }
+    }
+    const float inv_z = 1.0f / z;
+    auto slope = [&](float p, int k) {                       // a_k = d loss / d p_k (zero outside the clamp windows)
+      const float s_k = ce_target(k, l, pr), qv = 1.0f - p;
+      return -((p > 1e-8f && p < 1e8f) ? s_k / p : 0.f) + ((qv > 1e-8f && qv < 1e8f) ? (1.0f - s_k) / qv : 0.f);
+    };
+    float dot = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float p = expf(__ldg(src + (int64_t)k * HW) - m) * inv_z;
+      dot = fmaf(slope(p, k), p, dot);
+    }
+    for (int k = 0; k < K; ++k) {
+      const float p = expf(__ldg(src + (int64_t)k * HW) - m) * inv_z;
+      dst[(int64_t)k * HW] = p * (slope(p, k) - dot) * g;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" int acan_ce_loss_fwd(const float* scores, const int64_t* label, float* loss_out, float* count_out, float* ws,
+                                int B, int K, int64_t HW, int ignore_index, float eps, int prior_kind, void* stream) {
+  ACAN_CHECK_ARG(scores && label && loss_out && count_out && ws, "acan_ce_loss_fwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 1 && HW > 0, "acan_ce_loss_fwd: B=%d K=%d HW=%lld invalid", B, K, (long long)HW);
+  ACAN_CHECK_ARG(eps >= 0.f && eps <= 1.f && (prior_kind == 0 || prior_kind == 1), "acan_ce_loss_fwd: eps=%g prior_kind=%d invalid", eps, prior_kind);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)B * HW;
+  const int grid = grid_for(total);
+  const CePrior pr{eps, prior_kind, 1.0f / (float)(K - 1), (float)K / 10.0f};
+  ce_loss_fwd_kernel<<<grid, kThreads, 0, st>>>(scores, label, reinterpret_cast<float2*>(ws), K, HW, total, ignore_index, pr);
+  if (int e = launch_status("acan_ce_loss_fwd")) return e;
+  ord_loss_final_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const float2*>(ws), grid, loss_out, count_out);
+  return launch_status("acan_ce_loss_fwd/final");
+}
+
+extern "C" int acan_ce_loss_bwd(const float* scores, const int64_t* label, const float* count, const float* grad_out, float* grad_scores,
+                                int B, int K, int64_t HW, int ignore_index, float eps, int prior_kind, void* stream) {
+  ACAN_CHECK_ARG(scores && label && count && grad_out && grad_scores, "acan_ce_loss_bwd: null pointer");
+  ACAN_CHECK_ARG(B > 0 && K > 1 && HW > 0, "acan_ce_loss_bwd: sizes invalid");
+  ACAN_CHECK_ARG(eps >= 0.f && eps <= 1.f && (prior_kind == 0 || prior_kind == 1), "acan_ce_loss_bwd: eps=%g prior_kind=%d invalid", eps, prior_kind);
+  const int64_t total = (int64_t)B * HW;
+  const CePrior pr{eps, prior_kind, 1.0f / (float)(K - 1), (float)K / 10.0f};
+  ce_loss_bwd_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(scores, label, count, grad_out, grad_scores, K, HW, total,
+                                                                                        ignore_index, pr);
+  return launch_status("acan_ce_loss_bwd");
+}
+
 extern "C" int acan_ordinal_loss_ws_floats(void) { return 2 * acan::kNumSMs * acan::kBlocksPerSM + 8; }
 
 extern "C" int acan_ordinal_loss_fwd(const float* logits, const int64_t* label, float* loss_out, float* count_out, float* ws,

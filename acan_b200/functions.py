@@ -50,6 +50,24 @@ class FusedOrdinalLoss(torch.autograd.Function):
         return ops.ordinal_loss_backward(y, lab, count, grad_out, ctx.ignore_index), None, None
 
 
+class FusedCrossEntropyLoss(torch.autograd.Function):
+    """CrossEntropy2d(reduction='sum') on the class scores of the CE classifier (losses.py:103-141, 164-196): softmax, the smoothed
+    target and the per-class binary cross-entropy in one kernel forward, one backward; no [B,H,W,K] temporaries."""
+
+    @staticmethod
+    def forward(ctx, scores, label, ignore_index, eps, prior):
+        loss, count, y, lab = ops.ce_loss_forward(scores, label, ignore_index, eps, prior)
+        ctx.save_for_backward(y, lab, count)
+        ctx.cfg = (ignore_index, eps, prior, scores.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        y, lab, count = ctx.saved_tensors
+        ignore_index, eps, prior, dtype = ctx.cfg
+        return ops.ce_loss_backward(y, lab, count, grad_out, ignore_index, eps, prior).to(dtype), None, None, None, None
+
+
 class FusedTailLoss(torch.autograd.Function):
     """OrdinalRegression2d o decode_ord o Upsample(x8, bilinear, align_corners) on the STRIDE-8 pair logits (model.py:123-125,
     40-45; losses.py:103-158): the full-resolution logits and their gradient never exist (SURVEY §8f rows f-1 x f-2)."""

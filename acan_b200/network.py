@@ -258,6 +258,25 @@ class OrdinalRegression2d(nn.Module):
         return ent.sum(dim=1)[label != self.ignore_index].mean()
 
 
+class CrossEntropy2d(nn.Module):
+    """losses.py:164-196 with reduction='sum', no class weights (the configuration models/get_lossfunc.py:24-26 builds): a per-class
+    binary cross-entropy on softmax(scores) against the one-hot target, optionally smoothed (``eps``) with a uniform or gaussian prior.
+    Runs the fused kernels (acan_ce_loss_fwd/bwd) on class scores [B,K,H,W]."""
+
+    def __init__(self, ignore_index=None, reduction="sum", use_weights=False, weight=None, eps=0.0, priorType="uniform"):
+        super().__init__()
+        if use_weights or reduction != "sum":
+            raise NotImplementedError("only the reference's default CrossEntropy2d configuration is mirrored")
+        if priorType not in ("uniform", "gaussian"):
+            raise ValueError(f"priorType {priorType!r}")
+        self.ignore_index, self.eps, self.priorType = ignore_index, float(eps), priorType
+
+    def forward(self, pred, label):
+        if self.ignore_index is None:
+            self.ignore_index = pred.shape[1] + 1                  # as the reference (losses.py:131-132)
+        return fn.FusedCrossEntropyLoss.apply(pred, label, self.ignore_index, self.eps, self.priorType)
+
+
 RESNET_LAYERS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3]}
 
 
@@ -271,12 +290,16 @@ def create_network(args):
 
 
 def create_lossfunc(args, net):
-    """models/get_lossfunc.py:8-41 for the OR classifier (CE / OHEM losses are not mirrored)."""
-    if args.classifier != "OR":
-        raise NotImplementedError("acan_b200.create_lossfunc mirrors the OR configuration; use the reference's losses for CE/OHEM")
+    """models/get_lossfunc.py:8-41 for the OR and CE classifiers (the OHEM variant, which sorts on the host, is not mirrored)."""
+    if args.classifier == "OR":
+        app, aux = OrdinalRegression2d(ignore_index=0), OrdinalRegression2d(ignore_index=0)
+    elif args.classifier == "CE":
+        kw = dict(ignore_index=0, eps=getattr(args, "eps", 0.0), priorType=getattr(args, "prior", "uniform"))
+        app, aux = CrossEntropy2d(**kw), CrossEntropy2d(**kw)
+    else:
+        raise NotImplementedError("acan_b200.create_lossfunc mirrors the OR and CE configurations; use the reference's loss for OHEM")
     return net.LossFunc(min_depth=args.min_depth, max_depth=args.max_depth, num_classes=args.classes,
-                        AppearanceLoss=OrdinalRegression2d(ignore_index=0), AuxiliaryLoss=OrdinalRegression2d(ignore_index=0),
-                        AttentionLoss=AttentionLoss2d(scale=1), alpha=args.alpha, beta=args.beta)
+                        AppearanceLoss=app, AuxiliaryLoss=aux, AttentionLoss=AttentionLoss2d(scale=1), alpha=args.alpha, beta=args.beta)
 
 
 def install(net, criterion=None):

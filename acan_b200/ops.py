@@ -107,6 +107,33 @@ def ordinal_loss_backward(logits: torch.Tensor, label: torch.Tensor, count: torc
     return out
 
 
+def ce_loss_forward(scores: torch.Tensor, label: torch.Tensor, ignore_index: int, eps: float = 0.0, prior: str = "uniform"):
+    """(loss 0-dim, count 0-dim, scores fp32, label int64): CrossEntropy2d(reduction='sum') on class scores [B,K,H,W] (losses.py:164-196)."""
+    y = _cuda_f32(scores, "scores")
+    b, k, h, w = y.shape
+    lab = label.to(device=y.device, dtype=torch.int64).contiguous()
+    if lab.numel() != b * h * w:
+        raise _lib.AcanLibraryError(f"label {tuple(lab.shape)} does not match scores {tuple(y.shape)}")
+    lib = _lib.load()
+    loss = torch.empty((), device=y.device, dtype=torch.float32)
+    count = torch.empty((), device=y.device, dtype=torch.float32)
+    ws = torch.empty(int(lib.acan_ordinal_loss_ws_floats()), device=y.device, dtype=torch.float32)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.acan_ce_loss_fwd(y.data_ptr(), lab.data_ptr(), loss.data_ptr(), count.data_ptr(), ws.data_ptr(), b, k, h * w, int(ignore_index),
+                                        float(eps), 1 if prior == "gaussian" else 0, _lib.current_stream()), "acan_ce_loss_fwd")
+    return loss, count, y, lab
+
+
+def ce_loss_backward(scores, label, count, grad_out, ignore_index: int, eps: float = 0.0, prior: str = "uniform"):
+    b, k, h, w = scores.shape
+    g = grad_out.detach().to(device=scores.device, dtype=torch.float32).reshape(1).contiguous()
+    out = torch.empty_like(scores)
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.load().acan_ce_loss_bwd(scores.data_ptr(), label.data_ptr(), count.data_ptr(), g.data_ptr(), out.data_ptr(), b, k, h * w,
+                                                int(ignore_index), float(eps), 1 if prior == "gaussian" else 0, _lib.current_stream()), "acan_ce_loss_bwd")
+    return out
+
+
 def tail_loss_forward(z: torch.Tensor, label: torch.Tensor, ignore_index: int = 0):
     """(loss, count, z_nhwc, label): OrdinalRegression2d(decode_ord(upsample_x8(z))) from the stride-8 pair logits z [B,2K,h,w]
     (any float dtype / layout); label [B,8h,8w] bin indices."""

@@ -95,6 +95,16 @@ int acan_ordinal_loss_fwd(const float* logits, const int64_t* label, float* loss
 int acan_ordinal_loss_bwd(const float* logits, const int64_t* label, const float* count, const float* grad_out, float* grad_logits,
                           int B, int K, int64_t HW, int ignore_index, void* stream);
 
+/* CrossEntropy2d in the reference's live configuration (losses.py:103-141, 164-196: reduction='sum', no class weights) for the CE
+ * classifier -- SURVEY.md §8f row f-2: a per-class binary cross-entropy on softmax(scores) against the one-hot (eps = 0) or smoothed
+ * (eps > 0; prior_kind 0 = uniform 1/(K-1), 1 = gaussian sigma = K/10) target, log arguments clamped to [1e-8, 1e8], mean over the
+ * pixels whose label != ignore_index.   scores [B,K,HW] fp32, label [B,HW] int64;  ws: acan_ordinal_loss_ws_floats() floats;
+ * backward: grad_scores [B,K,HW] = grad_out * dloss/dscores (0 at ignored pixels). */
+int acan_ce_loss_fwd(const float* scores, const int64_t* label, float* loss_out, float* count_out, float* ws,
+                     int B, int K, int64_t HW, int ignore_index, float eps, int prior_kind, void* stream);
+int acan_ce_loss_bwd(const float* scores, const int64_t* label, const float* count, const float* grad_out, float* grad_scores,
+                     int B, int K, int64_t HW, int ignore_index, float eps, int prior_kind, void* stream);
+
 /* Training-mode classifier tail fused with the ordinal loss (SURVEY.md §8f rows f-1 x f-2): replaces
  * nn.Upsample(x8, bilinear, align_corners=True) (model.py:123-125, 228-230) -> decode_ord (model.py:40-45) ->
  * OrdinalRegression2d (losses.py:103-158) and their three backward passes.  Works from the STRIDE-8 pair logits; the

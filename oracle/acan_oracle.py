@@ -339,6 +339,27 @@ def ordinal_regression_loss(prob: Tensor, label: Tensor, ignore_index: int = 0) 
     return ent.sum(dim=1)[label.view(b, h, w) != ignore_index].mean()
 
 
+def cross_entropy_loss(score: Tensor, label: Tensor, ignore_index: int, eps: float = 0.0, prior: str = "uniform") -> Tensor:
+    """CrossEntropy2d with reduction='sum', no class weights (losses.py:103-141, 164-196): per valid pixel
+    -sum_k [ s_k log clamp(p_k) + (1 - s_k) log clamp(1 - p_k) ],  p = softmax over classes, s = one-hot smoothed by eps with a uniform
+    1/(K-1) or gaussian (sigma = K/10) prior on the other classes; mean over pixels with label != ignore_index."""
+    b, c, h, w = score.shape
+    p = torch.softmax(score, dim=1)
+    k = torch.arange(c, dtype=score.dtype).view(1, c, 1, 1)
+    lab = label.view(b, 1, h, w).to(score.dtype)
+    hot = (k == lab).to(score.dtype)
+    if eps == 0:
+        pri = 0.0
+    elif prior == "gaussian":
+        sig = c / 10.0
+        pri = torch.exp(-(k - lab) ** 2 / (2 * sig * sig)) / math.sqrt(2 * math.pi * sig * sig)
+    else:
+        pri = 1.0 / (c - 1)
+    s_ = (1 - eps) * hot + eps * pri * (1 - hot)
+    ent = -(s_ * torch.log(p.clamp(1e-8, 1e8)) + (1 - s_) * torch.log((1 - p).clamp(1e-8, 1e8)))
+    return ent.sum(dim=1)[label.view(b, h, w) != ignore_index].mean()
+
+
 # ---------------------------------------------------------------- evaluation helpers (SURVEY §8f row f-4)
 
 def compute_errors(gt: Tensor, pred: Tensor) -> Dict[str, Tensor]:

@@ -200,6 +200,25 @@ def golden_resnet_tiny():
          loss1=l1, loss3=l3, total=tot)
 
 
+def golden_ce_loss():
+    """models/losses.py CrossEntropy2d (reduction='sum') on class scores: plain, uniform- and gaussian-smoothed, with ignored pixels and a
+    saturated pixel (clamp windows); loss and d loss / d scores."""
+    from models.losses import CrossEntropy2d
+    K = 80
+    y = 2.0 * synth.randn("ce.y", 2, K, 8, 12)
+    y[0, :, 0, 0] = -30.0
+    y[0, 7, 0, 0] = 30.0                                               # p_7 -> 1, the others -> ~1e-26: both clamps
+    lab = _c2d(synth.depth_label("ce.lab", 2, 8, 12, 0.5, 10.5), *NYU).squeeze(1).long()
+    lab[0, 0, 0], lab[0, 0, 1] = 7, 0
+    out = {}
+    for tag, eps, prior in (("plain", 0.0, "uniform"), ("uniform", 0.1, "uniform"), ("gaussian", 0.2, "gaussian")):
+        yy = y.clone().requires_grad_(True)
+        loss = CrossEntropy2d(ignore_index=0, eps=eps, priorType=prior)(yy, lab)
+        loss.backward()
+        out[f"loss_{tag}"], out[f"grad_{tag}"] = loss.detach(), yy.grad
+    save("ce_loss", **out)
+
+
 def golden_eval():
     """utils/eval_utils.py (imported stand-alone: utils/__init__ pulls in matplotlib): compute_errors on a batch with invalid pixels,
     zeros and outliers in the prediction; predict_multi_scale (whole image at scale 1, 2x2 tiles at 1.25, with flips) on the toy net."""
@@ -225,6 +244,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eval":          # python tests/golden/make_golden.py eval  -> only the row f-4 fixtures
         golden_eval()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ce":            # ... ce -> only the CrossEntropy2d fixtures (row f-2)
+        golden_ce_loss()
+        sys.exit(0)
     torch.manual_seed(synth.SEED)
     torch.set_num_threads(os.cpu_count() or 1)
     golden_head()
@@ -232,3 +254,5 @@ if __name__ == "__main__":
     golden_attention_loss()
     golden_sadecoder()
     golden_resnet_tiny()
+    golden_eval()
+    golden_ce_loss()

@@ -175,3 +175,21 @@ def test_evaluation_helpers_against_reference_golden(golden):
         assert torch.allclose(O.predict_multi_scale(net, img, [1, 1.25], 4, True), torch.as_tensor(g["tta"]), rtol=1e-6, atol=1e-6)
         assert torch.allclose(O.predict_multi_scale(net, img, [1.25], 4, False), torch.as_tensor(g["tta_noflip"]), rtol=1e-6, atol=1e-6)
         assert torch.allclose(O.predict_whole_img(net, img, 0.75, True), torch.as_tensor(g["whole_075"]), rtol=1e-6, atol=1e-6)
+
+
+def test_cross_entropy_loss_against_reference_golden(golden):
+    """row f-2 (CE classifier): the oracle's CrossEntropy2d restatement vs the reference's loss and gradient (plain, uniform- and
+    gaussian-smoothed targets; ignored pixels; a saturated pixel that hits both clamp windows)."""
+    g = golden("ce_loss")
+    K = 80
+    y = 2.0 * synth.randn("ce.y", 2, K, 8, 12)
+    y[0, :, 0, 0] = -30.0
+    y[0, 7, 0, 0] = 30.0
+    lab = O.continuous2discrete(synth.depth_label("ce.lab", 2, 8, 12, 0.5, 10.5), 0.72, 10.0, 80).squeeze(1).long()
+    lab[0, 0, 0], lab[0, 0, 1] = 7, 0
+    for tag, eps, prior in (("plain", 0.0, "uniform"), ("uniform", 0.1, "uniform"), ("gaussian", 0.2, "gaussian")):
+        yy = y.clone().requires_grad_(True)
+        loss = O.cross_entropy_loss(yy, lab, 0, eps, prior)
+        loss.backward()
+        assert torch.allclose(loss.detach(), torch.as_tensor(g[f"loss_{tag}"]), rtol=1e-5), tag
+        assert torch.allclose(yy.grad, torch.as_tensor(g[f"grad_{tag}"]), rtol=1e-4, atol=1e-7), tag
