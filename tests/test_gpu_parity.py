@@ -855,3 +855,33 @@ def test_fused_cross_entropy_loss(golden, tag, eps, prior):
     (1.7 * want).backward()
     assert abs(float(l2) - float(want)) <= 1e-5 * abs(float(want))
     close(yd2.grad, yc.grad, 1e-4)
+
+
+def test_ce_classifier_network_trains_and_infers():
+    """classifierType='CE' end to end on the drop-in network: training step through CrossEntropy2d (fused kernels) + the attention loss,
+    then eval through the fused CE tail; the lazy eval path equals the reference-style one (upsample, head)."""
+    from acan_b200.network import ResNet, CrossEntropy2d
+    from acan_b200.modules import AttentionLoss2d
+    hh, ww, b = 64, 96, 2
+    torch.manual_seed(synth.SEED)
+    net = ResNet(*NYU, "CE", "soft", "attention", hh, ww, alpha=0, beta=1.0, layers=[1, 1, 1, 1]).to(DEV).train()
+    crit = net.LossFunc(*NYU, AppearanceLoss=CrossEntropy2d(ignore_index=0, eps=0.1), AttentionLoss=AttentionLoss2d(scale=1), alpha=0.0, beta=1.0)
+    x = synth.rand("cenet.x", b, 3, hh, ww).to(DEV)
+    label = synth.depth_label("cenet.y", b, hh, ww, 0.5, 10.5).to(DEV)
+    out = net(x)
+    assert tuple(out["y"].shape) == (b, NYU[2], hh, ww)
+    l1, _, l3, tot = crit(out, label, 1)
+    tot.backward()
+    want = O.cross_entropy_loss(out["y"].detach().double().cpu(), O.continuous2discrete(label.cpu(), *NYU).squeeze(1).long(), 0, 0.1, "uniform")
+    assert abs(float(l1) - float(want)) <= 1e-4 * abs(float(want))
+    gcls = net.classifier.conv.weight.grad
+    assert gcls is not None and torch.isfinite(gcls).all() and float(gcls.abs().max()) > 0
+    net.eval()
+    with torch.no_grad():
+        for mode in ("soft", "hard"):
+            net.inferenceType = mode
+            net.lazy_head = True
+            lazy = net.inference(net(x))
+            net.lazy_head = False
+            full = net.inference(net(x))
+            close(lazy, full, 1e-5)
