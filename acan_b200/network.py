@@ -169,9 +169,27 @@ class ResNet(BaseClassificationModel_):
         x = self.layer3(self.layer2(self.layer1(x)))
         return x, self.layer4(x)
 
+    def _inter_logits(self, mid):
+        """the auxiliary branch up to (not including) its x8 upsampling: stride-8 logits (model.py:113-121)"""
+        t = mid
+        for name, m in self.interout.named_children():
+            if name != "upsample":
+                t = m(t)
+        return t
+
     def forward(self, x):
         mid, x = self.encode(x)
-        inter_y = self.interout(mid) if self.use_inter else None
+        lazy_train = self.classifierType == "OR" and self.lazy_head
+        inter_y = None
+        if self.use_inter:
+            if lazy_train and (self.training or torch.is_grad_enabled()) and hasattr(self.interout, "upsample"):
+                # same lazy handle as 'y': the drop-in auxiliary loss works from the stride-8 logits
+                # (the reference's auxiliary branch ends in its 3x3 convolution: channel1 // 2 = 512 channels, i.e. 256 ordinal pairs,
+                #  whatever num_classes is -- model.py:113-121)
+                z_inter = self._inter_logits(mid)
+                inter_y = LazyLogitsProb(None, z_inter.shape[1] // 2, z=z_inter, upsample=self.interout.upsample)
+            else:
+                inter_y = self.interout(mid)
         sim_map = None
         if self.decoderType == "attention":
             x, sim_map = self.decoder(x)
@@ -182,7 +200,7 @@ class ResNet(BaseClassificationModel_):
             if self.use_inter and self.classifierType == "OR":
                 inter_y = self.decode_ord(inter_y)
             return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
-        if self.classifierType == "OR" and self.lazy_head:
+        if lazy_train:
             # 'y' keeps the STRIDE-8 pair logits; the drop-in ordinal loss / inference fuse the x8 upsampling and decode_ord
             # (SURVEY §8f rows f-1, f-2); any other consumer gets decode_ord(upsample(z)) with the usual autograd
             y = LazyLogitsProb(None, self.num_classes, z=self.classifier.conv(x), upsample=self.classifier.upsample)
@@ -190,7 +208,7 @@ class ResNet(BaseClassificationModel_):
             y = self.classifier(x)
             if self.classifierType == "OR":
                 y = self.decode_ord(y)
-        if self.classifierType == "OR" and self.use_inter:
+        if self.classifierType == "OR" and self.use_inter and not isinstance(inter_y, LazyLogitsProb):
             inter_y = self.decode_ord(inter_y)
         return {"inter_y": inter_y, "sim_map": sim_map, "y": y}
 

@@ -885,3 +885,31 @@ def test_ce_classifier_network_trains_and_infers():
             net.lazy_head = False
             full = net.inference(net(x))
             close(lazy, full, 1e-5)
+
+
+def test_auxiliary_branch_uses_the_fused_tail_loss():
+    """alpha != 0: 'inter_y' is the same lazy stride-8 handle as 'y' in training; the auxiliary OrdinalRegression2d runs the fused tail
+    loss and equals the reference-style path (upsample, decode_ord, loss on the dense tensor), value and gradients."""
+    from acan_b200.network import ResNet, OrdinalRegression2d
+    from acan_b200.modules import LazyLogitsProb
+    hh, ww, b = 64, 96, 2
+    x = synth.rand("aux.x", b, 3, hh, ww).to(DEV)
+    label = synth.depth_label("aux.y", b, hh, ww, 0.5, 10.5).to(DEV)
+    res = {}
+    for lazy in (True, False):
+        torch.manual_seed(synth.SEED)
+        net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0.5, beta=0.0, layers=[1, 1, 1, 1]).to(DEV).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.eval()
+        net.lazy_head = lazy
+        crit = net.LossFunc(*NYU, AppearanceLoss=OrdinalRegression2d(ignore_index=0), AuxiliaryLoss=OrdinalRegression2d(ignore_index=0), alpha=0.5, beta=0.0)
+        out = net(x)
+        k_aux = net.interout.conv1.out_channels // 2              # 256 ordinal pairs: the reference's auxiliary branch has no classification conv
+        assert isinstance(out["inter_y"], LazyLogitsProb) == lazy and tuple(out["inter_y"].shape) == (b, k_aux, hh, ww)
+        l1, l2, _, tot = crit(out, label, 1)
+        tot.backward()
+        res[lazy] = (float(l1), float(l2), net.interout.conv1.weight.grad.clone(), net.classifier.conv.weight.grad.clone())
+    assert abs(res[True][0] - res[False][0]) <= 1e-4 * abs(res[False][0]) and abs(res[True][1] - res[False][1]) <= 1e-4 * abs(res[False][1])
+    close(res[True][2], res[False][2], 2e-3)
+    close(res[True][3], res[False][3], 2e-3)
