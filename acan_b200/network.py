@@ -347,4 +347,9 @@ def install(net, criterion=None):
     fwd = ResNet.forward
     net.forward = types.MethodType(fwd, net)          # forward with the lazy 'y' handles (same dict, same keys)
     net.encode = types.MethodType(ResNet.encode, net)
+    net._inter_logits = types.MethodType(ResNet._inter_logits, net)
+    aux = getattr(criterion, "AuxiliaryLoss", None) if criterion is not None else None
+    if (type(aux).__name__ == "OrdinalRegression2d" and not getattr(aux, "use_weights", False)
+            and getattr(aux, "reduction", "sum") == "sum" and getattr(aux, "ignore_index", 0) is not None):
+        criterion.AuxiliaryLoss = OrdinalRegression2d(ignore_index=aux.ignore_index)
     return net
