@@ -855,21 +855,26 @@ __global__ void __launch_bounds__(256) kl_ds_kernel(const __half* __restrict__ p
 
 // per row: ln(bin) and ln(Z_i), Z_i = sum_j min(a_i/a_j, a_j/a_i)   (target-affinity normaliser, losses.py:40-46)
 __global__ void __launch_bounds__(256) gt_norm_kernel(const float* __restrict__ bins, float* __restrict__ logbin, float* __restrict__ lnz, int N) {
-  // grid (ceil(N/256), B): the image's log-bins are staged in shared memory, one thread per row sums exp(-|la_i - la_j|)
+  // grid (ceil(N/8), B): the image's log-bins are staged in shared memory; one WARP per row sums exp(-|la_i - la_j|) over j in lane
+  // strides with a fixed shuffle tree (one thread per row left the pass latency-bound: 11 k threads, N sequential ex2 each)
   extern __shared__ float la[];
   const int b = blockIdx.y;
   const float* a = bins + static_cast<size_t>(b) * N;
   for (int j = threadIdx.x; j < N; j += 256) { const float v = a[j]; la[j] = v > 0.f ? logf(v) * kLog2e : -INFINITY; }   // log2 units
   __syncthreads();
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= N) return;
   const float li = la[i];
   float z = 0.f;
   if (li > -INFINITY) {
-    for (int j = 0; j < N; ++j) z += ex2_approx(-fabsf(li - la[j]));      // exp2(-inf) = 0 for bin 0
+    for (int j = lane; j < N; j += 32) z += ex2_approx(-fabsf(li - la[j]));      // exp2(-inf) = 0 for bin 0
   }
-  logbin[static_cast<size_t>(b) * N + i] = li > -INFINITY ? li * kLn2 : -INFINITY;
-  lnz[static_cast<size_t>(b) * N + i] = z > 0.f ? lg2_approx(z) * kLn2 : 0.f;
+  z = warp_sum(z);
+  if (lane == 0) {
+    logbin[static_cast<size_t>(b) * N + i] = li > -INFINITY ? li * kLn2 : -INFINITY;
+    lnz[static_cast<size_t>(b) * N + i] = z > 0.f ? lg2_approx(z) * kLn2 : 0.f;
+  }
 }
 
 // selected rows of sim_map on CUDA cores (3 rows per image for the TensorBoard figure, vis_utils.py:107-121)
@@ -1161,7 +1166,7 @@ int prepare_target(const Workspace& w, const float* dis_label, int B, int H, int
   const int N = (H / 8) * (Wd / 8);
   nearest_bins_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(dis_label, w.bins, B, H, Wd);
   if (int e = launch_status("nearest_bins_kernel")) return e;
-  gt_norm_kernel<<<dim3((N + 255) / 256, B), 256, static_cast<size_t>(N) * sizeof(float), st>>>(w.bins, w.logbin, w.lnz, N);
+  gt_norm_kernel<<<dim3((N + 7) / 8, B), 256, static_cast<size_t>(N) * sizeof(float), st>>>(w.bins, w.logbin, w.lnz, N);
   return launch_status("gt_norm_kernel");
 }
 
