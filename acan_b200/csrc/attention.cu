@@ -757,39 +757,49 @@ __global__ void __launch_bounds__(256) pack_cast_kernel(const float4* __restrict
 }
 
 // delta[b,i] = sum_c dO[b,c,i] * O[b,c,i]   (= sum_j P_ij dP_ij, the softmax-backward row term)
-__global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ go, const float* __restrict__ o, float* __restrict__ delta,
-                                                     int* __restrict__ amax_bits, int C, int N) {
-  __shared__ float red[8][33];
-  const int b = blockIdx.y, i = blockIdx.x * 32 + (threadIdx.x & 31), wv = threadIdx.x >> 5;
-  float s = 0.f, am = 0.f;
-  if (i < N) {
+// grid (ceil(N/64), B): a lane owns 2 adjacent positions (8 B loads), the 8 warps stride over the channels, 8 channel rows of both
+// tensors in flight per thread (16 loads; the register target in __launch_bounds__ lets ptxas keep them batched)
+__global__ void __launch_bounds__(256, 2) delta_kernel(const float* __restrict__ go, const float* __restrict__ o, float* __restrict__ delta,
+                                                        int* __restrict__ amax_bits, int C, int N) {
+  __shared__ float2 red[8][33];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int i = blockIdx.x * 64 + lane * 2;
+  float2 s = make_float2(0.f, 0.f);
+  float am = 0.f;
+  if (i < N) {                                           // N % 8 == 0: a pair of positions is inside or outside together
     const size_t base = static_cast<size_t>(b) * C * N + i;
     int c = wv;
-    for (; c + 24 < C; c += 32) {                        // 4 independent row pairs in flight per thread
-      float gv[4], ov[4];
+    for (; c + 56 < C; c += 64) {
+      float2 gv[8], ov[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        gv[u] = __ldg(go + base + static_cast<size_t>(c + 8 * u) * N);
-        ov[u] = __ldg(o + base + static_cast<size_t>(c + 8 * u) * N);
+      for (int u = 0; u < 8; ++u) {
+        gv[u] = __ldg(reinterpret_cast<const float2*>(go + base + static_cast<size_t>(c + 8 * u) * N));
+        ov[u] = __ldg(reinterpret_cast<const float2*>(o + base + static_cast<size_t>(c + 8 * u) * N));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { s = fmaf(gv[u], ov[u], s); am = fmaxf(am, fabsf(gv[u])); }
+      for (int u = 0; u < 8; ++u) {
+        s.x = fmaf(gv[u].x, ov[u].x, s.x);
+        s.y = fmaf(gv[u].y, ov[u].y, s.y);
+        am = fmaxf(am, fmaxf(fabsf(gv[u].x), fabsf(gv[u].y)));
+      }
     }
     for (; c < C; c += 8) {
-      const float gv = __ldg(go + base + static_cast<size_t>(c) * N);
-      s = fmaf(gv, __ldg(o + base + static_cast<size_t>(c) * N), s);
-      am = fmaxf(am, fabsf(gv));
+      const float2 gv = __ldg(reinterpret_cast<const float2*>(go + base + static_cast<size_t>(c) * N));
+      const float2 ov = __ldg(reinterpret_cast<const float2*>(o + base + static_cast<size_t>(c) * N));
+      s.x = fmaf(gv.x, ov.x, s.x);
+      s.y = fmaf(gv.y, ov.y, s.y);
+      am = fmaxf(am, fmaxf(fabsf(gv.x), fabsf(gv.y)));
     }
   }
   am = warp_max(am);
-  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_int(am));   // |dO| max over the tensor (one atomic per warp)
-  red[wv][threadIdx.x & 31] = s;
+  if (lane == 0 && am > 0.f) atomicMax(amax_bits, __float_as_int(am));   // |dO| max over the tensor (one atomic per warp)
+  red[wv][lane] = s;
   __syncthreads();
   if (wv == 0 && i < N) {
-    float t = 0.f;
+    float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-    delta[static_cast<size_t>(b) * N + i] = t;
+    for (int k = 0; k < 8; ++k) { t.x += red[k][lane].x; t.y += red[k][lane].y; }
+    *reinterpret_cast<float2*>(delta + static_cast<size_t>(b) * N + i) = t;
   }
 }
 
@@ -1431,7 +1441,7 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
   if (agg) {
     // delta_i and max |dO| in one pass over dO; the power-of-two scale s keeps fp16 dO and dS in range whatever the loss scale
     ACAN_CUDA(cudaMemsetAsync(w.amax_bits, 0, 4, st));
-    delta_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(grad_ctx, ctx, w.delta, w.amax_bits, dv, N);
+    delta_kernel<<<dim3((N + 63) / 64, B), 256, 0, st>>>(grad_ctx, ctx, w.delta, w.amax_bits, dv, N);
     if (int e = launch_status("delta_kernel")) return e;
     gscale_kernel<<<1, 1, 0, st>>>(w.amax_bits, nullptr, inv_bn, w.gscale);
     if (int e = launch_status("gscale_kernel")) return e;
