@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libacan_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class AcanLibraryError(RuntimeError):
@@ -56,6 +56,11 @@ SIGNATURES = {
     "acan_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "acan_attn_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_fwd_nhwc_f16": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t] + [c_int] * 4 + [c_float, c_void_p]),
+    "acan_attn_fwd_nhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t]
+                           + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    "acan_attn_bwd_nhwc_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "acan_attn_bwd_nhwc": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                   c_void_p, c_int, c_void_p, c_int] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attn_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attention_loss": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_int, c_void_p]),
     "acan_gt_sim_map": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -18,19 +18,21 @@
 // FLOPs = (2*dk + dv) / (dk + dv) = 1.2.  Exact row statistics up front are also what the KL clamp
 //  and the backward pass need.
 //
-// All three passes are one warp-specialised kernel template (gemm_kernel<MODE>):
-//   warp 0   : TMA producer   (cp.async.bulk.tensor.3d, SWIZZLE_128B, mbarrier complete_tx)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN<=256, K=16)
-//   warps 2-5: epilogue       (tcgen05.ld 32x32b.x32 -> registers -> global), TMEM double-buffered so the
-//              epilogue of tile t overlaps the MMAs of tile t+1
-// persistent over a static tile schedule, grid = min(#tiles, 148).  Operands are fp16 (11-bit significand:
-// the rounding of TF32, at the bf16 MMA rate) with fp32 accumulation; bf16 operands miss the 1e-3 parity
-// bar on sim_map.
+// All passes (forward and backward) are one warp-specialised kernel template (gemm_kernel<MODE, CG, AM, BMN>), 320 threads:
+//   warp 0   : TMA producer   (cp.async.bulk.tensor.3d, SWIZZLE_128B, mbarrier complete_tx; K-major or MN-major operand boxes)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M = 128 per CTA, N = BN <= 256, K = 16)
+//   warps 2-9: epilogue, two groups of four warps (tcgen05.ld 32x32b.x32 -> registers -> SWIZZLE_128B staging in shared
+//              memory -> TMA store), TMEM double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1
+// persistent over a static tile schedule; CG = 2 (default) runs CTA pairs (cluster of 2, cta_group::2: a 256 x BN tile per pair).
+// The probabilities are fp16 operands (11-bit significand: the rounding of TF32, at the bf16 MMA rate) with fp32 accumulation;
+// bf16 probabilities miss the 1e-3 parity bar on sim_map.  V and dO may be bf16 (the two operand formats of a
+// kind::f16 MMA are independent fields of the instruction descriptor).
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
 
 namespace acan {
 
@@ -52,11 +54,22 @@ constexpr int kSmemBudget = 225 * 1024; // operand ring + epilogue staging; barr
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kShiftHeadroom = 14.0f, kSafeDiagMax = 72.0f;   // statistics-free probability pass, see diag_kernel
+constexpr float kKeepScale = 1024.0f;   // training path: normalised probabilities are stored as fp16(P * 2^10) (tails stay normal numbers)
+
+// Experiment knobs (mainloop-only timing, per-tile traces, tile-width / launch-mode overrides from the environment) exist only
+// in builds made with -DACAN_EXPERIMENT: the shipped library never reads the environment and never skips an epilogue.
+#ifdef ACAN_EXPERIMENT
+constexpr bool kExperiment = true;
+#else
+constexpr bool kExperiment = false;
+#endif
 
 // MODE_PV : O^T[dv, Nq] = V[dv, Nk] P[Nq, Nk]^T, both K-major (NCHW world), fp32 out.
 // MODE_PVT: O[Nq, dv]  = P[Nq, Nk] V[Nk, dv], B = V read in place from channels-last memory as an MN-major operand, fp16 out.
 // MODE_DS : backward: acc = dP[Nq, Nk] = dO^T V; epilogue dS = P o (dP - delta_i) (+ attention-loss term), scaled fp16 out.
-enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2, MODE_PVT = 3, MODE_DS = 4 };
+// MODE_PVT32: as MODE_PVT (accumulator rows = rows of A, row-major [rows, cols] output) with fp32 output.
+enum Mode { MODE_STATS = 0, MODE_PROBS = 1, MODE_PV = 2, MODE_PVT = 3, MODE_DS = 4, MODE_PVT32 = 5 };
+enum DType { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 
 constexpr int kOutChunkBytes = 128 * 128;   // epilogue staging: 128 rows x 128 B (one SWIZZLE_128B TMA-store box)
 constexpr int kDmaxSlots = 64;          // images whose diagonal maximum a probability-pass CTA caches in shared memory
@@ -70,6 +83,9 @@ struct GemmArgs {
   int stages;
   uint32_t idesc;
   float c;             // scale * log2(e)
+  int k_half;          // AM == 2 (symmetrised A): k-steps [0, k_half) read A K-major through tmap_a, [k_half, k_steps) read the
+                       //   same matrix transposed (MN-major boxes through tmap_a2); B k-coordinates restart at k_half
+  uint32_t idesc2;     //   instruction descriptor of the second half (a_major = MN)
   int skip_epilogue;   // experiments only (ACAN_SKIP_EPI=1): release the accumulator without reading it
   const float* dpart;  // fast path: [B, n_dpart] per-CTA maxima of the diagonal d_i = S_ii * c (diag_kernel); an image is "safe" when its
   int n_dpart;         //   maximum is <= kSafeDiagMax.  MODE_STATS skips the tiles of safe images (and exits at once when all are).
@@ -87,6 +103,13 @@ struct GemmArgs {
   float ds_inv_bn;       //   1 / (B N)
   const float* gscale; // backward: device pair (s, 1/s), the power-of-two gradient scale that keeps fp16 dO / dS in range
   const float* inv_l;  // MODE_PV / MODE_PVT: [B, N] 1 / l_i applied per query while the accumulator leaves TMEM (null = already normalised)
+  float out_scale;     // MODE_PVT / MODE_PVT32: constant factor on the output (host sets 1)
+  const float* out_gscale;   //   device scalar multiplied in as well (null = 1)
+  int out_bf16;        // MODE_PVT / MODE_DS: 16-bit output is bf16 instead of fp16
+  float* lsum_out;     // MODE_PVT / MODE_PVT32 with l_in: [B, N] the row sums go here (training path: the divisor of the stored probabilities)
+  float p_scale;       // MODE_PROBS (normalised): stored probabilities = P * p_scale (1, or kKeepScale on the training path)
+  const float* ds_lsum;  // MODE_DS (channels-last backward): [B, N] sum_j of the stored fp16 probabilities; p_ij = ds_p_ij / ds_lsum_i
+  int ds_new;          //   1: scale factors come from gscale[0..3] = (s_ds, 1/s_ds, s_ds/s_op, 1/s_op), delta was computed from the packed operand
   int pdl;             // host only: launch as a programmatic dependent of the previous kernel in the stream (one of ours, see griddep_wait)
   long long* trace;    // experiments only (ACAN_TRACE=1): per-tile clock64 stamps of CTA 0: [tile][4] = mma start, mma issued, epi start, epi end
   // MODE_STATS
@@ -114,6 +137,12 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool bf16) { return bf16 ? pack_bf162(a, b) : pack_half2(a, b); }
 
 // 16-byte chunk j (0..7) of row r (0..127) inside a 128 B-per-row SWIZZLE_128B staging buffer
 __device__ __forceinline__ uint4* staged_chunk(uint8_t* buf, int r, int j) {
@@ -155,10 +184,12 @@ __device__ __forceinline__ float image_dmax(const float* __restrict__ dpart, int
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues M = 256 MMAs that read both
 // shared memories and write both TMEMs, so the L2 -> SM operand traffic per FLOP drops by (128+BN)/(128+BN/2).
-// AMN / BMN: that operand is read as an MN-major tile (64-element-wide {MN x 64 K-row} TMA boxes, 8 KB apart).
-template <int MODE, int CG, bool AMN, bool BMN>
+// AM = 1 / BMN: that operand is read as an MN-major tile (64-element-wide {MN x 64 K-row} TMA boxes, 8 KB apart).
+// AM = 2: A is a square matrix that enters the product symmetrised, acc = (A + A^T) B: the k-loop runs over it twice, first
+// K-major (tmap_a) then MN-major (tmap_a2), both halves into the same accumulator (the two dF GEMMs of the backward pass).
+template <int MODE, int CG, int AM, bool BMN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
@@ -188,6 +219,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
+    if (AM == 2) tma_prefetch_desc(&tmap_a2);
     tma_prefetch_desc(&tmap_b);
     if (MODE != MODE_STATS) tma_prefetch_desc(&tmap_out);
   }
@@ -220,36 +252,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int ks = 0; ks < g.k_steps; ++ks) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          const bool a_mn = (AM == 1) || (AM == 2 && ks >= g.k_half);      // this k-step reads A as an MN-major tile
+          const int kk = (AM == 2 && ks >= g.k_half) ? ks - g.k_half : ks;  // k coordinate (both halves of AM == 2 walk the same k range)
+          uint32_t leader_bar = 0;
           if (CG == 1) {
             mbar_expect_tx(&bars->full[stage], stage_bytes);
-            if constexpr (AMN) {                   // MN-major A: two {64 rows-of-A x 64 k} boxes
-              for (uint32_t s = 0; s < BM / 64; ++s)
-                tma_load_3d(sa + s * 8192, &tmap_a, &bars->full[stage], a_row + static_cast<int>(s) * 64, ks * BK, b);
-            } else {
-              tma_load_3d(sa, &tmap_a, &bars->full[stage], ks * BK, a_row, b);
-            }
-            if constexpr (BMN) {                   // MN-major B: one {64 rows-of-B x 64 k} box per 64 rows
-              for (uint32_t s = 0; s < b_rows / 64; ++s)
-                tma_load_3d(sa + a_bytes + s * 8192, &tmap_b, &bars->full[stage], b_row + static_cast<int>(s) * 64, ks * BK, b);
-            } else {
-              tma_load_3d(sa + a_bytes, &tmap_b, &bars->full[stage], ks * BK, b_row, b);
-            }
           } else {
             // both CTAs' bytes complete on the LEADER's barrier; the leader arms it for the pair's total
             if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], stage_bytes * 2);
-            const uint32_t leader_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
-            if constexpr (AMN) {
-              for (uint32_t s = 0; s < BM / 64; ++s)
-                tma_load_3d_2sm(sa + s * 8192, &tmap_a, leader_bar, a_row + static_cast<int>(s) * 64, ks * BK, b);
-            } else {
-              tma_load_3d_2sm(sa, &tmap_a, leader_bar, ks * BK, a_row, b);
-            }
-            if constexpr (BMN) {
-              for (uint32_t s = 0; s < b_rows / 64; ++s)
-                tma_load_3d_2sm(sa + a_bytes + s * 8192, &tmap_b, leader_bar, b_row + static_cast<int>(s) * 64, ks * BK, b);
-            } else {
-              tma_load_3d_2sm(sa + a_bytes, &tmap_b, leader_bar, ks * BK, b_row, b);
-            }
+            leader_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+          }
+          auto ld = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if (CG == 1) tma_load_3d(dst, m, &bars->full[stage], c0, c1, b);
+            else         tma_load_3d_2sm(dst, m, leader_bar, c0, c1, b);
+          };
+          if (a_mn) {                            // MN-major A: two {64 rows-of-A x 64 k} boxes
+            const CUtensorMap* ma = (AM == 2) ? &tmap_a2 : &tmap_a;
+            for (uint32_t s = 0; s < BM / 64; ++s) ld(sa + s * 8192, ma, a_row + static_cast<int>(s) * 64, kk * BK);
+          } else {
+            ld(sa, &tmap_a, kk * BK, a_row);
+          }
+          if constexpr (BMN) {                   // MN-major B: one {64 rows-of-B x 64 k} box per 64 rows
+            for (uint32_t s = 0; s < b_rows / 64; ++s) ld(sa + a_bytes + s * 8192, &tmap_b, b_row + static_cast<int>(s) * 64, kk * BK);
+          } else {
+            ld(sa + a_bytes, &tmap_b, kk * BK, b_row);
           }
           if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
         }
@@ -263,26 +289,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (MODE == MODE_STATS && g.dpart != nullptr && image_dmax(g.dpart, g.n_dpart, tile / (g.n_tiles * g.m_tiles)) <= kSafeDiagMax) continue;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 0] = clock64();
+        if (kExperiment && g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 0] = clock64();
         const uint32_t d_tmem = tmem_base + acc * kMaxBN;
         for (int ks = 0; ks < g.k_steps; ++ks) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = sa + a_bytes;
+          const bool a_mn = (AM == 1) || (AM == 2 && ks >= g.k_half);
+          const uint32_t idesc = (AM == 2 && ks >= g.k_half) ? g.idesc2 : g.idesc;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = AMN ? umma_desc_mn_sw128(sa + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sa + k * UMMA_K * 2);
+            const uint64_t da = a_mn ? umma_desc_mn_sw128(sa + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sa + k * UMMA_K * 2);
             const uint64_t db = BMN ? umma_desc_mn_sw128(sb + k * UMMA_K * 128, 8192) : umma_desc_k_sw128(sb + k * UMMA_K * 2);
-            if (CG == 1) umma_f16(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
-            else         umma_f16_2sm(d_tmem, da, db, g.idesc, (ks | k) != 0 ? 1u : 0u);
+            if (CG == 1) umma_f16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            else         umma_f16_2sm(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           // smem slot free (in both CTAs of a pair) once these MMAs have read it
           if (CG == 1) umma_commit(&bars->empty[stage]); else umma_commit_2sm(&bars->empty[stage], 3);
           if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
         }
         if (CG == 1) umma_commit(&bars->tmem_full[acc]); else umma_commit_2sm(&bars->tmem_full[acc], 3);   // -> epilogue(s)
-        if (g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 1] = clock64();
+        if (kExperiment && g.trace && blockIdx.x == 0) g.trace[(tile / tile_step) * 4 + 1] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -322,10 +350,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (g.trace && blockIdx.x == 0 && threadIdx.x == 64) g.trace[(tile / tile_step) * 4 + 2] = clock64();
+      if (kExperiment && g.trace && blockIdx.x == 0 && threadIdx.x == 64) g.trace[(tile / tile_step) * 4 + 2] = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
 
-      if (g.skip_epilogue == 1) {
+      if (kExperiment && g.skip_epilogue == 1) {
         // nothing: mainloop-only timing experiment
       } else if constexpr (MODE == MODE_STATS) {
         float m = -INFINITY, l = 0.f;                   // m in raw dot-product units
@@ -367,7 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         } else {
           const float2 st = g.stats[brow];
           m2 = st.x;
-          inv_l = 1.0f / st.y;
+          inv_l = g.p_scale / st.y;
           log2_l = lg2_approx(st.y);
         }
         float l_acc = 0.f;                               // un-normalised mode: sum of the fp16-rounded p~ this group wrote
@@ -391,7 +419,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             if (two) l_acc += probs_unnorm_half(v1, nvalid - (ch + 1) * 32, g.c, m2, buf, row_in_tile, 1);
             fence_proxy_async();                              // generic-proxy smem writes -> visible to the TMA engine
             named_bar_sync(bar_id, 128);
-            if (store_leader && g.skip_epilogue != 2) {       // rows / columns beyond N are clipped by the tensor map
+            if (store_leader && !(kExperiment && g.skip_epilogue == 2)) {       // rows / columns beyond N are clipped by the tensor map
               tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
               tma_store_commit();
             }
@@ -428,29 +456,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   }
                 }
               }
-              if (g.skip_epilogue != 3) {
+              if (!(kExperiment && g.skip_epilogue == 3)) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;
+                for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]) * inv_l;      // inv_l carries p_scale
               }
               if (g.store_p) {
+                uint32_t hh[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hh[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+                if (g.lpart) {                   // training path: row sums of exactly the values the later passes will read
+                  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&hh[j]));
+                    s0 += (2 * j < nv) ? r.x : 0.f;
+                    s1 += (2 * j + 1 < nv) ? r.y : 0.f;
+                  }
+                  l_acc += s0 + s1;
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  *staged_chunk(buf, row_in_tile, half * 4 + q) =
-                      make_uint4(pack_half2(v[q * 8 + 0], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
-                                 pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+                  *staged_chunk(buf, row_in_tile, half * 4 + q) = make_uint4(hh[q * 4 + 0], hh[q * 4 + 1], hh[q * 4 + 2], hh[q * 4 + 3]);
               }
               if (srow && row_ok) {
                 float4* dst = reinterpret_cast<float4*>(srow + chh * 32);
+                const float us = g.p_scale != 1.0f ? 1.0f / g.p_scale : 1.0f;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                  if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                  if (q * 4 < nv) dst[q] = make_float4(v[q * 4 + 0] * us, v[q * 4 + 1] * us, v[q * 4 + 2] * us, v[q * 4 + 3] * us);
               }
             }
           }
           if (g.store_p) {
             fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA engine
             named_bar_sync(bar_id, 128);
-            if (store_leader && g.skip_epilogue != 2) { // rows / columns beyond N are clipped by the tensor map
+            if (store_leader && !(kExperiment && g.skip_epilogue == 2)) { // rows / columns beyond N are clipped by the tensor map
               tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
               tma_store_commit();
             }
@@ -458,13 +498,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         if (kl && row_ok) g.kl_part[part_idx] = kl_acc;
         if (kl && g.klw_part && row_ok) g.klw_part[part_idx] = klw_acc;
-        if (g.unnorm && row_ok) g.lpart[part_idx] = l_acc;
+        if ((g.unnorm || g.lpart) && row_ok) g.lpart[part_idx] = l_acc;
       } else if constexpr (MODE == MODE_DS) {
         // acc = dP_ij.  dS_ij = P_ij (dP_ij - delta_i) - gk (W_ij [in clamp window] - P_ij T_i),  gk = dLoss/dloss3 / (B N)
         const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
-        const float gs = g.gscale ? __ldg(g.gscale) : 1.0f;          // dP already carries the scale (dO was packed scaled)
-        const float delta_i = g.ds_delta[brow] * gs;
+        // legacy (fp32-NCHW ABI): dP already carries the scale s (dO was packed scaled), delta is unscaled.
+        // ds_new (channels-last ABI): delta was computed from the operand the GEMM read; acc and delta take s_ds / s_op, the loss term s_ds.
+        const float gs = g.gscale ? __ldg(g.gscale) : 1.0f;
+        const float acc_mul = g.ds_new ? __ldg(g.gscale + 2) : 1.0f;
+        const float delta_i = g.ds_delta ? g.ds_delta[brow] * (g.ds_new ? acc_mul : gs) : 0.f;
         const float gks = (g.ds_gl ? __ldg(g.ds_gl) * g.ds_inv_bn : 0.f) * gs;
+        const float pn = g.ds_lsum ? 1.0f / g.ds_lsum[brow] : 1.0f;       // stored probabilities -> normalised
         const bool kl = g.logbin != nullptr;
         float la_i = 0.f, lnz_i = 0.f, t_i = 0.f;
         if (kl) { la_i = g.logbin[brow]; lnz_i = g.lnz[brow]; t_i = g.ds_klT[brow]; }
@@ -489,9 +533,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float2 pp = __half22float2(*reinterpret_cast<const __half2*>(&pw[e]));
+                  float2 pp = __half22float2(*reinterpret_cast<const __half2*>(&pw[e]));
+                  pp.x *= pn; pp.y *= pn;
                   const int j = q * 8 + e * 2;
-                  float d0 = pp.x * (v[j] - delta_i), d1 = pp.y * (v[j + 1] - delta_i);
+                  float d0 = pp.x * (v[j] * acc_mul - delta_i), d1 = pp.y * (v[j + 1] * acc_mul - delta_i);
                   if (kl_row) {
                     const float lw0 = -fabsf(la_i - __ldg(la_cols + chh * 32 + j)) - lnz_i, lw1 = -fabsf(la_i - __ldg(la_cols + chh * 32 + j + 1)) - lnz_i;
                     const float w0 = ex2_approx(lw0 * kLog2e), w1 = ex2_approx(lw1 * kLog2e);
@@ -524,20 +569,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_store_commit();
           }
         }
-      } else if constexpr (MODE == MODE_PVT) {   // rows = query positions, columns = value channels; 64 fp16 columns per staged store
-        float rs = 1.0f;
-        if (g.l_in) {      // l_i = sum (fixed order) of the partial sums of the rounded p~ the probability pass wrote
+      } else if constexpr (MODE == MODE_PVT || MODE == MODE_PVT32) {   // rows = rows of A (query / key positions), columns = channels
+        float rs = g.out_scale;
+        if (g.out_gscale) rs *= __ldg(g.out_gscale);
+        if (g.l_in) {      // l_i = sum (fixed order) of the partial sums of the rounded probabilities the probability pass wrote
           const float* lp = g.l_in + static_cast<size_t>(b) * g.l_parts * g.m_rows + (row_ok ? row : 0);
           float l = 0.f;
           for (int t = 0; t < g.l_parts; ++t) l += __ldg(lp + static_cast<size_t>(t) * g.m_rows);
-          rs = 1.0f / l;
+          rs *= 1.0f / l;
           if (row_ok && nt == 0 && group == 0) {
             const size_t brow = static_cast<size_t>(b) * g.m_rows + row;
-            g.stats_w[brow].y = l;
+            if (g.stats_w) g.stats_w[brow].y = l;
             if (g.stats_w2) g.stats_w2[brow].y = l;
+            if (g.lsum_out) g.lsum_out[brow] = l;
           }
         }
-        for (int ch = 2 * group; ch < chunks; ch += 4) {
+        if constexpr (MODE == MODE_PVT32) {       // 32 fp32 columns (128 B) per staged store; the groups take alternate chunks
+          for (int ch = group; ch < chunks; ch += 2) {
+            float v[32];
+            tmem_ld_32x32(taddr + ch * 32, v);
+            if (store_leader) tma_store_wait_read<0>();
+            tmem_ld_wait();
+            named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *staged_chunk(buf, row_in_tile, q) = make_uint4(__float_as_uint(v[q * 4 + 0] * rs), __float_as_uint(v[q * 4 + 1] * rs),
+                                                              __float_as_uint(v[q * 4 + 2] * rs), __float_as_uint(v[q * 4 + 3] * rs));
+            fence_proxy_async();
+            named_bar_sync(bar_id, 128);
+            if (store_leader) {
+              tma_store_3d(&tmap_out, buf, col0 + ch * 32, row0, b);
+              tma_store_commit();
+            }
+          }
+        } else
+        for (int ch = 2 * group; ch < chunks; ch += 4) {   // 64 16-bit columns per staged store
           float v[2][32];
           const bool two = ch + 1 < chunks;                   // warp-uniform
           tmem_ld_32x32(taddr + ch * 32, v[0]);
@@ -551,8 +617,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *staged_chunk(buf, row_in_tile, half * 4 + q) =
-                    make_uint4(pack_half2(v[half][q * 8 + 0] * rs, v[half][q * 8 + 1] * rs), pack_half2(v[half][q * 8 + 2] * rs, v[half][q * 8 + 3] * rs),
-                               pack_half2(v[half][q * 8 + 4] * rs, v[half][q * 8 + 5] * rs), pack_half2(v[half][q * 8 + 6] * rs, v[half][q * 8 + 7] * rs));
+                    make_uint4(pack16(v[half][q * 8 + 0] * rs, v[half][q * 8 + 1] * rs, g.out_bf16), pack16(v[half][q * 8 + 2] * rs, v[half][q * 8 + 3] * rs, g.out_bf16),
+                               pack16(v[half][q * 8 + 4] * rs, v[half][q * 8 + 5] * rs, g.out_bf16), pack16(v[half][q * 8 + 6] * rs, v[half][q * 8 + 7] * rs, g.out_bf16));
             }
           }
           fence_proxy_async();
@@ -593,7 +659,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
 
-      if (g.trace && blockIdx.x == 0 && threadIdx.x == 64) g.trace[(tile / tile_step) * 4 + 3] = clock64();
+      if (kExperiment && g.trace && blockIdx.x == 0 && threadIdx.x == 64) g.trace[(tile / tile_step) * 4 + 3] = clock64();
       tc_fence_before();
       // one arrival per epilogue warp (8 x CG) on the LEADER's barrier releases the accumulator buffer
       __syncwarp();
@@ -738,6 +804,25 @@ __global__ void __launch_bounds__(256) combine_l_kernel(const float* __restrict_
   }
 }
 
+// bf16 / fp32 -> fp16, same layout, clamped to the fp16 range (exact for bf16 values inside it)
+template <bool SRC_BF16>
+__global__ void __launch_bounds__(256) to_half_kernel(const void* __restrict__ src, uint4* __restrict__ out, int64_t n8) {
+  auto cl = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
+    float f[8];
+    if (SRC_BF16) {
+      const uint4 u = ldg_nc_u4(reinterpret_cast<const uint4*>(src) + i);
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(wv[e] << 16); f[2 * e + 1] = __uint_as_float(wv[e] & 0xffff0000u); }
+    } else {
+      const float4 a = ldg_stream(reinterpret_cast<const float4*>(src) + 2 * i), b = ldg_stream(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    out[i] = make_uint4(pack_half2(cl(f[0]), cl(f[1])), pack_half2(cl(f[2]), cl(f[3])), pack_half2(cl(f[4]), cl(f[5])), pack_half2(cl(f[6]), cl(f[7])));
+  }
+}
+
 // ---- backward helpers
 // fp32 -> fp16 / bf16, same layout (clamped to the fp16 range for fp16)
 template <bool BF16>
@@ -842,16 +927,17 @@ __global__ void __launch_bounds__(256) scaled_sum_kernel(const float4* __restric
 // attention-loss-only dS (no aggregation gradient): dS_ij = -gk (W_ij [in window] - P_ij T_i), one CTA per row, scaled fp16 out
 __global__ void __launch_bounds__(256) kl_ds_kernel(const __half* __restrict__ p, const float* __restrict__ logbin, const float* __restrict__ lnz,
                                                      const float* __restrict__ klT, __half* __restrict__ ds, const float* __restrict__ grad_loss,
-                                                     float inv_bn, const float* __restrict__ gscale, int N) {
+                                                     float inv_bn, const float* __restrict__ gscale, int N, const float* __restrict__ lsum = nullptr) {
   const float gk = __ldg(grad_loss) * inv_bn * __ldg(gscale);
   const int64_t row = blockIdx.x;
+  const float pn = lsum ? 1.0f / lsum[row] : 1.0f;
   const int b = static_cast<int>(row / N);
   const float la_i = logbin[row], lnz_i = lnz[row], t_i = klT[row];
   const float* la = logbin + static_cast<size_t>(b) * N;
   const __half* pr = p + row * N;
   __half* dr = ds + row * N;
   for (int j = threadIdx.x; j < N; j += 256) {
-    const float pv = __half2float(pr[j]);
+    const float pv = __half2float(pr[j]) * pn;
     float d = 0.f;
     if (la_i > -INFINITY) {
       const float lw = -fabsf(la_i - la[j]) - lnz_i;
@@ -861,6 +947,79 @@ __global__ void __launch_bounds__(256) kl_ds_kernel(const __half* __restrict__ p
     }
     dr[j] = __float2half_rn(d);
   }
+}
+
+// channels-last backward: delta[row] = sum_c dO[row, c] * O[row, c] with dO the 16-bit operand the dP GEMM reads (so that
+// delta_i == sum_j p_ij dP_ij holds for the values the tensor cores see) and O the fp32 aggregation output; max |dO| on the side.
+// One warp per row, a lane owns 8 consecutive channels per step, 4 steps in flight.
+template <bool GO_BF16>
+__global__ void __launch_bounds__(256, 4) delta_nhwc_kernel(const uint4* __restrict__ go, const float4* __restrict__ o, float* __restrict__ delta,
+                                                             int* __restrict__ amax_bits, int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* g = go + row * (C / 8);
+  const float4* x = o + row * (C / 4);
+  float acc = 0.f, am = 0.f;
+  auto term = [&](const uint4& u, const float4& a, const float4& b) {
+    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+    const float of[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float g0, g1;
+      if (GO_BF16) { g0 = __uint_as_float(wv[e] << 16); g1 = __uint_as_float(wv[e] & 0xffff0000u); }
+      else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&wv[e])); g0 = t.x; g1 = t.y; }
+      acc = fmaf(g0, of[2 * e], acc);
+      acc = fmaf(g1, of[2 * e + 1], acc);
+      am = fmaxf(am, fmaxf(fabsf(g0), fabsf(g1)));
+    }
+  };
+  const int c8 = C / 8;
+  int k = lane;
+  for (; k + 96 < c8; k += 128) {
+    uint4 u[4]; float4 a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { u[q] = ldg_nc_u4(g + k + 32 * q); a[q] = __ldg(x + 2 * (k + 32 * q)); b[q] = __ldg(x + 2 * (k + 32 * q) + 1); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) term(u[q], a[q], b[q]);
+  }
+  for (; k < c8; k += 32) term(ldg_nc_u4(g + k), __ldg(x + 2 * k), __ldg(x + 2 * k + 1));
+  acc = warp_sum(acc);
+  am = warp_max(am);
+  if (lane == 0) {
+    delta[row] = acc;
+    if (amax_bits && am > 0.f) atomicMax(amax_bits, __float_as_int(am));
+  }
+}
+
+// max |x| over an fp32 tensor (fp32 grad_ctx: the operand pack needs its scale first)
+__global__ void __launch_bounds__(256) amax_f32_kernel(const float4* __restrict__ x, int64_t n4, int* __restrict__ amax_bits) {
+  float am = 0.f;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float4 v = ldg_stream(x + i);
+    am = fmaxf(am, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  am = warp_max(am);
+  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_int(am));
+}
+
+// channels-last backward scales, chosen on the device: sc = (s_ds, 1/s_ds, s_ds/s_op, 1/s_op).
+//   s_ds brings max |dO| to 2^-2 (dS = p (dP - delta) is stored as fp16(dS * s_ds)); without an aggregation gradient it brings the
+//   attention-loss gradient scale to ~1.   s_op = s_ds when dO was packed from fp32 (scaled while packing), 1 when it is read in place.
+__global__ void gscale4_kernel(const int* __restrict__ amax_bits, int packed, const float* __restrict__ grad_loss, float inv_bn, float* __restrict__ sc) {
+  float s = 1.0f;
+  if (amax_bits != nullptr) {
+    const float am = __int_as_float(*amax_bits);
+    s = (am > 0.f && am < INFINITY) ? exp2f(-2.0f - ceilf(log2f(am))) : 1.0f;
+  } else if (grad_loss != nullptr) {
+    const float gk = fabsf(*grad_loss * inv_bn);
+    s = (gk > 0.f && gk < INFINITY) ? exp2f(-ceilf(log2f(gk))) : 1.0f;
+  }
+  const float s_op = packed ? s : 1.0f;
+  sc[0] = s;
+  sc[1] = 1.0f / s;
+  sc[2] = s / s_op;
+  sc[3] = 1.0f / s_op;
 }
 
 // per row: ln(bin) and ln(Z_i), Z_i = sum_j min(a_i/a_j, a_j/a_i)   (target-affinity normaliser, losses.py:40-46)
@@ -892,7 +1051,8 @@ __global__ void __launch_bounds__(256) sim_rows_kernel(const __half* __restrict_
                                                         const int* __restrict__ rows, float* __restrict__ out,
                                                         int n_rows, int N, int dk, float c) {
   extern __shared__ float qrow[];
-  const int b = blockIdx.y, r = blockIdx.x, i = rows[r];
+  const int b = blockIdx.y, r = blockIdx.x;
+  const int i = min(max(rows[r], 0), N - 1);              // callers validate the indices; never read out of bounds anyway
   const __half* base = fh + static_cast<size_t>(b) * N * dk;
   for (int k = threadIdx.x; k < dk; k += 256) qrow[k] = __half2float(base[static_cast<size_t>(i) * dk + k]);
   __syncthreads();
@@ -933,39 +1093,35 @@ EncodeTiledFn get_encode_fn() {
 // tensor [batch][rows][inner] (inner contiguous) of fp16 (elem_bytes 2) or fp32 (4); box = {128 B of elements, box_rows, 1},
 // SWIZZLE_128B, out-of-bounds elements read as 0 / are not written
 int make_tmap(CUtensorMap* m, const void* base, int elem_bytes, int inner, int rows, int batch, size_t row_pitch_bytes, size_t batch_pitch_bytes,
-              int box_rows) {
+              int box_rows, bool bf16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch_bytes), static_cast<cuuint64_t>(batch_pitch_bytes)};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
+  CUresult r = fn(m, elem_bytes == 2 ? (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16) : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%d rows=%d batch=%d box_rows=%d)", (int)r, inner, rows, batch, box_rows);
   return 0;
 }
 
-// CTA-pair (cta_group::2) or single-CTA tiles; ACAN_CTA_GROUP=1 forces the single-CTA kernels (A/B measurements)
+// Experiment builds (-DACAN_EXPERIMENT) read overrides from the environment (ACAN_BN_QK / ACAN_BN_PV tile widths, ACAN_SKIP_EPI,
+// ACAN_TRACE, ACAN_EXACT_STATS, ACAN_PDL=0, ACAN_CTA_GROUP=1); the shipped library returns the default without looking.
 int env_int(const char* name, int dflt) {
+  if (!kExperiment) return dflt;
   const char* e = getenv(name);
   return (e && *e) ? atoi(e) : dflt;
 }
 
-// ACAN_PDL=0 launches every pass the ordinary way (A/B measurements)
-bool use_pdl() {
-  static int v = -1;
-  if (v < 0) v = env_int("ACAN_PDL", 1) ? 1 : 0;
-  return v == 1;
+bool use_pdl() {            // programmatic dependent launch between the passes of one call
+  static const bool v = env_int("ACAN_PDL", 1) != 0;
+  return v;
 }
 
-int cta_group() {
-  static int cg = 0;
-  if (cg == 0) {
-    const char* e = getenv("ACAN_CTA_GROUP");
-    cg = (e && e[0] == '1') ? 1 : 2;
-  }
+int cta_group() {           // CTA pairs (cta_group::2) unless an experiment build asks for single-CTA tiles
+  static const int cg = env_int("ACAN_CTA_GROUP", 2) == 1 ? 1 : 2;
   return cg;
 }
 
@@ -1002,6 +1158,10 @@ struct Workspace {
   float* diag;     // [B, N]  S_ii * c
   float* inv_l;    // [B, N]
   float* dpart;    // [B, ceil(N/128)]  per-CTA maxima of the diagonal (diag_kernel)
+  float* lpart;    // [B, 2*ceil(N/kMinBN), N]  training path: partial row sums of the stored (rounded) probabilities
+  float* lsum;     // [B, N]  their total: the divisor that makes the stored rows sum to exactly 1 (aggregation, backward)
+  float* klw_part; // [B, 2*ceil(N/kMinBN), N]  partial in-window target mass (attention loss)
+  float* klT;      // [B, N]  T_i = sum_j W_ij [W_ij / Q_ij inside the clamp window]: left by the loss forward for the backward
   size_t bytes;
 };
 
@@ -1024,22 +1184,39 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   w.diag = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.inv_l = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.dpart = reinterpret_cast<float*>(take(static_cast<size_t>(B) * ((N + kDiagRows - 1) / kDiagRows) * 4));
+  w.lpart = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
+  w.lsum = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.klw_part = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
+  w.klT = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.bytes = off;
   return w;
 }
 
-template <int MODE, int CG, bool AMN, bool BMN>
-int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st) {
+// opt-in to > 48 KB of dynamic shared memory: a per-device, per-function attribute (set once per device ordinal)
+template <typename K>
+int ensure_smem_optin(K kernel) {
+  static std::atomic<uint64_t> done{0};
+  int dev = 0;
+  ACAN_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    ACAN_CUDA((cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  return 0;
+}
+
+template <int MODE, int CG, int AM, bool BMN>
+int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st) {
   const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + static_cast<size_t>(g.bn / CG) * BK * 2;
   int stages = static_cast<int>((kSmemBudget - kOutBuffers * kOutChunkBytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   g.stages = stages;
   const size_t smem = stages * stage_bytes + kOutBuffers * kOutChunkBytes + sizeof(PipeBarriers) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ACAN_CUDA((cudaFuncSetAttribute(gemm_kernel<MODE, CG, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
-    attr_set = true;
-  }
+  if (int e = ensure_smem_optin(gemm_kernel<MODE, CG, AM, BMN>)) return e;
+  if (g.out_scale == 0.f) g.out_scale = 1.0f;
+  if (g.p_scale == 0.f) g.p_scale = 1.0f;
+  if (AM != 2) g.k_half = g.k_steps;
   const int tiles = g.batch * g.m_tiles * g.n_tiles;
   const int slots = kNumSMs / CG;
   cudaLaunchConfig_t cfg = {};
@@ -1054,14 +1231,15 @@ int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (g.pdl && use_pdl()) ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG, AMN, BMN>, ta, tb, tout, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG, AM, BMN>, ta, ta2, tb, tout, g);
   if (e != cudaSuccess) return fail((int)e, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return launch_status("acan gemm_kernel");
 }
 
-template <int MODE, bool AMN = false, bool BMN = (MODE == MODE_PVT)>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st, int cg) {
-  return cg == 2 ? launch_gemm_cg<MODE, 2, AMN, BMN>(ta, tb, tout, g, st) : launch_gemm_cg<MODE, 1, AMN, BMN>(ta, tb, tout, g, st);
+template <int MODE, int AM = 0, bool BMN = (MODE == MODE_PVT)>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st, int cg, const CUtensorMap* ta2 = nullptr) {
+  const CUtensorMap& a2 = ta2 ? *ta2 : ta;
+  return cg == 2 ? launch_gemm_cg<MODE, 2, AM, BMN>(ta, a2, tb, tout, g, st) : launch_gemm_cg<MODE, 1, AM, BMN>(ta, a2, tb, tout, g, st);
 }
 
 int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
@@ -1073,8 +1251,9 @@ int check_attn_shape(const char* who, int B, int N, int dk, int dv) {
 }
 
 // passes 1+2 over S = Fh Fh^T: statistics, then probabilities / sim_map / fused KL
+// keep: training path -- the stored probabilities are fp16(P * kKeepScale) and their row sums go to w.lpart (2 * n_tiles slices per row)
 int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_p, float* sim_map, bool kl, int B, int N, int dk, float scale, cudaStream_t st,
-                 bool need_stats, int* key_tiles, float* klw_part = nullptr) {
+                 bool need_stats, int* key_tiles, float* klw_part = nullptr, bool keep = false) {
   const int cg = cta_group();
   const int m_tiles = (N + BM * cg - 1) / (BM * cg);
   const int bn = env_int("ACAN_BN_QK", choose_bn(N, B * m_tiles, cg, 64));   // P leaves in 64-column (128 B) TMA-store boxes
@@ -1102,13 +1281,17 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
     g.lnz = w.lnz;
     g.kl_part = w.kl_part;
     g.klw_part = klw_part;
+    if (keep && want_p) { g.p_scale = kKeepScale; g.lpart = w.lpart; }
+#ifdef ACAN_EXPERIMENT
     static long long* trace_buf = nullptr;
     if (env_int("ACAN_TRACE", 0) && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
     g.trace = env_int("ACAN_TRACE", 0) ? trace_buf : nullptr;
+#endif
     {
       ProfScope ps(PROF_PROBS, st);
       if (int e = launch_gemm<MODE_PROBS>(ta, tb, tp, g, st, cg)) return e;
     }
+#ifdef ACAN_EXPERIMENT
     if (g.trace) {
       long long h[512];
       cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1119,6 +1302,7 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
         fprintf(stderr, "  %2d: %7lld %7lld | %7lld %7lld\n", i, h[i * 4] - h[0], h[i * 4 + 1] - h[0], h[i * 4 + 2] - h[0], h[i * 4 + 3] - h[0]);
       g.trace = nullptr;
     }
+#endif
   }
   *key_tiles = 2 * g.n_tiles;   // kl_part slices per row (key tile x epilogue group): callers reduce over them
   return 0;
@@ -1196,7 +1380,7 @@ static int attn_forward_impl(const float* feat, const float* value, float* ctx, 
   ACAN_CHECK_ARG(feat && row_stats && workspace, "acan_attn_fwd: null pointer");
   ACAN_CHECK_ARG((value == nullptr) == (ctx == nullptr), "acan_attn_fwd: value and ctx must be given together");
   if (int e = check_attn_shape("acan_attn_fwd", B, N, dk, value ? dv : 0)) return e;
-  ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N), "acan_attn_fwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
+  ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N && H % 8 == 0 && Wd % 8 == 0), "acan_attn_fwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
   ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "acan_attn_fwd: workspace must be 1024-byte aligned");
   const Workspace w = carve(workspace, B, N, dk, dv);
   if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_fwd: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
@@ -1264,61 +1448,99 @@ extern "C" int acan_attn_fwd_loss(const float* feat, const float* value, float* 
   return attn_forward_impl(feat, value, ctx, sim_map, row_stats, dis_label, H, W, loss_out, workspace, workspace_bytes, B, N, dk, dv, scale, stream);
 }
 
-// channels-last fp16 form: F and V are consumed where the convolutions left them, O is written channels-last fp16
-extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h, float* sim_map, float* row_stats,
-                                      const float* dis_label, int H, int Wd, float* loss_out,
-                                      void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, void* stream) {
-  ACAN_CHECK_ARG(feat_h && row_stats && workspace, "acan_attn_fwd_nhwc_f16: null pointer");
-  ACAN_CHECK_ARG((value_h == nullptr) == (ctx_h == nullptr), "acan_attn_fwd_nhwc_f16: value and ctx must be given together");
-  if (int e = check_attn_shape("acan_attn_fwd_nhwc_f16", B, N, dk, value_h ? dv : 0)) return e;
-  ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N), "acan_attn_fwd_nhwc_f16: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
-  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0 && reinterpret_cast<uintptr_t>(feat_h) % 16 == 0 &&
-                 reinterpret_cast<uintptr_t>(value_h) % 16 == 0 && reinterpret_cast<uintptr_t>(ctx_h) % 16 == 0,
-                 "acan_attn_fwd_nhwc_f16: workspace must be 1024-byte, tensors 16-byte aligned");
+// channels-last form: F and V are consumed where the convolutions left them (fp16, or bf16 for V), O is written channels-last.
+//   keep = 0 (inference): statistics-free probabilities when no sim_map / loss is requested (run_affinity_fast).
+//   keep = 1 (training):  exact two-pass statistics; the normalised probabilities stay in the workspace as fp16(P * 2^10) together
+//                         with the row sums of those rounded values (lsum) -- the divisor used by the aggregation here and by
+//                         acan_attn_bwd_nhwc, so that the rows the tensor cores read sum to exactly 1.
+extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* value, int value_dtype, void* ctx, int ctx_dtype,
+                                  float* sim_map, float* row_stats, const float* dis_label, int H, int Wd, float* loss_out,
+                                  void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, int keep, void* stream) {
+  ACAN_CHECK_ARG(feat && row_stats && workspace, "acan_attn_fwd_nhwc: null pointer");
+  ACAN_CHECK_ARG((value == nullptr) == (ctx == nullptr), "acan_attn_fwd_nhwc: value and ctx must be given together");
+  ACAN_CHECK_ARG(feat_dtype == DT_F16 || feat_dtype == DT_BF16 || feat_dtype == DT_F32, "acan_attn_fwd_nhwc: feat_dtype %d", feat_dtype);
+  ACAN_CHECK_ARG(!value || ((value_dtype == DT_F16 || value_dtype == DT_BF16) && (ctx_dtype == DT_F16 || ctx_dtype == DT_BF16 || ctx_dtype == DT_F32)),
+                 "acan_attn_fwd_nhwc: value must be fp16 / bf16 (got %d), ctx fp16 / bf16 / fp32 (got %d)", value_dtype, ctx_dtype);
+  if (int e = check_attn_shape("acan_attn_fwd_nhwc", B, N, dk, value ? dv : 0)) return e;
+  ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N && H % 8 == 0 && Wd % 8 == 0), "acan_attn_fwd_nhwc: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0 && reinterpret_cast<uintptr_t>(feat) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(value) % 16 == 0 && reinterpret_cast<uintptr_t>(ctx) % 16 == 0,
+                 "acan_attn_fwd_nhwc: workspace must be 1024-byte, tensors 16-byte aligned");
   const Workspace w = carve(workspace, B, N, dk, dv);
-  if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_fwd_nhwc_f16: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+  if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_fwd_nhwc: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
   if (int e = acan_device_check()) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float2* stats = reinterpret_cast<float2*>(row_stats);
-  const __half* fh = static_cast<const __half*>(feat_h);
+  const __half* fh = static_cast<const __half*>(feat);
+  if (feat_dtype != DT_F16) {          // bf16 (autocast) / fp32 features: one elementwise pass into the workspace pack
+    const int64_t n8 = static_cast<int64_t>(B) * N * dk / 8;
+    int64_t blocks = (n8 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (feat_dtype == DT_BF16) to_half_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(feat, reinterpret_cast<uint4*>(w.fh), n8);
+    else                       to_half_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(feat, reinterpret_cast<uint4*>(w.fh), n8);
+    if (int e = launch_status("to_half_kernel")) return e;
+    fh = w.fh;
+  }
   if (dis_label)
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
   int nt = 0;
-  const bool fast = value_h && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  const bool fast = !keep && value && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
   int l_parts = 0;
   if (fast) {
     if (int e = run_affinity_fast(w, fh, stats, B, N, dk, scale, st, false, &l_parts)) return e;
   } else {
-    if (int e = run_affinity(w, fh, stats, value_h != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt)) return e;
+    if (int e = run_affinity(w, fh, stats, value != nullptr, sim_map, dis_label != nullptr, B, N, dk, scale, st, true, &nt,
+                             (keep && dis_label) ? w.klw_part : nullptr, keep != 0)) return e;
+    l_parts = nt;
   }
   if (dis_label) {
     ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
     if (int e = launch_status("ordered_sum_kernel")) return e;
+    if (keep) {
+      const int64_t rows = static_cast<int64_t>(B) * N;
+      sum_parts_kernel<<<static_cast<int>((rows + 255) / 256), 256, 0, st>>>(w.klw_part, w.klT, nt, N, rows);
+      if (int e = launch_status("sum_parts_kernel")) return e;
+    }
   }
-  if (value_h) {
+  if (value) {
     // O[Nq, dv] = P[Nq, Nk] * V[Nk, dv]: A = P (K-major), B = V in place (MN-major: channels contiguous)
     const int cg = cta_group();
     const int m_tiles = (N + BM * cg - 1) / (BM * cg);
     const int bn = env_int("ACAN_BN_PV", choose_bn(dv, B * m_tiles, cg, 64 * cg, 64 * cg));   // 64-channel boxes per CTA
-    ACAN_CHECK_ARG(dv % 64 == 0 && bn % (64 * cg) == 0, "acan_attn_fwd_nhwc_f16: dv=%d / tile width %d not a multiple of 64 per CTA", dv, bn);
+    ACAN_CHECK_ARG(dv % 64 == 0 && bn % (64 * cg) == 0, "acan_attn_fwd_nhwc: dv=%d / tile width %d not a multiple of 64 per CTA", dv, bn);
+    const bool vb = value_dtype == DT_BF16;
+    const int ob = ctx_dtype == DT_F32 ? 4 : 2;
     CUtensorMap ta, tb, to;
     if (int e = make_tmap(&ta, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
-    if (int e = make_tmap(&tb, value_h, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, 64)) return e;
-    if (int e = make_tmap(&to, ctx_h, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, BM)) return e;
+    if (int e = make_tmap(&tb, value, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, 64, vb)) return e;
+    if (int e = make_tmap(&to, ctx, ob, dv, N, B, static_cast<size_t>(dv) * ob, static_cast<size_t>(N) * dv * ob, BM, ctx_dtype == DT_BF16)) return e;
     GemmArgs g;
     std::memset(&g, 0, sizeof(g));
     g.batch = B; g.m_tiles = m_tiles; g.n_tiles = (dv + bn - 1) / bn; g.k_steps = (N + BK - 1) / BK;
-    g.m_rows = N; g.n_cols = dv; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg, true); g.c = 0.f;
+    g.m_rows = N; g.n_cols = dv; g.bn = bn; g.idesc = umma_idesc_f16(bn, BM * cg, true, false, false, vb); g.c = 0.f;
     g.skip_epilogue = env_int("ACAN_SKIP_EPI", 0);
+    g.out_bf16 = ctx_dtype == DT_BF16;
     if (fast) {
       g.l_in = w.kl_part; g.l_parts = l_parts;
       g.stats_w = stats; g.stats_w2 = stats != w.stats ? w.stats : nullptr;
       g.pdl = 1;                         // directly behind the probability pass
+    } else if (keep) {
+      g.l_in = w.lpart; g.l_parts = l_parts;
+      g.lsum_out = w.lsum;
+      g.pdl = dis_label ? 0 : 1;
     }
     ProfScope ps(PROF_PV, st);
-    if (int e = launch_gemm<MODE_PVT>(ta, tb, to, g, st, cg)) return e;
+    if (ctx_dtype == DT_F32) { if (int e = launch_gemm<MODE_PVT32, 0, true>(ta, tb, to, g, st, cg)) return e; }
+    else                     { if (int e = launch_gemm<MODE_PVT, 0, true>(ta, tb, to, g, st, cg)) return e; }
   }
   return 0;
+}
+
+extern "C" int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h, float* sim_map, float* row_stats,
+                                      const float* dis_label, int H, int Wd, float* loss_out,
+                                      void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, void* stream) {
+  return acan_attn_fwd_nhwc(feat_h, DT_F16, value_h, DT_F16, ctx_h, DT_F16, sim_map, row_stats, dis_label, H, Wd, loss_out,
+                            workspace, workspace_bytes, B, N, dk, dv, scale, 0, stream);
 }
 
 extern "C" int acan_attn_rows(const void* workspace, const void* feat_pack, const int* row_idx_dev, int n_rows, float* rows_out,
@@ -1334,7 +1556,7 @@ extern "C" int acan_attn_rows(const void* workspace, const void* feat_pack, cons
 
 extern "C" int acan_attention_loss_fused(void* workspace, const void* feat_pack, const float* dis_label, float* loss_out,
                                          int B, int H, int W, int dk, int dv, float scale, void* stream) {
-  ACAN_CHECK_ARG(workspace && dis_label && loss_out && H >= 8 && W >= 8, "acan_attention_loss_fused: bad argument");
+  ACAN_CHECK_ARG(workspace && dis_label && loss_out && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "acan_attention_loss_fused: bad argument (H, W must be multiples of 8)");
   const int N = (H / 8) * (W / 8);
   if (int e = check_attn_shape("acan_attention_loss_fused", B, N, dk, dv)) return e;
   const Workspace w = carve(workspace, B, N, dk, dv);
@@ -1342,9 +1564,13 @@ extern "C" int acan_attention_loss_fused(void* workspace, const void* feat_pack,
   if (int e = prepare_target(w, dis_label, B, H, W, st)) return e;
   int nt = 0;
   const __half* fh = feat_pack ? static_cast<const __half*>(feat_pack) : w.fh;
-  if (int e = run_affinity(w, fh, w.stats, false, nullptr, true, B, N, dk, scale, st, false, &nt)) return e;
+  // (the in-window target mass T_i is left in the workspace for acan_attn_bwd_nhwc)
+  if (int e = run_affinity(w, fh, w.stats, false, nullptr, true, B, N, dk, scale, st, false, &nt, w.klw_part)) return e;
   ordered_sum_kernel<<<1, 1024, 0, st>>>(w.kl_part, static_cast<int64_t>(B) * nt * N, 1.0f / (static_cast<float>(B) * N), loss_out);
-  return launch_status("ordered_sum_kernel");
+  if (int e = launch_status("ordered_sum_kernel")) return e;
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  sum_parts_kernel<<<static_cast<int>((rows + 255) / 256), 256, 0, st>>>(w.klw_part, w.klT, nt, N, rows);
+  return launch_status("sum_parts_kernel");
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -1423,7 +1649,7 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
   ACAN_CHECK_ARG(!dis_label || grad_loss, "acan_attn_bwd: a label needs grad_loss (device scalar)");
   if (int e = check_attn_shape("acan_attn_bwd", B, N, dk, dv)) return e;
   ACAN_CHECK_ARG(N % 8 == 0 && (static_cast<int64_t>(dk) * N) % 8 == 0, "acan_attn_bwd: N must be a multiple of 8");
-  ACAN_CHECK_ARG(!dis_label || (H / 8) * (Wd / 8) == N, "acan_attn_bwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
+  ACAN_CHECK_ARG(!dis_label || ((H / 8) * (Wd / 8) == N && H % 8 == 0 && Wd % 8 == 0), "acan_attn_bwd: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
   ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "acan_attn_bwd: workspace must be 1024-byte aligned");
   const BwdWorkspace w = carve_bwd(workspace, B, N, dk, dv);
   if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_bwd: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
@@ -1472,7 +1698,7 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
       if (int e = make_tmap(&to, grad_value, 4, N, dv, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dv) * N * 4, BM)) return e;
       GemmArgs g = gemm_args(B, dv, N, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, false, false));
       g.gscale = w.gscale;
-      if (int e = launch_gemm<MODE_PV, false, true>(ta, tb, to, g, st, cg)) return e;
+      if (int e = launch_gemm<MODE_PV, 0, true>(ta, tb, to, g, st, cg)) return e;
     }
     {  // dP[i, j] = sum_c dO[c, i] V[c, j] (both operands MN-major from their NCHW packs) -> dS epilogue, scaled fp16 out
       const int m_tiles = (N + BM * cg - 1) / (BM * cg);
@@ -1483,7 +1709,7 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
       GemmArgs g = gemm_args(B, N, N, dv, bn, cg, umma_idesc_f16(bn, BM * cg, true, true, false));
       g.ds_delta = w.delta; g.ds_p = w.f.p; g.ds_klT = w.klT; g.ds_gl = dis_label ? grad_loss : nullptr; g.ds_inv_bn = inv_bn; g.gscale = w.gscale;
       g.logbin = dis_label ? w.f.logbin : nullptr; g.lnz = w.f.lnz;
-      if (int e = launch_gemm<MODE_DS, true, true>(ta, tb, to, g, st, cg)) return e;
+      if (int e = launch_gemm<MODE_DS, 1, true>(ta, tb, to, g, st, cg)) return e;
     }
   } else {
     kl_ds_kernel<<<static_cast<int>(rows), 256, 0, st>>>(w.f.p, w.f.logbin, w.f.lnz, w.klT, w.ds, grad_loss, inv_bn, w.gscale, N);
@@ -1497,14 +1723,14 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
       if (int e = make_tmap(&tb, w.ds, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, bn / cg)) return e;
       if (int e = make_tmap(&to, w.df1, 4, N, dk, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dk) * N * 4, BM)) return e;
       GemmArgs g = gemm_args(B, dk, N, N, bn, cg, umma_idesc_f16(bn, BM * cg, false, false, false));
-      if (int e = launch_gemm<MODE_PV, false, false>(ta, tb, to, g, st, cg)) return e;       // sum_j F[c,j] dS[i,j]
+      if (int e = launch_gemm<MODE_PV, 0, false>(ta, tb, to, g, st, cg)) return e;       // sum_j F[c,j] dS[i,j]
     }
     {
       const int bn = choose_bn(N, B * m_tiles, cg, 64 * cg, 64 * cg);
       if (int e = make_tmap(&tb, w.ds, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, 64)) return e;
       if (int e = make_tmap(&to, w.df2, 4, N, dk, B, static_cast<size_t>(N) * 4, static_cast<size_t>(dk) * N * 4, BM)) return e;
       GemmArgs g = gemm_args(B, dk, N, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, false, false));
-      if (int e = launch_gemm<MODE_PV, false, true>(ta, tb, to, g, st, cg)) return e;        // sum_j F[c,j] dS[j,i]
+      if (int e = launch_gemm<MODE_PV, 0, true>(ta, tb, to, g, st, cg)) return e;        // sum_j F[c,j] dS[j,i]
     }
     const int64_t n4 = static_cast<int64_t>(B) * dk * N / 4;
     int64_t blocks = (n4 + 255) / 256;
@@ -1512,6 +1738,157 @@ extern "C" int acan_attn_bwd(const float* feat, const float* value, const float*
     scaled_sum_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const float4*>(w.df1), reinterpret_cast<const float4*>(w.df2),
                                                                 reinterpret_cast<float4*>(grad_feat), scale, w.gscale, n4);
     if (int e = launch_status("scaled_sum_kernel")) return e;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ channels-last backward
+namespace acan {
+namespace {
+
+struct BwdScratch {
+  __half* ds;       // [B, N, N] fp16   dS * s_ds
+  __half* doh;      // [B, N, dv] fp16  grad_ctx packed (fp32 grad_ctx only)
+  float* delta;     // [B, N]
+  float* gscale;    // [4]
+  int* amax_bits;   // [1]
+  size_t bytes;
+};
+
+BwdScratch carve_scratch(void* base, int B, int N, int dv) {
+  BwdScratch w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return reinterpret_cast<uint8_t*>(base) + o; };
+  w.ds = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * N * 2));
+  w.doh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * dv * 2));
+  w.delta = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.gscale = reinterpret_cast<float*>(take(16));
+  w.amax_bits = reinterpret_cast<int*>(take(16));
+  w.bytes = off;
+  return w;
+}
+
+// accumulator rows = rows of A, row-major [rows, cols] output in fp32 / fp16 / bf16
+template <int AM>
+int launch_rowmajor(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GemmArgs& g, cudaStream_t st, int cg, int out_dtype,
+                    const CUtensorMap* ta2 = nullptr) {
+  g.out_bf16 = out_dtype == DT_BF16;
+  if (out_dtype == DT_F32) return launch_gemm<MODE_PVT32, AM, true>(ta, tb, to, g, st, cg, ta2);
+  return launch_gemm<MODE_PVT, AM, true>(ta, tb, to, g, st, cg, ta2);
+}
+
+}  // namespace
+}  // namespace acan
+
+extern "C" size_t acan_attn_bwd_nhwc_scratch_bytes(int B, int N, int dk, int dv) {
+  if (B <= 0 || N <= 0 || dk <= 0 || dv <= 0) return 0;
+  return carve_scratch(nullptr, B, N, dv).bytes;
+}
+
+// Backward of acan_attn_fwd_nhwc(keep = 1) (+ grad_loss * attention loss when have_loss) w.r.t. F and V, channels-last, on tcgen05:
+//   dV = P^T dO        dP = dO V^T        dS = p o (dP - delta) [+ loss term], p = P^ / lsum        dF = scale (dS + dS^T) F
+// `workspace` is the forward's: it still holds P^ (fp16(P 2^10)), lsum, the row statistics and -- after acan_attention_loss_fused or a
+// forward with a label -- ln(bin), ln Z and T_i.  V and dO are read in place as 16-bit MMA operands (fp16 or bf16, independently);
+// an fp32 grad_ctx is packed to fp16 with a power-of-two scale chosen on the device.  Four tensor-core launches, no P recompute.
+extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                                  const void* feat_h, const void* value, int value_dtype, const float* ctx32,
+                                  const void* grad_ctx, int go_dtype, int have_loss, const float* grad_loss,
+                                  void* grad_feat, int gf_dtype, void* grad_value, int gv_dtype,
+                                  int B, int N, int dk, int dv, float scale, void* stream) {
+  ACAN_CHECK_ARG(workspace && scratch && grad_feat, "acan_attn_bwd_nhwc: null pointer");
+  const bool agg = grad_ctx != nullptr;
+  ACAN_CHECK_ARG(!agg || (value && ctx32 && grad_value), "acan_attn_bwd_nhwc: value, ctx and grad_value are required with grad_ctx");
+  ACAN_CHECK_ARG(agg || have_loss, "acan_attn_bwd_nhwc: nothing to differentiate (no grad_ctx, no loss)");
+  ACAN_CHECK_ARG(!have_loss || grad_loss, "acan_attn_bwd_nhwc: the loss term needs grad_loss (device scalar)");
+  ACAN_CHECK_ARG(!agg || ((value_dtype == DT_F16 || value_dtype == DT_BF16) && (go_dtype == DT_F16 || go_dtype == DT_BF16 || go_dtype == DT_F32)),
+                 "acan_attn_bwd_nhwc: value must be fp16 / bf16, grad_ctx fp16 / bf16 / fp32");
+  auto dt_ok = [](int d) { return d == DT_F32 || d == DT_F16 || d == DT_BF16; };
+  ACAN_CHECK_ARG(dt_ok(gf_dtype) && (!agg || dt_ok(gv_dtype)), "acan_attn_bwd_nhwc: output dtype");
+  if (int e = check_attn_shape("acan_attn_bwd_nhwc", B, N, dk, dv)) return e;
+  ACAN_CHECK_ARG(dv % 64 == 0 && dk % 64 == 0, "acan_attn_bwd_nhwc: dk, dv must be multiples of 64");
+  ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0 && reinterpret_cast<uintptr_t>(scratch) % 1024 == 0,
+                 "acan_attn_bwd_nhwc: workspace and scratch must be 1024-byte aligned");
+  const Workspace w = carve(workspace, B, N, dk, dv);
+  const BwdScratch x = carve_scratch(scratch, B, N, dv);
+  if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_bwd_nhwc: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+  if (scratch_bytes < x.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_bwd_nhwc: scratch %zu < %zu bytes", scratch_bytes, x.bytes);
+  if (int e = acan_device_check()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cg = cta_group();
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  const __half* fh = feat_h ? static_cast<const __half*>(feat_h) : w.fh;
+  const float inv_bn = 1.0f / (static_cast<float>(B) * static_cast<float>(N));
+  const size_t pitchP = static_cast<size_t>(N) * 2, batchP = static_cast<size_t>(N) * N * 2;
+  const size_t pitchV = static_cast<size_t>(dv) * 2, batchV = static_cast<size_t>(N) * dv * 2;
+  const int m_tiles = (N + BM * cg - 1) / (BM * cg);
+  CUtensorMap ta, ta2, tb, to;
+
+  if (agg) {
+    const void* go = grad_ctx;          // the 16-bit operand the GEMMs read
+    bool go_bf16 = go_dtype == DT_BF16;
+    ACAN_CUDA(cudaMemsetAsync(x.amax_bits, 0, 4, st));
+    const int delta_grid = static_cast<int>((rows + 7) / 8);
+    if (go_dtype == DT_F32) {
+      const int64_t n = rows * dv;
+      int64_t blocks = (n / 4 + 255) / 256;
+      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      amax_f32_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const float4*>(grad_ctx), n / 4, x.amax_bits);
+      if (int e = launch_status("amax_f32_kernel")) return e;
+      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 1, nullptr, inv_bn, x.gscale);
+      if (int e = launch_status("gscale4_kernel")) return e;
+      if (int e = cast_launch(static_cast<const float*>(grad_ctx), x.doh, n, x.gscale, st, "pack dO (channels-last fp16)")) return e;
+      go = x.doh; go_bf16 = false;
+      delta_nhwc_kernel<false><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), reinterpret_cast<const float4*>(ctx32), x.delta, nullptr, rows, dv);
+      if (int e = launch_status("delta_nhwc_kernel")) return e;
+    } else {
+      if (go_bf16) delta_nhwc_kernel<true><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), reinterpret_cast<const float4*>(ctx32), x.delta, x.amax_bits, rows, dv);
+      else         delta_nhwc_kernel<false><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), reinterpret_cast<const float4*>(ctx32), x.delta, x.amax_bits, rows, dv);
+      if (int e = launch_status("delta_nhwc_kernel")) return e;
+      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 0, nullptr, inv_bn, x.gscale);
+      if (int e = launch_status("gscale4_kernel")) return e;
+    }
+    const bool vb = value_dtype == DT_BF16;
+    {  // dV[j, c] = 2^-10 / s_op * sum_i P^[i, j] dO[i, c]: A = P^ read MN-major (j contiguous), B = dO in place MN-major (c contiguous)
+      const int bn = choose_bn(dv, B * m_tiles, cg, 64 * cg, 64 * cg);
+      const int ob = gv_dtype == DT_F32 ? 4 : 2;
+      if (int e = make_tmap(&ta, w.p, 2, N, N, B, pitchP, batchP, 64)) return e;
+      if (int e = make_tmap(&tb, go, 2, dv, N, B, pitchV, batchV, 64, go_bf16)) return e;
+      if (int e = make_tmap(&to, grad_value, ob, dv, N, B, static_cast<size_t>(dv) * ob, static_cast<size_t>(N) * dv * ob, BM, gv_dtype == DT_BF16)) return e;
+      GemmArgs g = gemm_args(B, N, dv, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, true, false, go_bf16));
+      g.out_scale = 1.0f / kKeepScale; g.out_gscale = x.gscale + 3;
+      if (int e = launch_rowmajor<1>(ta, tb, to, g, st, cg, gv_dtype)) return e;
+    }
+    {  // dP[i, j] = sum_c dO[i, c] V[j, c]: both operands K-major in place -> dS epilogue, fp16(dS * s_ds) out
+      const int bn = choose_bn(N, B * m_tiles, cg, 64);
+      if (int e = make_tmap(&ta, go, 2, dv, N, B, pitchV, batchV, BM, go_bf16)) return e;
+      if (int e = make_tmap(&tb, value, 2, dv, N, B, pitchV, batchV, bn / cg, vb)) return e;
+      if (int e = make_tmap(&to, x.ds, 2, N, N, B, pitchP, batchP, BM)) return e;
+      GemmArgs g = gemm_args(B, N, N, dv, bn, cg, umma_idesc_f16(bn, BM * cg, false, false, go_bf16, vb));
+      g.ds_new = 1; g.ds_delta = x.delta; g.ds_p = w.p; g.ds_lsum = w.lsum; g.gscale = x.gscale;
+      g.ds_klT = w.klT; g.ds_gl = have_loss ? grad_loss : nullptr; g.ds_inv_bn = inv_bn;
+      g.logbin = have_loss ? w.logbin : nullptr; g.lnz = w.lnz;
+      if (int e = launch_gemm<MODE_DS, 0, false>(ta, tb, to, g, st, cg)) return e;
+    }
+  } else {
+    gscale4_kernel<<<1, 1, 0, st>>>(nullptr, 0, grad_loss, inv_bn, x.gscale);
+    if (int e = launch_status("gscale4_kernel")) return e;
+    kl_ds_kernel<<<static_cast<int>(rows), 256, 0, st>>>(w.p, w.logbin, w.lnz, w.klT, x.ds, grad_loss, inv_bn, x.gscale, N, w.lsum);
+    if (int e = launch_status("kl_ds_kernel")) return e;
+  }
+  {  // dF[i, c] = scale / s_ds * sum_j (dS[i, j] + dS[j, i]) F[j, c]: one launch, the k-loop walks dS K-major then MN-major into the same
+     // accumulator; B = F in place, MN-major (channels contiguous)
+    const int bn = choose_bn(dk, B * m_tiles, cg, 64 * cg, 64 * cg);
+    const int ob = gf_dtype == DT_F32 ? 4 : 2;
+    if (int e = make_tmap(&ta, x.ds, 2, N, N, B, pitchP, batchP, BM)) return e;
+    if (int e = make_tmap(&ta2, x.ds, 2, N, N, B, pitchP, batchP, 64)) return e;
+    if (int e = make_tmap(&tb, fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, 64)) return e;
+    if (int e = make_tmap(&to, grad_feat, ob, dk, N, B, static_cast<size_t>(dk) * ob, static_cast<size_t>(N) * dk * ob, BM, gf_dtype == DT_BF16)) return e;
+    GemmArgs g = gemm_args(B, N, dk, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, false));
+    g.k_half = g.k_steps;
+    g.k_steps *= 2;
+    g.idesc2 = umma_idesc_f16(bn, BM * cg, true, true);
+    g.out_scale = scale; g.out_gscale = x.gscale + 1;
+    if (int e = launch_rowmajor<2>(ta, tb, to, g, st, cg, gf_dtype, &ta2)) return e;
   }
   return 0;
 }

@@ -637,19 +637,25 @@ CoopGrid coop_grid(int64_t M, int C, int rows_per_thread) {
   return best;
 }
 
-// ACAN_BN_PLAIN_LAUNCH=1: launch the single-pass kernels as ordinary grids (experiment).  The grid is still at most one block per SM, so
+// ACAN_BN_PLAIN_LAUNCH=1 (builds with -DACAN_EXPERIMENT only): launch the single-pass kernels as ordinary grids (experiment).  The grid is still at most one block per SM, so
 // every block becomes resident as soon as the kernels ahead of it in the stream drain (nothing that runs later can hold an SM against it)
 // and the barrier's bounded spin still traps instead of hanging; an ordinary launch may start its first blocks under the previous
 // kernel's tail, which a cooperative launch (whole grid resident at once) cannot.
 bool bn_plain_launch() {
+#ifdef ACAN_EXPERIMENT
   static int v = -1;
   if (v < 0) { const char* e = getenv("ACAN_BN_PLAIN_LAUNCH"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
+#else
+  return false;             // the shipped library never reads the environment
+#endif
 }
 
 bool bn_use_coop(int C) {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ACAN_BN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }
+  int v = 1;
+#ifdef ACAN_EXPERIMENT
+  { const char* e = getenv("ACAN_BN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }
+#endif
   return v == 1 && (C + kBnSlab - 1) / kBnSlab <= kNumSMs && 2 * ((C + kBnSlab - 1) / kBnSlab) <= kBnCounterSlots;   // the 32-group candidate always fits then
 }
 

@@ -279,9 +279,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
 }
 
 // kind::f16 instruction descriptor: fp16 (or bf16) A/B, fp32 accumulate, M = m, N = n; each operand K-major or MN-major
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128, bool b_mn_major = false, bool a_mn_major = false, bool bf16 = false) {
+// (the two operand formats are independent descriptor fields: an fp16 A with a bf16 B is one legal kind::f16 instruction)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128, bool b_mn_major = false, bool a_mn_major = false, bool a_bf16 = false, bool b_bf16 = false) {
   return (1u << 4)                                         // c_format = F32
-       | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) // a_format = b_format = F16 (0) / BF16 (1)
+       | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) // a_format, b_format: F16 (0) / BF16 (1)
        | ((a_mn_major ? 1u : 0u) << 15)                    // a_major
        | ((b_mn_major ? 1u : 0u) << 16)                    // b_major
        | (static_cast<uint32_t>(n >> 3) << 17)             // n_dim

@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(1024) ordered_sum_kernel(const float* __restri
 using namespace acan;
 
 static int check_hw(const char* who, int B, int H, int W) {
-  if (B <= 0 || H < 8 || W < 8) return fail(ACAN_ERR_BAD_ARG, "%s: B=%d H=%d W=%d invalid (need H, W >= 8)", who, B, H, W);
+  // the kernels read label pixel (8 i, 8 j): F.interpolate(mode='nearest') to (H//8, W//8) picks exactly that one only when H and W
+  // are multiples of 8 (otherwise its source index is floor(i * H / (H//8))); the network itself needs multiples of 8 (README.md:52)
+  if (B <= 0 || H < 8 || W < 8 || (H % 8) != 0 || (W % 8) != 0)
+    return fail(ACAN_ERR_BAD_ARG, "%s: B=%d H=%d W=%d invalid (need H, W positive multiples of 8)", who, B, H, W);
   return 0;
 }
 

@@ -9,6 +9,7 @@
 //           shuffle reduction, optional keep-mask * 2.  Kernel 2/3: one warp per output neuron, the
 //           weight row is read once (coalesced 16 B loads) and dotted with all B inputs.
 #include "common.cuh"
+#include <atomic>
 #include <cuda_bf16.h>
 
 namespace acan {
@@ -108,10 +109,13 @@ __global__ void __launch_bounds__(128) linear_relu_kernel(const float* __restric
 template <int NI>
 int launch_linear_smem(const float* in, const float* W, const float* bias, float* out, int B, int O, cudaStream_t st, const char* what) {
   const size_t smem = static_cast<size_t>(B < kLinImages ? B : kLinImages) * NI * 128 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_done{0};                 // the opt-in is per device: one bit per device ordinal
+  int dev = 0;
+  ACAN_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     ACAN_CUDA(cudaFuncSetAttribute(linear_relu_smem_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinImages * NI * 128 * 4));
-    attr_set = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   linear_relu_smem_kernel<NI><<<(O + kLinWarps - 1) / kLinWarps, kLinWarps * 32, smem, st>>>(in, W, bias, out, B, O);
   return launch_status(what);

@@ -177,13 +177,64 @@ def _softmax_backward(p: torch.Tensor, dp: torch.Tensor) -> torch.Tensor:
 
 
 class Attention(torch.autograd.Function):
-    """ctx = aggregate(softmax(F^T F / sqrt(dk)), V) and, optionally, the fused attention loss.
+    """context = aggregate(softmax(F^T F / sqrt(dk)), V) on the channels-last tensor-core path (acan_attn_fwd_nhwc, keep = 1).
 
-    forward(feat [B,dk,h,w], value [B,dv,h,w], dis_label [B,1,H,W] | None, holder)
-      -> (context [B,dv,h,w], loss 0-dim (0 when no label))
-    ``holder`` is a python object that receives ``.ws`` (operand pack / statistics) for lazy sim_map access.
-    backward: acan_attn_bwd (tcgen05: dV, dP -> dS with the loss term fused, dF).
+    forward(feat [B,dk,h,w], value [B,dv,h,w], holder) -> (context [B,dv,h,w] in value's dtype, token 0-dim)
+    ``holder`` receives ``.ws`` (this forward's workspace: operand pack, statistics, probabilities) for lazy sim_map access.
+    ``token`` ties the attention loss into this node: ``AttentionLossOnToken`` (built by the drop-in AttentionLoss2d from the lazy
+    sim_map) runs the fused loss kernel forward and, in backward, only parks its upstream gradient in the workspace; since the token
+    is an output of this node, autograd runs this node's backward afterwards, and ONE acan_attn_bwd_nhwc call differentiates the
+    aggregation and the loss together (dV, dP -> dS with the loss term in its epilogue, dF).  Unused outputs arrive as None.
     """
+
+    @staticmethod
+    def forward(ctx, feat, value, holder):
+        out = ops.attention_forward_train(feat, value)
+        ws = out["ws"]
+        holder.ws, holder.row_stats = ws, out["row_stats"]
+        holder.gen = getattr(holder, "gen", 0) + 1
+        ctx.ws, ctx.feat_dtype, ctx.value_dtype = ws, feat.dtype, value.dtype
+        ctx.save_for_backward(out["value16"], out["ctx32"])
+        ctx.set_materialize_grads(False)
+        o = out["ctx32"]
+        if value.dtype in (torch.float16, torch.bfloat16):
+            o = o.to(value.dtype)
+        token = torch.zeros((), device=feat.device, dtype=torch.float32)
+        return o.permute(0, 3, 1, 2), token
+
+    @staticmethod
+    def backward(ctx, grad_ctx, grad_token):
+        value16, ctx32 = ctx.saved_tensors
+        ws = ctx.ws
+        grad_loss = ws.pending_loss_grad if grad_token is not None else None
+        ws.pending_loss_grad = None
+        if grad_ctx is None and grad_loss is None:
+            return None, None, None
+        gf, gv = ops.attention_backward_cl(ws, value16, ctx32, grad_ctx, grad_loss, ctx.feat_dtype, ctx.value_dtype)
+        return gf.permute(0, 3, 1, 2), (gv.permute(0, 3, 1, 2) if gv is not None else None), None
+
+
+class AttentionLossOnToken(torch.autograd.Function):
+    """AttentionLoss2d.forward (losses.py:54-62) for the lazy sim_map of an ``Attention`` node: the value comes from the fused
+    tensor-core KL over that forward's workspace (which also leaves the target statistics there); the gradient is delivered by
+    ``Attention.backward`` (see there)."""
+
+    @staticmethod
+    def forward(ctx, token, dis_label, ws):
+        ctx.ws = ws
+        loss = ops.attention_loss_fused(ws, dis_label)
+        ws.has_target = True
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.ws.pending_loss_grad = grad_out
+        return torch.zeros((), device=grad_out.device, dtype=torch.float32), None, None
+
+
+class AttentionLegacy(torch.autograd.Function):
+    """The same through the fp32-NCHW C ABI (acan_attn_fwd / acan_attn_bwd): kept for callers that hold fp32 NCHW tensors and want
+    fp32 NCHW results without any layout change, and as the A/B partner of the channels-last path in the tests."""
 
     @staticmethod
     def forward(ctx, feat, value, dis_label, holder):

@@ -33,18 +33,22 @@ class LazySimMap:
     ``functions.SimMap`` -- with autograd back to F.
     """
 
-    def __init__(self, feat: torch.Tensor, holder, batch_slice: Optional[slice] = None, to_cpu: bool = False, gen: Optional[int] = None):
+    def __init__(self, feat: torch.Tensor, holder, batch_slice: Optional[slice] = None, to_cpu: bool = False, gen: Optional[int] = None,
+                 token: Optional[torch.Tensor] = None, ws=None):
         self._feat = feat
         self._holder = holder
         self._gen = holder.gen if gen is None else gen
         self._slice = batch_slice
         self._cpu = to_cpu
         self._dense = None
-        self._own_ws = None
+        self._own_ws = ws          # training forwards own their workspace (it outlives later forwards of the module)
+        self._token = token        # output of the fn.Attention node this sim_map belongs to (ties the attention loss into its backward)
 
     def _ws(self):
         """operand pack + row statistics for THIS forward: the module's workspace if it still belongs to it,
         otherwise (the module ran again since) a private re-pack."""
+        if self._own_ws is not None:
+            return self._own_ws
         if self._holder.gen == self._gen and self._holder.ws is not None:
             return self._holder.ws
         if self._own_ws is None:
@@ -79,13 +83,13 @@ class LazySimMap:
         return self._feat.requires_grad
 
     def cpu(self):
-        return LazySimMap(self._feat, self._holder, self._slice, True, self._gen)
+        return LazySimMap(self._feat, self._holder, self._slice, True, self._gen, self._token, self._own_ws)
 
     def cuda(self, *a, **k):
-        return LazySimMap(self._feat, self._holder, self._slice, False, self._gen)
+        return LazySimMap(self._feat, self._holder, self._slice, False, self._gen, self._token, self._own_ws)
 
     def detach(self):
-        return LazySimMap(self._feat.detach(), self._holder, self._slice, self._cpu, self._gen)
+        return LazySimMap(self._feat.detach(), self._holder, self._slice, self._cpu, self._gen, None, self._own_ws)
 
     def materialize(self) -> torch.Tensor:
         if self._dense is None:
@@ -98,6 +102,10 @@ class LazySimMap:
     def rows(self, points) -> torch.Tensor:
         """sim_map[:, points] -> [B, len(points), N] via the selected-rows kernel (no N x N tensor)."""
         idx = torch.as_tensor(points, dtype=torch.int64).reshape(-1)
+        n = int(self.shape[1])
+        if idx.numel() == 0 or int(idx.min()) < -n or int(idx.max()) >= n:
+            raise IndexError(f"sim_map row index out of range for N={n}")
+        idx = idx % n                                       # python-style negative indices
         out = ops.attention_rows(self._ws(), idx)
         if self._slice is not None:
             out = out[self._slice]
@@ -106,7 +114,7 @@ class LazySimMap:
     def __getitem__(self, key):
         if isinstance(key, slice):
             if self._slice is None:
-                return LazySimMap(self._feat, self._holder, key, self._cpu, self._gen)
+                return LazySimMap(self._feat, self._holder, key, self._cpu, self._gen, self._token, self._own_ws)
         elif isinstance(key, tuple) and len(key) == 2 and key[0] == slice(None) and not isinstance(key[1], slice):
             k1 = key[1]
             if isinstance(k1, int):
@@ -280,10 +288,19 @@ class LazyLogitsProb:
 
 
 class _Holder:
-    """per-module slot for the attention workspace of the latest forward (operand pack, row statistics)."""
-    ws = None
-    row_stats = None
-    gen = 0
+    """per-module slot for the attention workspace of the latest forward (operand pack, row statistics).  Inference workspaces are
+    pooled by shape and never dropped while the module lives: a captured CUDA graph (GraphedPredictor) holds their raw addresses, and an
+    eager forward with another batch size in between (the validation loop's last batch, test-time augmentation) must not free them."""
+
+    def __init__(self):
+        self.ws = None
+        self.row_stats = None
+        self.gen = 0
+        self.pool = {}
+
+    def pooled(self, shape, device):
+        ws = self.pool.get((shape, device))
+        return ws
 
 
 class Reshape(nn.Module):
@@ -367,10 +384,12 @@ class SelfAttentionBlock_(PixelAttentionBlock_):
         self.lazy_sim_map = True      # False: always materialise sim_map like the reference does
 
     def forward(self, x):
-        feat = self.key_features(x).float()
-        value = self.f_value(x).float()
-        context, _ = fn.Attention.apply(feat, value, None, self._holder)
-        sim_map = LazySimMap(feat, self._holder)
+        # F and V go to the channels-last tensor-core path as the projections left them: 16-bit channels_last tensors (the autocast
+        # training step) are read in place, fp32 NCHW tensors (the reference's own dtype) take one cast + transpose copy each
+        feat = self.key_features(x)
+        value = self.f_value(x)
+        context, token = fn.Attention.apply(feat, value, self._holder)
+        sim_map = LazySimMap(feat, self._holder, token=token, ws=self._holder.ws)
         if not self.lazy_sim_map:
             sim_map = sim_map.materialize()
         return [context, sim_map]
@@ -426,7 +445,9 @@ class SADecoder(nn.Module):
             with torch.autocast("cuda", dtype=torch.float16):
                 feat = sa.key_features(x)
                 value = sa.f_value(x)
-        out = ops.attention_forward_cl(feat, value, ws=sa._holder.ws)
+        shape_key = ((feat.shape[0], feat.shape[2] * feat.shape[3], feat.shape[1], value.shape[1]), feat.device)
+        out = ops.attention_forward_cl(feat, value, ws=sa._holder.pool.get(shape_key))
+        sa._holder.pool[shape_key] = out["ws"]
         sa._holder.ws = out["ws"]
         sa._holder.row_stats = out["row_stats"]
         sa._holder.gen += 1
@@ -497,6 +518,9 @@ class AttentionLoss2d(nn.Module):
 
     def forward(self, sim_map, label):
         if isinstance(sim_map, LazySimMap):
+            if sim_map._token is not None and sim_map._own_ws is not None and sim_map._slice is None:
+                # training: value from the fused KL over that forward's workspace, gradient through the fn.Attention node it belongs to
+                return fn.AttentionLossOnToken.apply(sim_map._token, label, sim_map._own_ws)
             return FusedAttentionLoss.apply(sim_map._feat, label, sim_map)
         return fn.AttentionLossMaterialised.apply(sim_map, label)
 

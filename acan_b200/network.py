@@ -165,16 +165,26 @@ class ResNet(BaseClassificationModel_):
         return nn.Sequential(*units)
 
     def encode(self, x):
+        """(layer3 output, layer4 output).  With the auxiliary branch in train() the reference runs ``interout`` -- whose first
+        module is Dropout2d(0.2, inplace=True) -- BEFORE layer4 (model.py:216-222), so layer4 sees the dropped features.  Same here,
+        but the dropout is applied out of place: layer3's output is saved by the ReLU / BatchNorm that produced it, and an in-place
+        multiply on it makes autograd refuse the backward pass ("modified by an inplace operation")."""
         x = self.maxpool(fn.bn_act(self.bn1, self.conv1(x), relu=True))
         x = self.layer3(self.layer2(self.layer1(x)))
+        if getattr(self, "use_inter", False) and self.interout is not None:
+            d = self.interout.dropout1
+            if d.training and d.p > 0:
+                x = torch.nn.functional.dropout2d(x, d.p, True, False)
         return x, self.layer4(x)
 
-    def _inter_logits(self, mid):
-        """the auxiliary branch up to (not including) its x8 upsampling: stride-8 logits (model.py:113-121)"""
+    def _inter_logits(self, mid, with_upsample=False):
+        """the auxiliary branch on ``mid`` = encode()[0] (its leading dropout already applied there) up to -- or, with_upsample,
+        including -- its x8 upsampling (model.py:113-121)"""
         t = mid
         for name, m in self.interout.named_children():
-            if name != "upsample":
-                t = m(t)
+            if name == "dropout1" or (name == "upsample" and not with_upsample):
+                continue
+            t = m(t)
         return t
 
     def forward(self, x):
@@ -189,7 +199,7 @@ class ResNet(BaseClassificationModel_):
                 z_inter = self._inter_logits(mid)
                 inter_y = LazyLogitsProb(None, z_inter.shape[1] // 2, z=z_inter, upsample=self.interout.upsample)
             else:
-                inter_y = self.interout(mid)
+                inter_y = self._inter_logits(mid, with_upsample=True)
         sim_map = None
         if self.decoderType == "attention":
             x, sim_map = self.decoder(x)
@@ -258,13 +268,15 @@ class OrdinalRegression2d(nn.Module):
     training-mode 'y' handle it runs the fused decode_ord + loss kernels (SURVEY §8f row f-2, acan_ordinal_loss_fwd/bwd);
     given a dense probability tensor it is the plain torch restatement."""
 
-    def __init__(self, ignore_index=0, reduction="sum", use_weights=False, weight=None):
+    def __init__(self, ignore_index=None, reduction="sum", use_weights=False, weight=None):      # defaults as losses.py:144-145
         super().__init__()
         if use_weights or reduction != "sum":
             raise NotImplementedError("only the reference's default OrdinalRegression2d configuration is mirrored")
         self.ignore_index = ignore_index
 
     def forward(self, pred, label):
+        if self.ignore_index is None:
+            self.ignore_index = pred.shape[1] + 1                  # as the reference (losses.py:131-132)
         if isinstance(pred, LazyLogitsProb) and pred.z is not None:
             return fn.FusedTailLoss.apply(pred.z, label, self.ignore_index)              # fused with the x8 upsampling and decode_ord
         if isinstance(pred, LazyLogitsProb) and pred.shape[2] * pred.shape[3] % 4 == 0:

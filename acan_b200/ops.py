@@ -168,6 +168,7 @@ def tail_loss_backward(z_nhwc: torch.Tensor, label: torch.Tensor, count: torch.T
 # ------------------------------------------------------------------------------------ training-mode BN (+ ReLU, + residual)
 
 _BN_WS = {}          # (device index, stream) -> zero-initialised scratch (arrival counters + partials), grown on demand
+_BN_WS_RETIRED = []  # outgrown buffers stay alive: a captured CUDA graph may still hold their address
 
 
 def _bn_ws(device: torch.device, c: int) -> torch.Tensor:
@@ -175,6 +176,8 @@ def _bn_ws(device: torch.device, c: int) -> torch.Tensor:
     need = int(_lib.load().acan_bn_ws_floats(c))
     t = _BN_WS.get(key)
     if t is None or t.numel() < need:
+        if t is not None:
+            _BN_WS_RETIRED.append(t)
         t = torch.zeros(max(need, int(_lib.load().acan_bn_ws_floats(2048))), device=device, dtype=torch.float32)
         _BN_WS[key] = t
     return t
@@ -309,6 +312,8 @@ class AttnWorkspace:
         self.ptr = (base + 1023) // 1024 * 1024
         self.scale = None
         self.feat_pack = None     # channels-last fp16 F of the last forward when it was consumed in place (kept alive here)
+        self.has_target = False   # ln(bin) / ln Z / T_i of an attention-loss forward are in the workspace
+        self.pending_loss_grad = None   # upstream gradient of the attention loss, parked here by its autograd node for the fused backward
 
 
 def attention_forward(feat: torch.Tensor, value: Optional[torch.Tensor], want_sim_map: bool = False,
@@ -379,7 +384,79 @@ def attention_forward_cl(feat: torch.Tensor, value: Optional[torch.Tensor], want
     return {"ctx": ctx.permute(0, 3, 1, 2) if ctx is not None else None, "sim_map": sim, "row_stats": stats, "loss": loss, "ws": ws}
 
 
-_bwd_scratch = {}
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _nhwc_dense(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """[B,C,h,w] (any layout) -> dense [B,h,w,C] in `dtype` (default: its own); a view when it already is, else ONE cast + transpose copy."""
+    v = t.permute(0, 2, 3, 1)
+    if (dtype is None or v.dtype == dtype) and v.is_contiguous():
+        return v
+    out = torch.empty(v.shape, device=t.device, dtype=dtype or t.dtype)
+    out.copy_(v)
+    return out
+
+
+def attention_forward_train(feat: torch.Tensor, value: torch.Tensor, dis_label: Optional[torch.Tensor] = None):
+    """Training-mode attention (acan_attn_fwd_nhwc, keep = 1) on whatever the projections produced:
+      feat  [B,dk,h,w]  fp16 channels_last is read in place; bf16 / fp32 take one pass into the workspace's fp16 pack
+      value [B,dv,h,w]  fp16 / bf16 channels_last is read in place (bf16 stays bf16: mixed-format MMA); fp32 is rounded to fp16
+    Returns dict(ctx32 [B,h,w,dv] fp32, row_stats, loss | None, ws, feat_pack [B,h,w,dk] fp16 | None, value16 [B,h,w,dv]).
+    The workspace is NEW for every call and belongs to the caller's autograd node: it keeps the probabilities for the backward pass."""
+    if not (feat.is_cuda and value.is_cuda):
+        raise _lib.AcanLibraryError("attention inputs must be CUDA tensors: acan_b200 has no CPU path")
+    b, dk, h, w = feat.shape
+    dv = value.shape[1]
+    n = h * w
+    f = _nhwc_dense(feat.detach(), None if feat.dtype in (torch.float16, torch.bfloat16) else torch.float16)
+    v = _nhwc_dense(value.detach(), value.dtype if value.dtype in (torch.float16, torch.bfloat16) else torch.float16)
+    ws = AttnWorkspace(b, n, dk, dv, f.device)
+    ws.scale = float(dk) ** -0.5
+    ctx32 = torch.empty((b, h, w, dv), device=f.device, dtype=torch.float32)
+    stats = torch.empty((b, n, 2), device=f.device, dtype=torch.float32)
+    lab = _cuda_f32(dis_label, "dis_label") if dis_label is not None else None
+    hh, ww = (lab.shape[-2:] if lab is not None else (0, 0))
+    loss = torch.empty((), device=f.device, dtype=torch.float32) if lab is not None else None
+    with torch.cuda.device(f.device):
+        _lib.check(_lib.load().acan_attn_fwd_nhwc(f.data_ptr(), _DT[f.dtype], v.data_ptr(), _DT[v.dtype], ctx32.data_ptr(), 0, 0, stats.data_ptr(),
+                                                  _lib.ptr(lab), hh, ww, _lib.ptr(loss), ws.ptr, ws.bytes, b, n, dk, dv, ws.scale, 1, _lib.current_stream()),
+                   "acan_attn_fwd_nhwc")
+    ws.feat_pack = f if f.dtype == torch.float16 else None      # None: the fp16 pack lives in the workspace
+    ws.has_target = lab is not None
+    return {"ctx32": ctx32, "row_stats": stats, "loss": loss, "ws": ws, "feat_pack": ws.feat_pack, "value16": v}
+
+
+_bwd_scratch = {}          # (device, bytes) -> buffer; entries are never dropped (captured CUDA graphs hold their addresses)
+
+
+def attention_backward_cl(ws: "AttnWorkspace", value16: torch.Tensor, ctx32: torch.Tensor, grad_ctx: Optional[torch.Tensor],
+                          grad_loss: Optional[torch.Tensor], gf_dtype: torch.dtype, gv_dtype: torch.dtype):
+    """(grad_feat [B,h,w,dk], grad_value [B,h,w,dv] | None) from acan_attn_bwd_nhwc.  `ws`: the forward's workspace (probabilities, row sums;
+    target statistics if the attention loss ran on it).  grad_ctx [B,dv,h,w] any layout: 16-bit channels_last is read in place.
+    grad_loss: 0-dim CUDA tensor (upstream gradient of the attention loss) or None."""
+    b, n, dk, dv = ws.shape
+    dev = ws._buf.device
+    hh, wd = ctx32.shape[1], ctx32.shape[2]
+    agg = grad_ctx is not None
+    go = None
+    if agg:
+        go = _nhwc_dense(grad_ctx.detach(), grad_ctx.dtype if grad_ctx.dtype in _DT else torch.float32)
+    lib = _lib.load()
+    nbytes = int(lib.acan_attn_bwd_nhwc_scratch_bytes(b, n, dk, dv))
+    key = (dev, nbytes)
+    buf = _bwd_scratch.get(key)
+    if buf is None:
+        buf = _bwd_scratch[key] = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
+    sptr = (buf.data_ptr() + 1023) // 1024 * 1024
+    gf = torch.empty((b, hh, wd, dk), device=dev, dtype=gf_dtype)
+    gv = torch.empty((b, hh, wd, dv), device=dev, dtype=gv_dtype) if agg else None
+    gl = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1) if grad_loss is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.acan_attn_bwd_nhwc(ws.ptr, ws.bytes, sptr, nbytes, _lib.ptr(ws.feat_pack), _lib.ptr(value16) if agg else 0,
+                                          _DT[value16.dtype] if agg else 1, _lib.ptr(ctx32) if agg else 0, _lib.ptr(go), _DT[go.dtype] if agg else 1,
+                                          int(gl is not None), _lib.ptr(gl), gf.data_ptr(), _DT[gf_dtype], _lib.ptr(gv), _DT[gv_dtype],
+                                          b, n, dk, dv, ws.scale, _lib.current_stream()), "acan_attn_bwd_nhwc")
+    return gf, gv
 
 
 def attention_backward(feat: torch.Tensor, row_stats: torch.Tensor, value: Optional[torch.Tensor] = None,
@@ -401,8 +478,7 @@ def attention_backward(feat: torch.Tensor, row_stats: torch.Tensor, value: Optio
     lib = _lib.load()
     nbytes = int(lib.acan_attn_bwd_workspace_bytes(b, n, dk, dv))
     key = (f.device, nbytes)
-    if key not in _bwd_scratch:                      # one scratch buffer per (device, size), reused across steps
-        _bwd_scratch.clear()
+    if key not in _bwd_scratch:                      # one scratch buffer per (device, size), reused across steps, never dropped
         _bwd_scratch[key] = torch.empty(nbytes + 1024, device=f.device, dtype=torch.uint8)
     buf = _bwd_scratch[key]
     ptr = (buf.data_ptr() + 1023) // 1024 * 1024

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ACAN_ABI_VERSION 2
+#define ACAN_ABI_VERSION 3
 
 #define ACAN_ERR_BAD_ARG     10001   /* null pointer, non-positive size, unsupported shape */
 #define ACAN_ERR_WORKSPACE   10002   /* workspace smaller than *_workspace_bytes() */
@@ -232,6 +232,43 @@ int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h,
                            void* workspace, size_t workspace_bytes,
                            int B, int N, int dk, int dv, float scale, void* stream);
 
+/* General channels-last form (the training step's entry; acan_attn_fwd_nhwc_f16 is this call with fp16 everywhere and keep = 0).
+ * Element types (ACAN_DT_*): feat fp16 (read in place), bf16 or fp32 (one elementwise pass into the workspace's fp16 pack);
+ * value fp16 or bf16, read in place (the two operand formats of a kind::f16 MMA are independent: fp16 probabilities x bf16 values
+ * is one instruction); ctx fp16, bf16 or fp32.
+ *   keep = 0  inference: statistics-free probability pass when neither sim_map nor the loss is requested.
+ *   keep = 1  training (autograd through sadecoder.py:42-49, 80-90): exact two-pass row statistics; the normalised probabilities stay
+ *             in the workspace as fp16(P * 2^10) together with the row sums of those rounded values, which is the divisor used by
+ *             the aggregation here and by acan_attn_bwd_nhwc -- the rows the tensor cores read then sum to exactly 1, which is what
+ *             keeps the softmax-backward cancellation (sum_j dS_ij = 0) intact in 16-bit operands.  Ask for ctx in fp32 when a
+ *             backward pass follows: delta_i = sum_c dO_ic O_ic needs the unrounded aggregation output. */
+#define ACAN_DT_F32  0
+#define ACAN_DT_F16  1
+#define ACAN_DT_BF16 2
+int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* value, int value_dtype, void* ctx, int ctx_dtype,
+                       float* sim_map, float* row_stats, const float* dis_label, int H, int W, float* loss_out,
+                       void* workspace, size_t workspace_bytes, int B, int N, int dk, int dv, float scale, int keep, void* stream);
+
+/* Backward of acan_attn_fwd_nhwc(keep = 1), channels-last, four tensor-core launches and no recomputation of P:
+ *   dV = P^T dO      dP = dO V^T      dS = p o (dP - delta_i) - g/(B N) (W o [clamp window] - p T_i)      dF = scale (dS + dS^T) F
+ *   workspace   the FORWARD's workspace, untouched since: probabilities, their row sums, row statistics; with have_loss also what
+ *               acan_attention_loss_fused (or a forward with a label) left there: ln(bin), ln Z, the in-window target mass T_i
+ *   scratch     acan_attn_bwd_nhwc_scratch_bytes(), 1024-byte aligned (dS, an fp16 pack of an fp32 grad_ctx, delta, scales)
+ *   feat_h      [B,N,dk] fp16 as given to the forward (NULL: the workspace pack, when the forward converted bf16 / fp32 features)
+ *   value       [B,N,dv] fp16 / bf16 as given to the forward, ctx32 [B,N,dv] fp32 the forward's output
+ *   grad_ctx    [B,N,dv] fp16 / bf16 (read in place as an MMA operand) or fp32 (packed to fp16 with a power-of-two scale chosen on
+ *               the device); NULL when only the attention loss is differentiated
+ *   have_loss   adds *grad_loss (DEVICE scalar) * d(attention loss)/dF
+ *   grad_feat   [B,N,dk], grad_value [B,N,dv]; fp32 / fp16 / bf16 each.
+ * delta_i is computed from the very operand the dP GEMM reads and dS is formed with p = P^/lsum, so sum_j dS_ij = 0 holds for the
+ * values the tensor cores see; measured gradient error vs fp64 autograd <= 5e-4 (max-norm relative) at the reference's channel counts. */
+size_t acan_attn_bwd_nhwc_scratch_bytes(int B, int N, int dk, int dv);
+int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                       const void* feat_h, const void* value, int value_dtype, const float* ctx32,
+                       const void* grad_ctx, int go_dtype, int have_loss, const float* grad_loss,
+                       void* grad_feat, int gf_dtype, void* grad_value, int gv_dtype,
+                       int B, int N, int dk, int dv, float scale, void* stream);
+
 /* Selected rows of sim_map (vis_utils.py:107-121 reads rows N/4, N/2, 3N/4 only):
  *   rows_out [B, n_rows, N] fp32 for row indices row_idx[0..n_rows) (int32, device).
  * Needs the workspace left by a preceding forward with the same (B, N, dk, dv); feat_pack = NULL after
@@ -257,7 +294,8 @@ int acan_gt_sim_map(const float* dis_label, float* gt, float* bins_ws, int B, in
 /* Fused, streamed form on its own: the loss straight from the fp16 operand pack and row statistics an
  * acan_attn_fwd call left in `workspace` -- sim_map is recomputed tile by tile on the tensor cores and
  * never touches HBM.  Same value as acan_attention_loss(sim_map) up to fp16-operand rounding of S.
- * feat_pack: as for acan_attn_rows. */
+ * feat_pack: as for acan_attn_rows.  Also leaves ln(bin), ln Z and the in-window target mass T_i in the workspace
+ * (what acan_attn_bwd_nhwc(have_loss = 1) reads). */
 int acan_attention_loss_fused(void* workspace, const void* feat_pack, const float* dis_label, float* loss_out,
                               int B, int H, int W, int dk, int dv, float scale, void* stream);
 

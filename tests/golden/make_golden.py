@@ -102,6 +102,23 @@ def golden_sab_small():
          nbt_after=after["f_key.bn.num_batches_tracked"])
 
 
+def golden_sab_train():
+    """train()-mode SelfAttentionBlock_ at a size the tensor-core kernels take (dk = 64, dv = 128, N = 24): context, sim_map and the
+    f_key BatchNorm buffers after ONE forward -- the reference calls the shared f_key / f_query module twice (sadecoder.py:44-45), so
+    the running statistics take two momentum steps and num_batches_tracked ends at 2."""
+    blk = SelfAttentionBlock_(64, 64, 128)
+    sd = synth.fill_state_dict(blk.state_dict())
+    blk.load_state_dict(sd)
+    x = synth.feature_map("sabt.x", 2, 64, 4, 6)
+    blk.train()
+    with torch.no_grad():
+        ctx_t, sim_t = blk(x)
+    after = blk.state_dict()
+    save("sab_train", keys=np.array(list(sd.keys())), shapes=np.array([str(tuple(v.shape)) for v in sd.values()]),
+         ctx_train=ctx_t, sim_train=sim_t, rm_after=after["f_key.bn.running_mean"], rv_after=after["f_key.bn.running_var"],
+         nbt_after=after["f_key.bn.num_batches_tracked"], rm_q_after=after["f_query.bn.running_mean"])
+
+
 def golden_sadecoder():
     for name, (hh, ww, b) in (("sadecoder_24", (32, 48, 2)), ("sadecoder_1064", (224, 304, 1))):
         dec = SADecoder(height=hh, width=ww)
@@ -244,6 +261,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "eval":          # python tests/golden/make_golden.py eval  -> only the row f-4 fixtures
         golden_eval()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sabt":          # ... sabt -> only the train-mode SelfAttentionBlock_ fixture
+        golden_sab_train()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ce":            # ... ce -> only the CrossEntropy2d fixtures (row f-2)
         golden_ce_loss()
         sys.exit(0)
@@ -251,6 +271,7 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     golden_head()
     golden_sab_small()
+    golden_sab_train()
     golden_attention_loss()
     golden_sadecoder()
     golden_resnet_tiny()

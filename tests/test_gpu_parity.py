@@ -456,33 +456,110 @@ def test_attention_full_size_properties():
     assert torch.equal(out3["ctx"], fast["ctx"][perm])                            # images are independent units
 
 
-@pytest.mark.parametrize("b,h,w,dk,dv,tol", [(2, 4, 6, 128, 256, 5e-3), (1, 28, 38, 512, 2048, 2e-3), (2, 16, 16, 512, 2048, 2e-3)])
-def test_attention_backward_against_oracle_autograd(b, h, w, dk, dv, tol):
-    """tcgen05 backward (acan_attn_bwd: dV, dP -> dS with the loss term, dF) vs fp64 autograd through the oracle.  Every
-    tensor-core operand is fp16 (11 bits): the chain P, dO, V, dS, F rounds five times, 2e-3 max-norm at the real channel
-    counts, 5e-3 at the toy sizes where the dot products are too short to average the rounding down."""
+GRAD_TOL = 1e-3      # north-star tolerance, now held by the gradients too (channels-last path)
+
+
+def _train_inputs(b, h, w, dk, dv, f_dtype, v_dtype, tag="bw"):
+    """16-bit-representable operands (what the autocast training step hands over): the oracle sees exactly the same values."""
+    f = synth.feature_map(f"{tag}.f.{h}.{dk}", b, dk, h, w).to(f_dtype).float()
+    v = synth.feature_map(f"{tag}.v.{h}.{dv}", b, dv, h, w).to(v_dtype).float()
+    go = (synth.randn(f"{tag}.go.{h}.{dv}", b, dv, h, w) * 1e-3).to(v_dtype).float()   # small upstream gradient: exercises the dS range scaling
+    dis = O.continuous2discrete(synth.depth_label(f"{tag}.lab.{h}", b, h * 8, w * 8, 0.5, 10.5), *NYU)
+    return f, v, go, dis
+
+
+def _oracle_grads(f, v, go, dis, gl):
+    fc, vc = f.double().requires_grad_(True), v.double().requires_grad_(True)
+    sim = O.affinity(fc)
+    ctx = O.aggregate(sim, vc)
+    tot = (ctx * go.double()).sum() if go is not None else 0.0
+    if gl:
+        tot = tot + gl * O.attention_loss(sim, dis.double())
+    tot.backward()
+    return ctx.detach(), fc.grad, vc.grad
+
+
+@pytest.mark.parametrize("v_dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("b,h,w,dk,dv", [(2, 4, 6, 128, 256), (1, 28, 38, 512, 2048), (2, 16, 16, 512, 2048), (1, 32, 44, 512, 2048)])
+def test_attention_training_path_against_oracle_autograd(b, h, w, dk, dv, v_dtype):
+    """Channels-last training path (acan_attn_fwd_nhwc keep=1 + acan_attention_loss_fused + acan_attn_bwd_nhwc), operands read in place
+    (fp16 F, bf16 or fp16 V / dO: the bf16 case is a mixed-format MMA against the fp16 probabilities), vs fp64 autograd through the
+    oracle on the same values: context and all gradients <= 1e-3 max-norm relative, at the reference's channel counts and at a toy size."""
+    from acan_b200 import functions as fn
+    from acan_b200.modules import AttentionLoss2d, LazySimMap, _Holder
+    f, v, go, dis = _train_inputs(b, h, w, dk, dv, torch.float16, v_dtype)
+    cl = torch.channels_last
+    for gl, use_ctx in ((0.7, True), (0.0, True), (0.7, False)):
+        fd = f.to(DEV).half().contiguous(memory_format=cl).requires_grad_(True)
+        vd = v.to(DEV).to(v_dtype).contiguous(memory_format=cl).requires_grad_(True)
+        holder = _Holder()
+        ctx, token = fn.Attention.apply(fd, vd, holder)
+        assert ctx.dtype == v_dtype and ctx.permute(0, 2, 3, 1).is_contiguous()
+        tot = 0.0
+        if use_ctx:
+            tot = (ctx.float() * go.to(DEV)).sum()
+        if gl:
+            tot = tot + gl * AttentionLoss2d()(LazySimMap(fd, holder, token=token, ws=holder.ws), dis.to(DEV))
+        tot.backward()
+        want_ctx, want_gf, want_gv = _oracle_grads(f, v, go if use_ctx else None, dis, gl)
+        close(ctx.float(), want_ctx, 4.5e-3 if v_dtype == torch.bfloat16 else TOL)        # the 16-bit copy handed to the network (bf16: 2^-9 rounding)
+        assert fd.grad.dtype == torch.float16 and fd.grad.permute(0, 2, 3, 1).is_contiguous()
+        close(fd.grad, want_gf, GRAD_TOL)
+        if use_ctx:
+            close(vd.grad, want_gv, 4.5e-3 if v_dtype == torch.bfloat16 else GRAD_TOL)       # returned in V's dtype
+        else:
+            assert vd.grad is None
+
+
+@pytest.mark.parametrize("b,h,w,dk,dv", [(2, 4, 6, 128, 256), (1, 28, 38, 512, 2048)])
+def test_attention_training_path_fp32_tensors(b, h, w, dk, dv):
+    """The same entry points fed by fp32 NCHW tensors (the reference's dtype: the drop-in module in an fp32 training step): F and V are
+    rounded to fp16 once, an fp32 grad_ctx is packed to fp16 with a device-chosen power-of-two scale; outputs come back fp32.  The fp32
+    context (ctx32, what the backward's delta uses) is held to 1e-3; the gradients include the operand rounding of fp32 inputs."""
+    from acan_b200 import functions as fn
+    from acan_b200.modules import AttentionLoss2d, LazySimMap, _Holder
+    f = synth.feature_map(f"bw32.f.{h}", b, dk, h, w)
+    v = synth.feature_map(f"bw32.v.{h}", b, dv, h, w)
+    go = synth.randn(f"bw32.go.{h}", b, dv, h, w) * 1e-3
+    dis = O.continuous2discrete(synth.depth_label(f"bw32.lab.{h}", b, h * 8, w * 8, 0.5, 10.5), *NYU)
+    fd, vd = f.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    holder = _Holder()
+    ctx, token = fn.Attention.apply(fd, vd, holder)
+    assert ctx.dtype == torch.float32
+    ((ctx * go.to(DEV)).sum() + 0.7 * AttentionLoss2d()(LazySimMap(fd, holder, token=token, ws=holder.ws), dis.to(DEV))).backward()
+    want_ctx, want_gf, want_gv = _oracle_grads(f, v, go, dis, 0.7)
+    close(ctx, want_ctx)
+    close(fd.grad, want_gf, 1.5e-3)
+    close(vd.grad, want_gv, GRAD_TOL)
+
+
+def test_attention_training_row_sums_are_consistent():
+    """What makes the 16-bit backward accurate: the stored probabilities are renormalised by the sum of their ROUNDED values, so the rows
+    the tensor cores read sum to one and sum_j dS_ij = 0 (softmax backward) holds: dF of a constant feature direction vanishes."""
+    from acan_b200 import ops
+    b, h, w, dk, dv = 1, 16, 16, 128, 256
+    f, v, go, dis = _train_inputs(b, h, w, dk, dv, torch.float16, torch.float16, tag="rs")
+    out = ops.attention_forward_train(f.to(DEV).half().contiguous(memory_format=torch.channels_last), v.to(DEV).half().contiguous(memory_format=torch.channels_last))
+    ones = torch.ones(b, dv, h, w, device=DEV, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    out1 = ops.attention_forward_train(f.to(DEV).half().contiguous(memory_format=torch.channels_last), ones)
+    assert float((out1["ctx32"] - 1.0).abs().max()) <= 2e-6          # rows sum to 1 to fp32 accumulation accuracy
+
+
+def test_attention_legacy_fp32_abi_backward():
+    """acan_attn_fwd_loss / acan_attn_bwd (fp32 NCHW ABI, kept for callers without channels-last tensors) vs the oracle."""
     from acan_b200 import functions as fn
     from acan_b200.modules import _Holder
+    b, h, w, dk, dv = 1, 28, 38, 512, 2048
     f = synth.feature_map(f"bw.f.{h}.{dk}", b, dk, h, w)
     v = synth.feature_map(f"bw.v.{h}.{dv}", b, dv, h, w)
     dis = O.continuous2discrete(synth.depth_label(f"bw.lab.{h}", b, h * 8, w * 8, 0.5, 10.5), *NYU)
-    go = synth.randn(f"bw.go.{h}.{dv}", b, dv, h, w) * 1e-3                     # small upstream gradient: exercises the fp16 range scaling
+    go = synth.randn(f"bw.go.{h}.{dv}", b, dv, h, w) * 1e-3
     fd, vd = f.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
-    ctx, loss = fn.Attention.apply(fd, vd, dis.to(DEV), _Holder())
+    ctx, loss = fn.AttentionLegacy.apply(fd, vd, dis.to(DEV), _Holder())
     ((ctx * go.to(DEV)).sum() + 0.7 * loss).backward()
-    fc, vc = f.double().requires_grad_(True), v.double().requires_grad_(True)
-    sim = O.affinity(fc)
-    ((O.aggregate(sim, vc) * go.double()).sum() + 0.7 * O.attention_loss(sim, dis.double())).backward()
-    close(fd.grad, fc.grad, tol)
-    close(vd.grad, vc.grad, tol)
-    # aggregation gradient alone (no label), and the loss gradient alone
-    fd2, vd2 = f.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
-    ctx2, _ = fn.Attention.apply(fd2, vd2, None, _Holder())
-    (ctx2 * go.to(DEV)).sum().backward()
-    fc2, vc2 = f.double().requires_grad_(True), v.double().requires_grad_(True)
-    (O.aggregate(O.affinity(fc2), vc2) * go.double()).sum().backward()
-    close(fd2.grad, fc2.grad, tol)
-    close(vd2.grad, vc2.grad, tol)
+    _, want_gf, want_gv = _oracle_grads(f, v, go, dis, 0.7)
+    close(fd.grad, want_gf, 2e-3)
+    close(vd.grad, want_gv, 2e-3)
 
 
 # ------------------------------------------------------------------------------------ modules against the reference goldens
