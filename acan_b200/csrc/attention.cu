@@ -1192,20 +1192,6 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   return w;
 }
 
-// opt-in to > 48 KB of dynamic shared memory: a per-device, per-function attribute (set once per device ordinal)
-template <typename K>
-int ensure_smem_optin(K kernel) {
-  static std::atomic<uint64_t> done{0};
-  int dev = 0;
-  ACAN_CUDA(cudaGetDevice(&dev));
-  const uint64_t bit = 1ull << (dev & 63);
-  if (!(done.load(std::memory_order_acquire) & bit)) {
-    ACAN_CUDA((cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
-    done.fetch_or(bit, std::memory_order_release);
-  }
-  return 0;
-}
-
 template <int MODE, int CG, int AM, bool BMN>
 int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tout, GemmArgs& g, cudaStream_t st) {
   const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + static_cast<size_t>(g.bn / CG) * BK * 2;
@@ -1213,7 +1199,17 @@ int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensor
   if (stages > kMaxStages) stages = kMaxStages;
   g.stages = stages;
   const size_t smem = stages * stage_bytes + kOutBuffers * kOutChunkBytes + sizeof(PipeBarriers) + 1024;
-  if (int e = ensure_smem_optin(gemm_kernel<MODE, CG, AM, BMN>)) return e;
+  {  // opt-in to > 48 KB of dynamic shared memory: a per-device, per-function attribute (this static is per kernel instantiation;
+     // one bit per device ordinal)
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    ACAN_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+      ACAN_CUDA((cudaFuncSetAttribute(gemm_kernel<MODE, CG, AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+      done.fetch_or(bit, std::memory_order_release);
+    }
+  }
   if (g.out_scale == 0.f) g.out_scale = 1.0f;
   if (g.p_scale == 0.f) g.p_scale = 1.0f;
   if (AM != 2) g.k_half = g.k_steps;
