@@ -1228,7 +1228,7 @@ int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensor
   cfg.attrs = attr;
   cfg.numAttrs = (g.pdl && use_pdl()) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, CG, AM, BMN>, ta, ta2, tb, tout, g);
-  if (e != cudaSuccess) return fail((int)e, "gemm_kernel launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail((int)e, "gemm_kernel launch: %s", cudaGetErrorString(e)); }
   return launch_status("acan gemm_kernel");
 }
 

@@ -20,7 +20,8 @@ int  fail(int code, const char* fmt, ...);
 
 #define ACAN_CUDA(expr)                                                       \
   do { cudaError_t e__ = (expr);                                              \
-       if (e__ != cudaSuccess) return ::acan::fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__)); } while (0)
+       if (e__ != cudaSuccess) { (void)cudaGetLastError();   /* consume it: a stale error must not be blamed on the next launch */ \
+         return ::acan::fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__)); } } while (0)
 
 void note_launch();                       // counts kernels launched by this library (acan_launch_count)
 inline int launch_status(const char* what) {

@@ -14,17 +14,25 @@ import torch
 import torch.distributed as dist
 
 
-def init_distributed(backend: Optional[str] = None) -> tuple:
-    """(rank, world_size, local_rank) from the torchrun environment; no-op for a single process."""
+def init_distributed(backend: Optional[str] = None, high_priority: bool = True) -> tuple:
+    """(rank, world_size, local_rank) from the torchrun environment; no-op for a single process.  ``high_priority``: the NCCL
+    communicator's stream gets the high CUDA priority, so the CTAs of a gradient all-reduce are placed as soon as SMs free up under the
+    backward pass that is still replaying (at equal priority they queue behind every pending CTA of the compute kernels)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            kw["device_id"] = torch.device("cuda", local)
+            if high_priority:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.is_high_priority_stream = True
+                kw["pg_options"] = opts
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
 

@@ -93,6 +93,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._bind_flat_gradients()
+        optimizer.zero_grad(set_to_none=True)                  # the captured backward must CREATE its gradients (no in-place accumulation)
+        for s_ in self._shadows:
+            s_.grad = None
         from . import _lib
         n0 = _lib.load().acan_launch_count()
         if self._split:
@@ -186,7 +189,6 @@ class GraphedTrainStep:
     def _collect(self, pick) -> None:
         """gradients of this phase -> their slices of the flat buffer (two multi-tensor copies: the 16-bit shadow gradients, converted;
         the few fp32 ones autograd produced directly)."""
-        sh = [(p, s_) for p, s_ in zip(self._shadow_params, self._shadows) if p in set(pick(self._shadow_params)) and s_.grad is not None] if False else None
         chosen = {id(p) for p in pick(self._flat_params)}
         dst, src = [], []
         for p, s_ in zip(self._shadow_params, self._shadows):

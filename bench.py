@@ -6,30 +6,40 @@
 
 Workload = BASELINE.json configs[1]: full ACAN forward (dilated ResNet-101 backbone + context aggregation module +
 ordinal soft inference), NYU-shaped 256x352 synthetic batch of 16 images per GPU (weak scaling, no data-path
-collective: every image is an independent unit, SURVEY.md §8e).  One step = net(images) -> net.inference(y), the
+collective: every image is an independent unit, SURVEY.md section 8e).  One step = net(images) -> net.inference(y), the
 reference's eval call pattern (depthest_trainer.py:184-185), with the drop-in modules of acan_b200/.
 
-  value    images/s with the batch already resident in HBM (CUDA events, max over ranks).
-  e2e      the same call with HOST buffers: pinned images -> H2D, forward, inference, depth -> D2H, every step.
-  roofline the dominant hand-written kernel (aggregation pass O^T = V P^T on tcgen05), its CUDA-event time measured
-           live in this run via the library's event hooks, against MEASURED_PEAKS.json; `attention_core` and `head`
-           give the same arithmetic for the whole fused CAM core and the depth head.
-  cpu_baseline  the oracle port of the reference forward on the host cores, bounded sample (rank 0, N = 1).
---impl reference times that CPU path alone (the reference is PyTorch-on-CPU code; the oracle is its restatement).
+  value     images/s with the batch already resident in HBM (CUDA events over EXACTLY K steps, max over ranks); `timed_1s` repeats the
+            measurement over a region of at least one second, with the SM clock sampled throughout.
+  e2e       the same call with HOST buffers: pinned images -> H2D, forward, inference, depth -> D2H, every step.
+  parity    the benched network's depth for the first images of the timed batch against the reference's CPU path on the same weights
+            (N = 1): the run FAILS above the tolerance written there.
+  roofline  the dominant hand-written kernel (aggregation pass O = P V on tcgen05), its CUDA-event time measured live in this run via the
+            library's event hooks, against MEASURED_PEAKS.json; `attention_core`, `head`, `tail` give the same arithmetic for the whole
+            fused CAM core, the depth head and the fused classifier tail.
+  train     configs[3] / [4] sub-record: the beta = 1 training step (forward + losses + backward + NCCL gradient all-reduce + SGD), B = 8
+            per GPU, with the all-reduce time and a replica-consistency check (--no-train skips it; --workload train prints it alone).
+  gpu_reference  (N = 1) the UNMODIFIED reference modules (baseline/_ref) on the same B200, fp32 eager and bf16 autocast: configs[1]
+            forward, the CAM module alone, the configs[3] training step -- the like-for-like GPU baseline.
+  c3_kitti_hard  (N = 1) configs[2]: KITTI 160x512, batch 32, hard ordinal inference, with the count of bin indices that differ from
+            ATen's fp32 upsample -> decode -> count path on the same logits.
+  cpu_baseline   the reference's CPU path on the host cores, bounded sample (rank 0, N = 1).
+--impl reference times that CPU path alone: the reference's own modules (baseline/_ref, kind "reference"; the oracle port if absent).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
+import gc
 import json
+import math
 import os
-import subprocess
 import sys
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "baseline")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -40,6 +50,10 @@ DMIN, DMAX, K = 0.72, 10.0, 80
 LAYERS101 = [3, 4, 23, 3]
 AMP = torch.float16      # 16-bit autocast for the cuDNN convolutions; fp16 lets the CAM consume F and V in place
 WORKLOAD = "configs[1]: full ACAN fwd (ResNet-101 + CAM + OR soft inference), NYU 256x352, batch 16 per GPU"
+# benched arithmetic = fp16 activations through 101 folded-BN layers: max-norm relative depth error vs the fp32 reference; the fp32
+# drop-in network holds 1e-3 (tests/test_gpu_fullsize.py), DESIGN.md section 4 explains the split
+PARITY_TOL_MAX, PARITY_TOL_MEAN = 2e-2, 2e-3
+REF_SAMPLE_BATCH = 4     # images per step of the CPU reference arm (a bounded sample of the 16-image step: ~1-3 s of host time per step)
 
 
 def peaks():
@@ -91,12 +105,12 @@ class ClockSampler:
                 "reasons": sorted(name for bit, name in self.REASONS.items() if self.mask & bit)}
 
 
-def build_net(device):
+def build_net(device, hh=H, ww=W, batch=BATCH, inference="soft", dmin=DMIN, dmax=DMAX):
     from acan_b200.network import ResNet
     torch.manual_seed(2019)
-    net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=0, layers=LAYERS101)
+    net = ResNet(dmin, dmax, K, "OR", inference, "attention", hh, ww, alpha=0, beta=0, layers=LAYERS101)
     net = net.to(device).to(memory_format=torch.channels_last)
-    # BN calibration (SURVEY §8d: never eval() on raw running statistics): one train()-mode pass with momentum 1
+    # BN calibration (SURVEY section 8d: never eval() on raw running statistics): one train()-mode pass with momentum 1
     # puts the batch statistics of a synthetic batch into the running buffers, then eval().
     bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
     for m in bns:
@@ -106,7 +120,7 @@ def build_net(device):
         if isinstance(m, torch.nn.Dropout2d):
             m.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=AMP):
-        net(torch.rand(BATCH, 3, H, W, device=device).contiguous(memory_format=torch.channels_last))
+        net(torch.rand(batch, 3, hh, ww, device=device).contiguous(memory_format=torch.channels_last))
     for m in bns:
         m.momentum = 0.1
     from acan_b200.inference import optimize_for_inference
@@ -120,42 +134,102 @@ def step_device(net, images):
     return net.inference(net(images))                # the reference's eval call pattern (depthest_trainer.py:184-185)
 
 
-def cpu_reference_forward(sd_cpu, n_iter, warm, threads):
-    """oracle port of the reference forward (ResNet-101 + CAM + decode_ord + soft OR) on the host cores, B = 1."""
+# ------------------------------------------------------------------------------------ the reference's CPU path
+
+def cpu_reference_callable(sd_cpu=None, hh=H, ww=W, calibrate_batch=0):
+    """(fn(images) -> depth, kind): the UNMODIFIED reference network (baseline/_ref) in eval mode on the host, loaded with `sd_cpu`
+    (or, with sd_cpu None, the reference's own random init under seed 2019 followed by the BN calibration pass of SURVEY section 8d);
+    the oracle port of the same forward when no copy of the reference is present."""
+    try:
+        import refload
+        ref = refload.load_reference()
+    except Exception:
+        ref = None
+    if ref is not None:
+        torch.manual_seed(2019)
+        net = ref.models.create_network(refload.reference_args(height=hh, width=ww))
+        if sd_cpu is not None:
+            net.load_state_dict(sd_cpu)
+        elif calibrate_batch:
+            bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+            for m in bns:
+                m.momentum = 1.0
+            net.train()
+            for m in net.modules():
+                if isinstance(m, torch.nn.Dropout2d):
+                    m.eval()
+            with torch.no_grad():
+                net(torch.rand(calibrate_batch, 3, hh, ww))
+            for m in bns:
+                m.momentum = 0.1
+        net.eval()
+
+        def fn(x):
+            with torch.no_grad():
+                return net.inference(net(x))
+        return fn, "reference"
     from oracle import acan_oracle as O
-    torch.set_num_threads(threads)
-    x = torch.rand(1, 3, H, W)
+    if sd_cpu is None:
+        from acan_b200.network import ResNet
+        torch.manual_seed(2019)
+        sd_cpu = {k: v.detach() for k, v in ResNet(DMIN, DMAX, K, "OR", "soft", "attention", hh, ww, layers=LAYERS101).state_dict().items()}
+
+    def fn(x):
+        with torch.no_grad():
+            return O.inference(O.acan_forward(x, sd_cpu, LAYERS101, "OR", training=False)["y"], "OR", "soft", DMIN, DMAX, K)
+    return fn, "port"
+
+
+def time_cpu(fn, batch, n_iter, warm):
+    x = torch.rand(batch, 3, H, W)
     times = []
-    with torch.no_grad():
-        for i in range(warm + n_iter):
-            t0 = time.perf_counter()
-            out = O.acan_forward(x, sd_cpu, LAYERS101, "OR", training=False)
-            depth = O.inference(out["y"], "OR", "soft", DMIN, DMAX, K)
-            dt = time.perf_counter() - t0
-            if i >= warm:
-                times.append(dt)
-    return times, depth
+    for i in range(warm + n_iter):
+        t0 = time.perf_counter()
+        fn(x)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, on the arm's config (B = 16 per step)."""
     if rank != 0:
         return
-    from acan_b200.network import ResNet
-    torch.manual_seed(2019)
-    net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=0, layers=LAYERS101)
-    sd = {k: v.detach() for k, v in net.state_dict().items()}
     threads = os.cpu_count() or 1
-    times, _ = cpu_reference_forward(sd, args.steps, args.warmup, threads)
+    torch.set_num_threads(threads)
+    fn, kind = cpu_reference_callable(None, calibrate_batch=4)
+    times = time_cpu(fn, REF_SAMPLE_BATCH, args.steps, args.warmup)
     tot = sum(times)
-    val = len(times) / tot
-    sample = f"B=1 image per step x {len(times)} steps, fp32, torch CPU ops, eval-mode BN"
+    val = REF_SAMPLE_BATCH * len(times) / tot
+    sample = (f"bounded sample: {REF_SAMPLE_BATCH} of the step's {BATCH} images per step x {len(times)} steps ({tot:.1f} s), fp32, torch CPU ops on {threads} threads, eval-mode BN on calibrated statistics; "
+              + ("the unmodified reference modules (baseline/_ref: models.create_network -> net.inference(net(x)))" if kind == "reference"
+                 else "oracle port of the reference forward (no copy of the reference on this host)"))
     print(json.dumps({
         "impl": "reference", "metric": "ACAN NYU-shape forward images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------ helpers
+
+def ev_time(fn_, iters=10, warm=3):
+    for _ in range(warm):
+        fn_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn_()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / iters
+
+
+def free_cuda():
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 TRAIN_BATCH = 8
@@ -163,15 +237,16 @@ TRAIN_WORKLOAD = "configs[3]: ACAN training step with attention loss (beta=1, al
 
 
 def run_train(args, rank, world, device, lib):
-    """--workload train: BASELINE.json configs[3] (and configs[4] under torchrun): ResNet-101 + CAM + fused ordinal tail loss +
-    fused attention loss, forward + backward + SGD(momentum) step; N > 1 averages gradients with the bucketed NCCL all-reduce
-    of acan_b200.parallel (overlapped with backward).  bf16 autocast, channels_last; the hand-written kernels run in fp16
-    operands / fp32 accumulate (attention) and fp32 (losses)."""
+    """configs[3] (and configs[4] under torchrun): ResNet-101 + CAM + fused ordinal tail loss + fused attention loss, forward + backward +
+    SGD(momentum) step; N > 1 averages gradients with NCCL (acan_b200.training.GraphedTrainStep: the late layers' segment of the flat
+    gradient buffer is all-reduced while the early layers' backward graph replays).  bf16 autocast, channels_last; the attention core runs
+    fp16 probabilities x bf16 values / gradients in place (fp32 accumulate), the losses fp32.  Returns the record (rank 0) or None."""
     import torch.distributed as dist
     from acan_b200 import ops
     from acan_b200.modules import AttentionLoss2d
     from acan_b200.network import OrdinalRegression2d, ResNet
     from acan_b200.parallel import GradAllReducer
+    from acan_b200.training import GraphedTrainStep
     B = TRAIN_BATCH
     torch.manual_seed(2019)
     net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=1.0, layers=LAYERS101).to(device)
@@ -186,14 +261,13 @@ def run_train(args, rank, world, device, lib):
     dev_x = [t.to(device, non_blocking=True) for t in host_x]
     dev_y = [t.to(device, non_blocking=True) for t in host_y]
 
-    from acan_b200.training import GraphedTrainStep
     graph_note = None
     try:
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
-                                graph=not args.no_graph)
+                                graph=not args.no_graph, overlap=not args.no_overlap)
     except Exception as e:          # same kernels either way: a failed capture must not cost the measurement
         torch.cuda.synchronize()
-        graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]})"
         reducer.enabled = True
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None, graph=False)
 
@@ -202,7 +276,7 @@ def run_train(args, rank, world, device, lib):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         step(dev_x[i % n_rot], dev_y[i % n_rot])
     barrier()
     launches0 = lib.acan_launch_count()
@@ -213,11 +287,21 @@ def run_train(args, rank, world, device, lib):
         loss = step(dev_x[i % n_rot], dev_y[i % n_rot])
     e1.record()
     barrier()
-    clocks = sampler.stop()
     elapsed = e0.elapsed_time(e1) * 1e-3
+    # >= 1 s region
+    long_steps = max(args.steps, int(math.ceil(1.2 / max(elapsed / args.steps, 1e-4))))
+    e0.record()
+    for i in range(long_steps):
+        loss = step(dev_x[i % n_rot], dev_y[i % n_rot])
+    e1.record()
+    barrier()
+    elapsed_long = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop()
     launches = lib.acan_launch_count() - launches0
-    if step.graph is not None:                       # replays do not pass through the library's host-side launch counter
+    if step.graphs:                                  # replays do not pass through the library's host-side launch counter
         launches = step.library_launches_per_step * args.steps
+    else:
+        launches = launches * args.steps // (args.steps + long_steps)
     assert bool(torch.isfinite(loss)), "training loss is not finite"
     # end to end: pinned host images + labels in, the loss value out, every step
     barrier()
@@ -226,7 +310,19 @@ def run_train(args, rank, world, device, lib):
         loss_host = float(step(host_x[i % n_rot], host_y[i % n_rot]))     # pinned host -> the step's static device buffers, loss -> host
     barrier()
     e2e_elapsed = time.perf_counter() - t0
-    t = torch.tensor([elapsed, e2e_elapsed], device=device, dtype=torch.float64)
+    # the gradient all-reduce on its own (what the split schedule hides / exposes): the whole flat buffer, and the exposed early segment
+    ar_ms = ar_early_ms = None
+    n_grad = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    if world > 1:
+        flat = getattr(step, "_flat", None)
+        if flat is None:
+            flat = torch.zeros(n_grad, device=device)
+        keep = flat.clone()
+        ar_ms = ev_time(lambda: dist.all_reduce(flat, op=dist.ReduceOp.AVG), iters=10) * 1e3
+        ne = getattr(step, "_n_early", n_grad)
+        ar_early_ms = ev_time(lambda: dist.all_reduce(flat[:ne], op=dist.ReduceOp.AVG), iters=10) * 1e3
+        flat.copy_(keep)
+    t = torch.tensor([elapsed, e2e_elapsed, elapsed_long], device=device, dtype=torch.float64)
     in_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -236,41 +332,32 @@ def run_train(args, rank, world, device, lib):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         in_sync = bool((hi - lo).abs() <= 1e-9 * hi.abs())
-    elapsed, e2e_elapsed = float(t[0]), float(t[1])
+    elapsed, e2e_elapsed, elapsed_long = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    # roofline of the dominant hand-written group of the step: attention forward (+ fused loss) and backward, stand-alone, same shape
+        return None
+    # rooflines of the step's hand-written kernel groups, stand-alone at the step's shapes
     pk = peaks()
     n = (H // 8) * (W // 8)
-    f = torch.relu(torch.randn(B, 512, H // 8, W // 8, device=device))
-    v = torch.relu(torch.randn(B, 2048, H // 8, W // 8, device=device))
+    cl = torch.channels_last
+    f = torch.relu(torch.randn(B, 512, H // 8, W // 8, device=device)).half().contiguous(memory_format=cl)
+    v = torch.relu(torch.randn(B, 2048, H // 8, W // 8, device=device)).bfloat16().contiguous(memory_format=cl)
     lab = torch.randint(0, K, (B, 1, H, W), device=device).float()
-    go = torch.randn(B, 2048, H // 8, W // 8, device=device) * 1e-3
-    o = ops.attention_forward(f, v, dis_label=lab)
-
-    def ev(fn_, iters=10):
-        for _ in range(3):
-            fn_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn_()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e-3 / iters
-    t_f = ev(lambda: ops.attention_forward(f, v, dis_label=lab, ws=o["ws"]))
-    t_b = ev(lambda: ops.attention_backward(f, o["row_stats"], v, o["ctx"], go, lab, 1.0))
-    bwd_flops = B * 10240.0 * n * n
+    go = (torch.randn(B, 2048, H // 8, W // 8, device=device) * 1e-3).bfloat16().contiguous(memory_format=cl)
+    gl = torch.ones((), device=device)
+    o = ops.attention_forward_train(f, v)
+    ops.attention_loss_fused(o["ws"], lab)
+    t_f = ev_time(lambda: ops.attention_forward_train(f, v))
+    t_l = ev_time(lambda: ops.attention_loss_fused(o["ws"], lab))
+    t_b = ev_time(lambda: ops.attention_backward_cl(o["ws"], o["value16"], o["ctx32"], go, gl, torch.float16, torch.bfloat16))
+    fwd_flops, bwd_flops = B * 5120.0 * n * n, B * 10240.0 * n * n
     del f, v, lab, go, o
-    # the dominant hand-written kernels of the step by time are the BN (+ReLU/+residual) passes (105 layers, ~3.3 ms of the step): the
-    # backward kernel at the most common large layer shape (layer3's 1024-channel maps), operands rotated through > 2x L2, replayed from
-    # a CUDA graph so that the number is device time, not host launch rate
+    # the dominant hand-written kernels of the step by time are the BN (+ReLU/+residual) passes (105 layers): the backward kernel at the
+    # most common large layer shape (layer3's 1024-channel maps), operands rotated through > 2x L2, replayed from a CUDA graph so that the
+    # number is device time, not host launch rate
     bc, bh, bw = 1024, H // 8, W // 8
     n_rot = 14
-    xs = [torch.randn(B, bc, bh, bw, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(n_rot)]
-    gs = [torch.randn(B, bc, bh, bw, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(n_rot)]
+    xs = [torch.randn(B, bc, bh, bw, device=device, dtype=torch.bfloat16).contiguous(memory_format=cl) for _ in range(n_rot)]
+    gs = [torch.randn(B, bc, bh, bw, device=device, dtype=torch.bfloat16).contiguous(memory_format=cl) for _ in range(n_rot)]
     wgt, bia = torch.ones(bc, device=device), torch.zeros(bc, device=device)
     outs = [ops.bn_train_forward(xx, wgt, bia, None, None, 0.1, 1e-5, True, None) for xx in xs]
     ys_, mean_, invstd_ = [t_[0] for t_ in outs], outs[0][1], outs[0][2]
@@ -299,19 +386,27 @@ def run_train(args, rank, world, device, lib):
     t_bn_f = graph_time([lambda xx=xx: ops.bn_train_forward(xx, wgt, bia, None, None, 0.1, 1e-5, True, None) for xx in xs])
     t_bn_b = graph_time([lambda k=k: ops.bn_train_backward(xs[k], ys_[k], gs[k], wgt, mean_, invstd_, False) for k in range(n_rot)])
     bn_elems = float(B * bc * bh * bw)
-    out = {
+    if world > 1:
+        sched = ("dp%d: batch-sharded replicas; backward split at layer3 into two CUDA graphs, the late layers' slice of the flat fp32 gradient buffer "
+                 "all-reduced on the (high-priority) NCCL stream while the second graph replays, the early slice after it, then the optimizer graph" % world
+                 if getattr(step, "_split", False) else
+                 "dp%d: batch-sharded replicas; one backward graph, one in-place NCCL all-reduce of the flat fp32 gradient buffer, optimizer graph" % world)
+    else:
+        sched = "dp1"
+    return {
         "metric": "ACAN NYU-shape training images/sec", "value": world * B * args.steps / elapsed, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": TRAIN_WORKLOAD, "parallelism": (f"dp{world} (batch-sharded replicas; NCCL gradient all-reduce " +
-                                   ("bucketed, overlapped with backward from grad hooks)" if args.no_graph else "one in-place all-reduce of a flat fp32 gradient buffer between the backward graph and the optimizer graph)")) if world > 1 else "dp1",
-                   "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd fp16 operands / fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
-                   "launch": graph_note or ("eager" if args.no_graph else "whole step (fwd + losses + bwd + SGD) replayed from a CUDA graph; N > 1: backward graph, one NCCL all-reduce, optimizer graph (acan_b200.training.GraphedTrainStep)"),
-                   "l2": f"{n_rot} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},
+        "timed_1s": {"steps": long_steps, "seconds": elapsed_long, "ms_per_step": elapsed_long / long_steps * 1e3, "value": world * B * long_steps / elapsed_long},
+        "config": {"workload": TRAIN_WORKLOAD, "parallelism": sched,
+                   "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd on the channels-last path: fp16 probabilities x bf16 values / gradients read in place, fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
+                   "launch": graph_note or ("eager" if args.no_graph else "step replayed from CUDA graphs (acan_b200.training.GraphedTrainStep): forward + losses + backward, optimizer graph re-captured when a scheduler changes lr"),
+                   "l2": f"{8} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_elapsed / args.steps * 1e3},
         "gpu_launches": int(launches),
+        "allreduce_ms": ar_ms, "allreduce_early_segment_ms": ar_early_ms, "gradient_bytes": n_grad * 4, "replicas_in_sync": in_sync,
         "roofline": {"bound": "hbm", "kernel": "bn_bwd_coop_kernel<bf16> (BN + ReLU backward: one cooperative launch, 14 B per element algorithmic: dy, y, x read for the "
                                "statistics, read again -- from L2 -- for dx, dx written), layer3 shape [8,1024,32,44], stand-alone, graph-replayed over 14 rotating operand sets",
                      "achieved": 14.0 * bn_elems / t_bn_b / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": 14.0 * bn_elems / t_bn_b / 1e9 / pk["hbm"],
@@ -319,14 +414,96 @@ def run_train(args, rank, world, device, lib):
                      "note": "traffic = dram read 71.5 MB + write 4.6 MB from profiles/r01b_train_kernels_bn_tailloss.ncu-rep (the 23 MB of dx are still in L2 when the kernel ends)"},
         "bn_forward": {"bound": "hbm", "what": "bn_fwd_coop_kernel<bf16>, same shape, 6 B per element algorithmic", "achieved": 6.0 * bn_elems / t_bn_f / 1e9, "peak": pk["hbm"],
                        "unit": "GB/s", "frac": 6.0 * bn_elems / t_bn_f / 1e9 / pk["hbm"], "launch_us": t_bn_f * 1e6},
-        "attention_bwd": {"bound": "tensor", "what": "acan_attn_bwd (P recompute, dV, dP -> dS with fused attention-loss term, dF: five tcgen05 GEMMs + packs), fp32-NCHW ABI, "
-                                                     "stand-alone at the step's shape, algorithmic 10240*N^2 FLOP/img",
+        "attention_bwd": {"bound": "tensor", "what": "acan_attn_bwd_nhwc (delta, dV, dP -> dS with the attention-loss term, symmetrised dF: four tcgen05 launches, operands in place, "
+                                                     "probabilities kept from the forward), stand-alone at the step's shape, algorithmic 10240*N^2 FLOP/img",
                           "achieved": bwd_flops / t_b / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": bwd_flops / t_b / 1e12 / pk["tensor"], "launch_us": t_b * 1e6},
-        "attention_fwd_loss_us": t_f * 1e6, "loss": loss_host, "replicas_in_sync": in_sync, "cpu_baseline": None,
+        "attention_fwd_train": {"bound": "tensor", "what": "acan_attn_fwd_nhwc keep=1 (statistics + probability + aggregation passes, fp32 context), algorithmic 5120*N^2 FLOP/img",
+                                "achieved": fwd_flops / t_f / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": fwd_flops / t_f / 1e12 / pk["tensor"], "launch_us": t_f * 1e6},
+        "attention_loss_us": t_l * 1e6, "loss": loss_host,
     }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ N = 1 extras
+
+def gpu_reference_extras(device, sd_cpu, ours_c2_ms, ours_train_ms, ours_cam_us):
+    """the UNMODIFIED reference modules on this GPU (depthest_main.py:59-77 settings: cudnn.benchmark on, PyTorch's default TF32 policy):
+    configs[1] forward + inference, the CAM module alone, the configs[3] training step; fp32 eager and bf16 autocast."""
+    try:
+        import refload
+        ref = refload.load_reference()
+    except Exception as e:
+        return {"unavailable": str(e)[:200]}
+    out = {"what": "unmodified reference modules (baseline/_ref) on the same B200, eager PyTorch, cudnn.benchmark=True, CUDA events"}
+    torch.manual_seed(0)
+    net = ref.models.create_network(refload.reference_args(height=H, width=W, beta=1.0))
+    net.load_state_dict(sd_cpu)
+    net = net.to(device).eval()
+    x = torch.rand(BATCH, 3, H, W, device=device)
+    feat = torch.relu(torch.randn(BATCH, 2048, H // 8, W // 8, device=device))
+    with torch.no_grad():
+        t32 = ev_time(lambda: net.inference(net(x)), iters=5, warm=2)
+        c32 = ev_time(lambda: net.decoder(feat), iters=10, warm=2)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            t16 = ev_time(lambda: net.inference(net(x)), iters=5, warm=2)
+            c16 = ev_time(lambda: net.decoder(feat), iters=10, warm=2)
+    out["c2_forward_ms"] = {"fp32": t32 * 1e3, "bf16_autocast": t16 * 1e3, "ours": ours_c2_ms,
+                            "speedup_vs_fp32": t32 * 1e3 / ours_c2_ms, "speedup_vs_bf16": t16 * 1e3 / ours_c2_ms}
+    out["cam_module_us"] = {"fp32": c32 * 1e6, "bf16_autocast": c16 * 1e6, "ours": ours_cam_us,
+                            "speedup_vs_fp32": c32 * 1e6 / ours_cam_us, "speedup_vs_bf16": c16 * 1e6 / ours_cam_us,
+                            "what": "SADecoder.forward on [16,2048,32,44] features (projections + attention + pooling branch + merge)"}
+    del x, feat
+    if ours_train_ms is not None:
+        net.train()
+        crit = ref.models.create_lossfunc(refload.reference_args(height=H, width=W, beta=1.0), net)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9, weight_decay=5e-4)
+        xb = torch.rand(TRAIN_BATCH, 3, H, W, device=device)
+        yb = (torch.rand(TRAIN_BATCH, 1, H, W, device=device) * 10 + 0.5) * (torch.rand(TRAIN_BATCH, 1, H, W, device=device) > 0.1).float()
+
+        def one(amp):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                loss = crit(net(xb), yb.clone(), 1)[3]
+            loss.backward()
+            opt.step()
+        s32 = ev_time(lambda: one(False), iters=4, warm=2)
+        s16 = ev_time(lambda: one(True), iters=4, warm=2)
+        out["c4_train_step_ms"] = {"fp32": s32 * 1e3, "bf16_autocast": s16 * 1e3, "ours": ours_train_ms,
+                                   "speedup_vs_fp32": s32 * 1e3 / ours_train_ms, "speedup_vs_bf16": s16 * 1e3 / ours_train_ms}
+    return out
+
+
+def c3_line(device, steps):
+    """BASELINE.json configs[2]: KITTI 160x512, batch 32, hard ordinal inference; device-resident images/s from the CUDA-graph replay, and the
+    bin indices of the fused tail against ATen's fp32 upsample_bilinear2d -> decode_ord -> count(p > 0.5) on the same stride-8 logits."""
+    from acan_b200 import ops
+    from acan_b200.inference import GraphedPredictor
+    hh, ww, b = 160, 512, 32
+    dmin, dmax = 1.98, 80.0
+    net = build_net(device, hh, ww, b, "hard", dmin, dmax)
+    xs = [torch.rand(b, 3, hh, ww, device=device).contiguous(memory_format=torch.channels_last) for _ in range(4)]
+    pred = GraphedPredictor(net, xs[0])
+    for i in range(3):
+        pred.predict(xs[i % 4])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        pred.predict(xs[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    with torch.no_grad():
+        z = net(xs[0])["y"]._z.float()
+        _, idx = ops.tail_inference(z, "OR", "hard", dmin, dmax, K, want_index=True)
+        up = torch.nn.functional.interpolate(z.contiguous(), scale_factor=8, mode="bilinear", align_corners=True).view(b, K, 2, hh, ww)
+        e = torch.exp(up)
+        want = (e[:, :, 1] / (e[:, :, 0] + e[:, :, 1]) > 0.5).float().sum(1, keepdim=True)
+        bad = int((idx.float() != want).sum())
+    del pred, net, xs, up, e, want
+    free_cuda()
+    return {"workload": "configs[2]: KITTI 160x512, batch 32, ResNet-101 + CAM + OR hard inference", "value": b * steps / sec, "unit": "images/s",
+            "ms_per_step": sec / steps * 1e3, "steps": steps,
+            "hard_index_mismatches_vs_aten_fp32": bad, "pixels": b * hh * ww}
 
 
 def main():
@@ -336,11 +513,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="train workload: launch the step eagerly instead of replaying its CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying their CUDA graphs")
+    ap.add_argument("--no-overlap", action="store_true", help="train, N > 1: one backward graph + one all-reduce (A/B against the split schedule)")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3]/[4] training sub-record")
+    ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 extras (reference on the GPU, configs[2] line)")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
-                    help="infer (default): BASELINE.json configs[1], the headline.  train: configs[3]/[4], the beta=1 training step, B=8 per GPU")
+                    help="infer (default): BASELINE.json configs[1], the headline (+ the train sub-record).  train: only configs[3]/[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    knobs = sorted(k for k in os.environ if k.startswith("ACAN_"))
+    if knobs:
+        sys.exit(f"bench.py refuses to run with experiment variables set ({', '.join(knobs)}): the shipped library ignores them, and a number "
+                 "measured under an experiment build is not a bench value")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -360,14 +544,18 @@ def main():
     _lib.check(lib.acan_device_check(), "acan_device_check")
     torch.backends.cudnn.benchmark = True                 # as depthest_main.py:65
     if args.workload == "train":
-        run_train(args, rank, world, device, lib)
+        rec = run_train(args, rank, world, device, lib)
+        if rank == 0:
+            rec["cpu_baseline"] = None
+            print(json.dumps(rec))
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     net = build_net(device)
     n_rot = 8                                             # 8 distinct input batches = 138 MB > 126 MB L2
     host = [torch.rand(BATCH, 3, H, W).contiguous(memory_format=torch.channels_last).pin_memory() for _ in range(n_rot)]
     dev_in = [h.to(device, non_blocking=True) for h in host]
-    depth_host = torch.empty(BATCH, 1, H, W).pin_memory()
     torch.cuda.synchronize()
 
     def barrier():
@@ -398,9 +586,18 @@ def main():
         depth = run(dev_in[i % n_rot])
     e1.record()
     barrier()
-    clocks = sampler.stop()
     elapsed = e0.elapsed_time(e1) * 1e-3
     launches = lib.acan_launch_count() - launches0 if pred is None else pred.library_launches_per_step * args.steps
+    # the same measurement over a region of at least one second (the K-step region above is ~0.1 s: too short for the clock sampler)
+    long_steps = max(args.steps, int(math.ceil(1.2 / max(elapsed / args.steps, 1e-4))))
+    e0.record()
+    for i in range(long_steps):
+        depth = run(dev_in[i % n_rot])
+    e1.record()
+    barrier()
+    elapsed_long = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop()
+    depth_first = run(dev_in[0]).clone()                   # for the parity record
 
     # ---- per-kernel CUDA-event brackets (roofline): the same K steps on the same inputs, launched eagerly with the library's
     #      event hooks on (events cannot be timed from inside a replayed graph); not part of `value`
@@ -435,97 +632,107 @@ def main():
     e2e_elapsed = time.perf_counter() - t0
     assert got == args.steps and bool(torch.isfinite(out_host).all())
 
-    t = torch.tensor([elapsed, e2e_elapsed], device=device, dtype=torch.float64)
+    t = torch.tensor([elapsed, e2e_elapsed, elapsed_long], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed, e2e_elapsed = float(t[0]), float(t[1])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    elapsed, e2e_elapsed, elapsed_long = float(t[0]), float(t[1]), float(t[2])
 
-    pk = peaks()
-    n = (H // 8) * (W // 8)
-    per_launch = lambda k: (ms[k] / max(cnt[k], 1)) * 1e-3          # noqa: E731  seconds per bracket
-    pv_flops = BATCH * 2.0 * n * n * 2048                           # a4: 2*N^2*dv per image
-    core_flops = BATCH * 5120.0 * n * n                             # a2+a4: 2*N^2*(dk+dv) per image
-    t_pv = per_launch(3)
-    t_core = per_launch(0) + per_launch(1) + per_launch(2) + per_launch(3)
-    head_bytes = BATCH * 324.0 * H * W                              # prob -> depth: (K+1)*HW*4 per image
-    t_tail = per_launch(4)                                          # in-step: fused upsample + decode_ord + head on stride-8 logits
-    # the HBM-bound head kernel (prob [B,K,H,W] -> depth) is no longer on the eval path (the fused tail reads 0.9 MB / image);
-    # its roofline is measured here on its own, same shape, CUDA events, 3 warm-up + 10 timed launches
-    from acan_b200 import ops
-    prob = torch.rand(BATCH, K, H, W, device=device)
-    for _ in range(3):
-        ops.head_inference(prob, "OR", "soft", DMIN, DMAX, K)
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record()
-    for _ in range(10):
-        ops.head_inference(prob, "OR", "soft", DMIN, DMAX, K)
-    h1.record()
-    torch.cuda.synchronize()
-    t_head = h0.elapsed_time(h1) * 1e-4
-    del prob
-    # the whole attention core as the step runs it (one acan_attn_fwd_nhwc_f16 call: diagonal, fallback statistics, probability
-    # and aggregation passes chained by programmatic dependent launch), stand-alone at the same shape, no event hooks in between
-    # (the in-step per-pass brackets below record events between the passes, which serialises them)
-    fcl = torch.relu(torch.randn(BATCH, 512, H // 8, W // 8, device=device)).half().contiguous(memory_format=torch.channels_last)
-    vcl = torch.relu(torch.randn(BATCH, 2048, H // 8, W // 8, device=device)).half().contiguous(memory_format=torch.channels_last)
-    ws_core = ops.attention_forward_cl(fcl, vcl)["ws"]
-    for _ in range(3):
-        ops.attention_forward_cl(fcl, vcl, ws=ws_core)
-    h0.record()
-    for _ in range(20):
-        ops.attention_forward_cl(fcl, vcl, ws=ws_core)
-    h1.record()
-    torch.cuda.synchronize()
-    t_core_call = h0.elapsed_time(h1) * 1e-3 / 20
-    del fcl, vcl, ws_core
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
-    # profiles/r01b_attn_cl_4launch_pdl.ncu-rep (157.2 MB + 65.0 MB; algorithmic V 92 + P 63 MB read, O 92 MB fp16 written)
-    roof = {"bound": "tensor", "kernel": "gemm_kernel<MODE_PVT, CG=2> (aggregation O = P V on tcgen05, CTA pairs, V read in place MN-major)",
-            "achieved": pv_flops / t_pv / 1e12,
-            "peak": pk["tensor"], "unit": "TFLOP/s", "frac": pv_flops / t_pv / 1e12 / pk["tensor"], "traffic": 222.2e6,
-            "peak_source": pk["src"] + " (bf16 burst; the kernel is timed inside the step, so the sustained figure is given beside it)",
-            "frac_vs_sustained": (pv_flops / t_pv / 1e12 / pk["tensor_sustained"]) if pk.get("tensor_sustained") else None,
-            "launch_us": t_pv * 1e6, "launches_timed": cnt[3]}
-    extra = {
-        "attention_core": {"bound": "tensor", "what": "whole CAM core call (diagonal + fallback statistics + probability + aggregation passes), algorithmic "
-                                   "5120*N^2 FLOP/img, CUDA events around 20 stand-alone calls at the step's shape; `us_in_step` = the per-pass event "
-                                   "brackets inside the timed steps (events between the passes disable their launch overlap)",
-                           "achieved": core_flops / t_core_call / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": core_flops / t_core_call / 1e12 / pk["tensor"],
-                           "call_us": t_core_call * 1e6, "frac_in_step": core_flops / t_core / 1e12 / pk["tensor"],
-                           "us_in_step": {"pack": per_launch(0) * 1e6, "stats": per_launch(1) * 1e6, "probs": per_launch(2) * 1e6, "pv": t_pv * 1e6}},
-        "head": {"bound": "hbm", "what": "OR soft inference prob -> depth kernel, 324*HW B/img, measured stand-alone at the same shape", "achieved": head_bytes / t_head / 1e9 if t_head > 0 else None,
-                 "peak": pk["hbm"], "unit": "GB/s", "frac": head_bytes / t_head / 1e9 / pk["hbm"] if t_head > 0 else None, "launch_us": t_head * 1e6},
-        "tail": {"what": "fused classifier tail in the step: x8 bilinear + decode_ord + OR soft head from stride-8 logits (expf/div-bound; "
-                         "replaces upsample 1.9 ms + layout copy 1.0 ms + decode_ord 0.22 ms + head 0.07 ms of the unfused step)", "launch_us": t_tail * 1e6},
-        "pool_branch_us": per_launch(5) * 1e6,
-    }
-    out = {
-        "metric": "ACAN NYU-shape forward images/sec", "value": world * BATCH * args.steps / elapsed, "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (batch-sharded replicas, no collective in inference)",
-                   "precision": "fp16 channels_last cuDNN convs with folded BN and fused bias/ReLU/residual epilogues (acan_b200.inference.optimize_for_inference); attention core fp16 operands / fp32 accumulate, F and V consumed in place; fused upsample+decode+head tail in fp32",
-                   "l2": f"{n_rot} rotating input batches (138 MB) + ~190 MB of fp16 weights per step exceed the 126 MB L2; no explicit flush",
-                   "launch": launch_note},
-        "clocks": clocks,
-        "e2e": {"value": world * BATCH * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
-                "d2h_bytes_per_step": BATCH * H * W * 4, "ms_per_step": e2e_elapsed / args.steps * 1e3},
-        "gpu_launches": int(launches), "roofline": roof, **extra,
-    }
+    out = None
+    if rank == 0:
+        pk = peaks()
+        n = (H // 8) * (W // 8)
+        per_launch = lambda k: (ms[k] / max(cnt[k], 1)) * 1e-3          # noqa: E731  seconds per bracket
+        pv_flops = BATCH * 2.0 * n * n * 2048                           # a4: 2*N^2*dv per image
+        core_flops = BATCH * 5120.0 * n * n                             # a2+a4: 2*N^2*(dk+dv) per image
+        t_pv = per_launch(3)
+        t_core = per_launch(0) + per_launch(1) + per_launch(2) + per_launch(3)
+        head_bytes = BATCH * 324.0 * H * W                              # prob -> depth: (K+1)*HW*4 per image
+        t_tail = per_launch(4)                                          # in-step: fused upsample + decode_ord + head on stride-8 logits
+        from acan_b200 import ops
+        prob = torch.rand(BATCH, K, H, W, device=device)
+        t_head = ev_time(lambda: ops.head_inference(prob, "OR", "soft", DMIN, DMAX, K), iters=10)
+        del prob
+        cl = torch.channels_last
+        fcl = torch.relu(torch.randn(BATCH, 512, H // 8, W // 8, device=device)).half().contiguous(memory_format=cl)
+        vcl = torch.relu(torch.randn(BATCH, 2048, H // 8, W // 8, device=device)).half().contiguous(memory_format=cl)
+        ws_core = ops.attention_forward_cl(fcl, vcl)["ws"]
+        t_core_call = ev_time(lambda: ops.attention_forward_cl(fcl, vcl, ws=ws_core), iters=20)
+        del fcl, vcl, ws_core
+        xdec = torch.relu(torch.randn(BATCH, 2048, H // 8, W // 8, device=device)).half().contiguous(memory_format=cl)
+        with torch.no_grad():
+            t_cam = ev_time(lambda: net.decoder(xdec), iters=10)
+        del xdec
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
+        # profiles/r01b_attn_cl_4launch_pdl.ncu-rep (157.2 MB + 65.0 MB; algorithmic V 92 + P 63 MB read, O 92 MB fp16 written)
+        roof = {"bound": "tensor", "kernel": "gemm_kernel<MODE_PVT, CG=2> (aggregation O = P V on tcgen05, CTA pairs, V read in place MN-major)",
+                "achieved": pv_flops / t_pv / 1e12,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": pv_flops / t_pv / 1e12 / pk["tensor"], "traffic": 222.2e6,
+                "peak_source": pk["src"] + " (bf16 burst; the kernel is timed inside the step, so the sustained figure is given beside it)",
+                "frac_vs_sustained": (pv_flops / t_pv / 1e12 / pk["tensor_sustained"]) if pk.get("tensor_sustained") else None,
+                "launch_us": t_pv * 1e6, "launches_timed": cnt[3]}
+        extra = {
+            "attention_core": {"bound": "tensor", "what": "whole CAM core call (diagonal + fallback statistics + probability + aggregation passes), algorithmic "
+                                       "5120*N^2 FLOP/img, CUDA events around 20 stand-alone calls at the step's shape; `us_in_step` = the per-pass event "
+                                       "brackets inside the timed steps (events between the passes disable their launch overlap)",
+                               "achieved": core_flops / t_core_call / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": core_flops / t_core_call / 1e12 / pk["tensor"],
+                               "call_us": t_core_call * 1e6, "frac_in_step": core_flops / t_core / 1e12 / pk["tensor"],
+                               "us_in_step": {"pack": per_launch(0) * 1e6, "stats": per_launch(1) * 1e6, "probs": per_launch(2) * 1e6, "pv": t_pv * 1e6}},
+            "head": {"bound": "hbm", "what": "OR soft inference prob -> depth kernel, 324*HW B/img, measured stand-alone at the same shape", "achieved": head_bytes / t_head / 1e9,
+                     "peak": pk["hbm"], "unit": "GB/s", "frac": head_bytes / t_head / 1e9 / pk["hbm"], "launch_us": t_head * 1e6},
+            "tail": {"what": "fused classifier tail in the step: x8 bilinear + decode_ord + OR soft head from stride-8 logits (MUFU / shared-memory bound; "
+                             "replaces upsample 1.9 ms + layout copy 1.0 ms + decode_ord 0.22 ms + head 0.07 ms of the unfused step)", "launch_us": t_tail * 1e6},
+            "pool_branch_us": per_launch(5) * 1e6,
+            "cam_module_us": t_cam * 1e6,
+        }
+        out = {
+            "metric": "ACAN NYU-shape forward images/sec", "value": world * BATCH * args.steps / elapsed, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+            "timed_1s": {"steps": long_steps, "seconds": elapsed_long, "ms_per_step": elapsed_long / long_steps * 1e3, "value": world * BATCH * long_steps / elapsed_long},
+            "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (batch-sharded replicas, no collective in inference)",
+                       "precision": "fp16 channels_last cuDNN convs with folded BN and fused bias/ReLU/residual epilogues (acan_b200.inference.optimize_for_inference); attention core fp16 operands / fp32 accumulate, F and V consumed in place; fused upsample+decode+head tail in fp32",
+                       "l2": f"{n_rot} rotating input batches (138 MB) + ~190 MB of fp16 weights per step exceed the 126 MB L2; no explicit flush",
+                       "launch": launch_note},
+            "clocks": clocks,
+            "e2e": {"value": world * BATCH * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
+                    "d2h_bytes_per_step": BATCH * H * W * 4, "ms_per_step": e2e_elapsed / args.steps * 1e3},
+            "gpu_launches": int(launches), "roofline": roof, **extra,
+        }
+    sd_cpu = net.source_state
+    x_par = host[0][:2].contiguous().float()
+    del pred, net, dev_in
+    free_cuda()
 
-    if world == 1 and not args.no_cpu_baseline:
-        sd = net.source_state
-        threads = os.cpu_count() or 1
-        times, d_cpu = cpu_reference_forward(sd, 60, 2, threads)
-        out["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "images/s", "cores": threads, "kind": "port",
-                               "sample": f"B=1 image x {len(times)} forwards of the same network (oracle port, fp32 torch CPU ops), {sum(times):.1f} s"}
-    else:
-        out["cpu_baseline"] = None
-    print(json.dumps(out))
+    # ---- configs[3] / [4]: the training step as a sub-record (all ranks take part: it contains the gradient all-reduce)
+    train = None
+    if not args.no_train:
+        train = run_train(args, rank, world, device, lib)
+        free_cuda()
+    if rank == 0:
+        out["train"] = train
+        if world == 1 and not args.no_extras:
+            out["gpu_reference"] = gpu_reference_extras(device, sd_cpu, out["ms_per_step"], train["ms_per_step"] if train else None, out["cam_module_us"])
+            free_cuda()
+            out["c3_kitti_hard"] = c3_line(device, args.steps)
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            fn, kind = cpu_reference_callable(sd_cpu)
+            want = fn(x_par)                                  # the reference's depth for the first two images of the timed batch
+            gotd = depth_first[:2].float().cpu()
+            e_max = float((gotd - want).abs().max() / want.abs().max())
+            e_mean = float(((gotd - want).abs() / want.abs()).mean())
+            out["parity"] = {"depth_rel_err_max_norm": e_max, "depth_rel_err_mean": e_mean, "tolerance": {"max_norm": PARITY_TOL_MAX, "mean": PARITY_TOL_MEAN},
+                             "config": f"configs[1] network as benched (ResNet-101, 256x352, fp16 folded-BN), images 0-1 of timed batch 0, vs the reference's CPU path ({kind}) on the same weights",
+                             "fp32_arm": "the fp32 drop-in network holds <= 1e-3 at this config: tests/test_gpu_fullsize.py"}
+            times = time_cpu(fn, REF_SAMPLE_BATCH, 6, 1)
+            out["cpu_baseline"] = {"value": REF_SAMPLE_BATCH * len(times) / sum(times), "unit": "images/s", "cores": threads, "kind": kind,
+                                   "sample": f"bounded sample: {REF_SAMPLE_BATCH} of the step's {BATCH} images per step x {len(times)} steps of the same network ({'unmodified reference modules' if kind == 'reference' else 'oracle port'}, fp32 torch CPU ops), {sum(times):.1f} s"}
+            print(json.dumps(out))
+            assert e_max <= PARITY_TOL_MAX and e_mean <= PARITY_TOL_MEAN, f"parity of the benched network vs the reference failed: {out['parity']}"
+        else:
+            out["cpu_baseline"] = None
+            print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
