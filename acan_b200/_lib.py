@@ -26,6 +26,7 @@ SIGNATURES = {
     "acan_device_check": (c_int, []),
     "acan_launch_count": (ctypes.c_longlong, []),
     "acan_profile_begin": (c_int, [c_int]),
+    "acan_profile_begin_coarse": (c_int, [c_int]),
     "acan_profile_end": (c_int, [c_void_p, c_void_p]),
     "acan_decode_ord_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "acan_decode_ord_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),

@@ -25,8 +25,8 @@
 //              memory -> TMA store), TMEM double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1
 // persistent over a static tile schedule; CG = 2 (default) runs CTA pairs (cluster of 2, cta_group::2: a 256 x BN tile per pair).
 // The probabilities are fp16 operands (11-bit significand: the rounding of TF32, at the bf16 MMA rate) with fp32 accumulation;
-// bf16 probabilities miss the 1e-3 parity bar on sim_map.  V and dO may be bf16 (the two operand formats of a
-// kind::f16 MMA are independent fields of the instruction descriptor).
+// bf16 probabilities miss the 1e-3 parity bar on sim_map.  V and dO therefore have to be fp16 too: the instruction
+// descriptor has one format field per operand, but an fp16 x bf16 kind::f16 MMA traps as an illegal instruction on sm_100a (measured).
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cmath>
@@ -109,7 +109,7 @@ struct GemmArgs {
   float* lsum_out;     // MODE_PVT / MODE_PVT32 with l_in: [B, N] the row sums go here (training path: the divisor of the stored probabilities)
   float p_scale;       // MODE_PROBS (normalised): stored probabilities = P * p_scale (1, or kKeepScale on the training path)
   const float* ds_lsum;  // MODE_DS (channels-last backward): [B, N] sum_j of the stored fp16 probabilities; p_ij = ds_p_ij / ds_lsum_i
-  int ds_new;          //   1: scale factors come from gscale[0..3] = (s_ds, 1/s_ds, s_ds/s_op, 1/s_op), delta was computed from the packed operand
+  int ds_new;          //   1: scale factors come from gscale[0..4] = (s_ds, 1/s_ds, s_ds/s_op, 1/s_op, delta_mul)
   int pdl;             // host only: launch as a programmatic dependent of the previous kernel in the stream (one of ours, see griddep_wait)
   long long* trace;    // experiments only (ACAN_TRACE=1): per-tile clock64 stamps of CTA 0: [tile][4] = mma start, mma issued, epi start, epi end
   // MODE_STATS
@@ -149,6 +149,18 @@ __device__ __forceinline__ uint4* staged_chunk(uint8_t* buf, int r, int j) {
   return reinterpret_cast<uint4*>(buf + r * 128 + ((j ^ (r & 7)) << 4));
 }
 
+// Sum of the two fp16 values packed in `u`, WITHOUT conversion instructions: the 15 magnitude bits of each half are placed where an fp32
+// keeps its exponent / mantissa, which reads as value * 2^-112 (normal and subnormal halves alike; the probabilities are >= 0 so there is
+// no sign to carry).  The caller multiplies the accumulated sum by 2^112 once.  Two logic ops + one add per element on the full-rate
+// integer / FMA pipes -- the half -> float conversions of the obvious version share the quarter-rate pipe with the ex2 of the same
+// epilogue and made the probability pass epilogue-bound (profiles/r02_notes.md).
+__device__ __forceinline__ float half2_sum_scaled(uint32_t u) {
+  const float lo = __uint_as_float((u << 13) & 0x0fffe000u);
+  const float hi = __uint_as_float((u >> 3) & 0x0fffe000u);
+  return lo + hi;
+}
+constexpr float kHalfSumRescale = 5192296858534827628530496329220096.0f;   // 2^112
+
 // One 32-column half of a 64-column staged chunk of the un-normalised probability pass: p~ = exp2(S*c - shift_i) -> fp16 ->
 // swizzled staging row; returns the sum of the ROUNDED values (what the aggregation pass will read: measurably more accurate
 // than summing the fp32 values).  Columns >= nv lie beyond N: p~ = 0.
@@ -162,16 +174,16 @@ __device__ __forceinline__ float probs_unnorm_half(float (&v)[32], int nv, float
   uint32_t h[16];
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < 16; j += 2) {
     h[j] = pack_half2(ex2_approx(v[2 * j]), ex2_approx(v[2 * j + 1]));
-    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-    s0 += r.x;
-    s1 += r.y;
+    h[j + 1] = pack_half2(ex2_approx(v[2 * j + 2]), ex2_approx(v[2 * j + 3]));
+    s0 += half2_sum_scaled(h[j]);
+    s1 += half2_sum_scaled(h[j + 1]);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q)
     *staged_chunk(buf, row_in_tile, half * 4 + q) = make_uint4(h[q * 4 + 0], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
-  return s0 + s1;
+  return (s0 + s1) * kHalfSumRescale;
 }
 
 // max_i d_i of image b from the per-CTA maxima diag_kernel left (<= 13 values for N <= 1664)
@@ -465,14 +477,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) hh[j] = pack_half2(v[2 * j], v[2 * j + 1]);
                 if (g.lpart) {                   // training path: row sums of exactly the values the later passes will read
-                  float s0 = 0.f, s1 = 0.f;
+                  float s0 = 0.f, s1 = 0.f;      // (N % 8 == 0: a packed pair lies inside or outside the valid columns together)
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&hh[j]));
-                    s0 += (2 * j < nv) ? r.x : 0.f;
-                    s1 += (2 * j + 1 < nv) ? r.y : 0.f;
+                  for (int j = 0; j < 16; j += 2) {
+                    s0 += (2 * j < nv) ? half2_sum_scaled(hh[j]) : 0.f;
+                    s1 += (2 * j + 2 < nv) ? half2_sum_scaled(hh[j + 1]) : 0.f;
                   }
-                  l_acc += s0 + s1;
+                  l_acc += (s0 + s1) * kHalfSumRescale;
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -506,7 +517,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // ds_new (channels-last ABI): delta was computed from the operand the GEMM read; acc and delta take s_ds / s_op, the loss term s_ds.
         const float gs = g.gscale ? __ldg(g.gscale) : 1.0f;
         const float acc_mul = g.ds_new ? __ldg(g.gscale + 2) : 1.0f;
-        const float delta_i = g.ds_delta ? g.ds_delta[brow] * (g.ds_new ? acc_mul : gs) : 0.f;
+        const float delta_i = g.ds_delta ? g.ds_delta[brow] * (g.ds_new ? __ldg(g.gscale + 4) : gs) : 0.f;
         const float gks = (g.ds_gl ? __ldg(g.ds_gl) * g.ds_inv_bn : 0.f) * gs;
         const float pn = g.ds_lsum ? 1.0f / g.ds_lsum[brow] : 1.0f;       // stored probabilities -> normalised
         const bool kl = g.logbin != nullptr;
@@ -804,10 +815,12 @@ __global__ void __launch_bounds__(256) combine_l_kernel(const float* __restrict_
   }
 }
 
-// bf16 / fp32 -> fp16, same layout, clamped to the fp16 range (exact for bf16 values inside it)
+// bf16 / fp32 -> fp16, same layout, times *gscale (null = 1), clamped to the fp16 range (exact for bf16 values whose product stays a
+// normal fp16: a power-of-two scale only moves the exponent)
 template <bool SRC_BF16>
-__global__ void __launch_bounds__(256) to_half_kernel(const void* __restrict__ src, uint4* __restrict__ out, int64_t n8) {
-  auto cl = [](float x) { return fminf(fmaxf(x, -65504.f), 65504.f); };
+__global__ void __launch_bounds__(256) to_half_kernel(const void* __restrict__ src, uint4* __restrict__ out, int64_t n8, const float* __restrict__ gscale = nullptr) {
+  const float sc = gscale ? __ldg(gscale) : 1.0f;
+  auto cl = [sc](float x) { return fminf(fmaxf(x * sc, -65504.f), 65504.f); };
   for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * 256) {
     float f[8];
     if (SRC_BF16) {
@@ -1003,10 +1016,12 @@ __global__ void __launch_bounds__(256) amax_f32_kernel(const float4* __restrict_
   if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(amax_bits, __float_as_int(am));
 }
 
-// channels-last backward scales, chosen on the device: sc = (s_ds, 1/s_ds, s_ds/s_op, 1/s_op).
+// channels-last backward scales, chosen on the device: sc = (s_ds, 1/s_ds, s_ds/s_op, 1/s_op, delta_mul).
 //   s_ds brings max |dO| to 2^-2 (dS = p (dP - delta) is stored as fp16(dS * s_ds)); without an aggregation gradient it brings the
-//   attention-loss gradient scale to ~1.   s_op = s_ds when dO was packed from fp32 (scaled while packing), 1 when it is read in place.
-__global__ void gscale4_kernel(const int* __restrict__ amax_bits, int packed, const float* __restrict__ grad_loss, float inv_bn, float* __restrict__ sc) {
+//   attention-loss gradient scale to ~1.   s_op = s_ds when dO was packed to fp16 (scaled while packing), 1 when it is read in place.
+//   delta_mul takes delta to the scale of dS: s_ds when delta was computed from the unscaled gradient, s_ds / s_op from the packed one.
+__global__ void gscale4_kernel(const int* __restrict__ amax_bits, int packed, int delta_from_packed, const float* __restrict__ grad_loss, float inv_bn,
+                               float* __restrict__ sc) {
   float s = 1.0f;
   if (amax_bits != nullptr) {
     const float am = __int_as_float(*amax_bits);
@@ -1020,6 +1035,7 @@ __global__ void gscale4_kernel(const int* __restrict__ amax_bits, int packed, co
   sc[1] = 1.0f / s;
   sc[2] = s / s_op;
   sc[3] = 1.0f / s_op;
+  sc[4] = delta_from_packed ? s / s_op : s;
 }
 
 // per row: ln(bin) and ln(Z_i), Z_i = sum_j min(a_i/a_j, a_j/a_i)   (target-affinity normaliser, losses.py:40-46)
@@ -1455,8 +1471,10 @@ extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* 
   ACAN_CHECK_ARG(feat && row_stats && workspace, "acan_attn_fwd_nhwc: null pointer");
   ACAN_CHECK_ARG((value == nullptr) == (ctx == nullptr), "acan_attn_fwd_nhwc: value and ctx must be given together");
   ACAN_CHECK_ARG(feat_dtype == DT_F16 || feat_dtype == DT_BF16 || feat_dtype == DT_F32, "acan_attn_fwd_nhwc: feat_dtype %d", feat_dtype);
-  ACAN_CHECK_ARG(!value || ((value_dtype == DT_F16 || value_dtype == DT_BF16) && (ctx_dtype == DT_F16 || ctx_dtype == DT_BF16 || ctx_dtype == DT_F32)),
-                 "acan_attn_fwd_nhwc: value must be fp16 / bf16 (got %d), ctx fp16 / bf16 / fp32 (got %d)", value_dtype, ctx_dtype);
+  // (an fp16 A with a bf16 B is NOT a legal kind::f16 MMA on sm_100a although the descriptor has one format field per operand: measured,
+  //  the instruction traps as illegal -- so V shares the probabilities' format)
+  ACAN_CHECK_ARG(!value || (value_dtype == DT_F16 && (ctx_dtype == DT_F16 || ctx_dtype == DT_BF16 || ctx_dtype == DT_F32)),
+                 "acan_attn_fwd_nhwc: value must be fp16 (got %d), ctx fp16 / bf16 / fp32 (got %d)", value_dtype, ctx_dtype);
   if (int e = check_attn_shape("acan_attn_fwd_nhwc", B, N, dk, value ? dv : 0)) return e;
   ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N && H % 8 == 0 && Wd % 8 == 0), "acan_attn_fwd_nhwc: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
   ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0 && reinterpret_cast<uintptr_t>(feat) % 16 == 0 &&
@@ -1466,6 +1484,7 @@ extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* 
   if (workspace_bytes < w.bytes) return fail(ACAN_ERR_WORKSPACE, "acan_attn_fwd_nhwc: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
   if (int e = acan_device_check()) return e;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope core_scope(PROF_CORE, st);
   float2* stats = reinterpret_cast<float2*>(row_stats);
   const __half* fh = static_cast<const __half*>(feat);
   if (feat_dtype != DT_F16) {          // bf16 (autocast) / fp32 features: one elementwise pass into the workspace pack
@@ -1758,7 +1777,7 @@ BwdScratch carve_scratch(void* base, int B, int N, int dv) {
   w.ds = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * N * 2));
   w.doh = reinterpret_cast<__half*>(take(static_cast<size_t>(B) * N * dv * 2));
   w.delta = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
-  w.gscale = reinterpret_cast<float*>(take(16));
+  w.gscale = reinterpret_cast<float*>(take(32));
   w.amax_bits = reinterpret_cast<int*>(take(16));
   w.bytes = off;
   return w;
@@ -1784,8 +1803,8 @@ extern "C" size_t acan_attn_bwd_nhwc_scratch_bytes(int B, int N, int dk, int dv)
 // Backward of acan_attn_fwd_nhwc(keep = 1) (+ grad_loss * attention loss when have_loss) w.r.t. F and V, channels-last, on tcgen05:
 //   dV = P^T dO        dP = dO V^T        dS = p o (dP - delta) [+ loss term], p = P^ / lsum        dF = scale (dS + dS^T) F
 // `workspace` is the forward's: it still holds P^ (fp16(P 2^10)), lsum, the row statistics and -- after acan_attention_loss_fused or a
-// forward with a label -- ln(bin), ln Z and T_i.  V and dO are read in place as 16-bit MMA operands (fp16 or bf16, independently);
-// an fp32 grad_ctx is packed to fp16 with a power-of-two scale chosen on the device.  Four tensor-core launches, no P recompute.
+// forward with a label -- ln(bin), ln Z and T_i.  V and an fp16 dO are read in place as MMA operands; a bf16 / fp32 grad_ctx is packed to
+// fp16 times a power of two chosen on the device.  Three tensor-core launches (dV, dP -> dS, symmetrised dF), no P recompute.
 extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
                                   const void* feat_h, const void* value, int value_dtype, const float* ctx32,
                                   const void* grad_ctx, int go_dtype, int have_loss, const float* grad_loss,
@@ -1796,8 +1815,8 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
   ACAN_CHECK_ARG(!agg || (value && ctx32 && grad_value), "acan_attn_bwd_nhwc: value, ctx and grad_value are required with grad_ctx");
   ACAN_CHECK_ARG(agg || have_loss, "acan_attn_bwd_nhwc: nothing to differentiate (no grad_ctx, no loss)");
   ACAN_CHECK_ARG(!have_loss || grad_loss, "acan_attn_bwd_nhwc: the loss term needs grad_loss (device scalar)");
-  ACAN_CHECK_ARG(!agg || ((value_dtype == DT_F16 || value_dtype == DT_BF16) && (go_dtype == DT_F16 || go_dtype == DT_BF16 || go_dtype == DT_F32)),
-                 "acan_attn_bwd_nhwc: value must be fp16 / bf16, grad_ctx fp16 / bf16 / fp32");
+  ACAN_CHECK_ARG(!agg || (value_dtype == DT_F16 && (go_dtype == DT_F16 || go_dtype == DT_BF16 || go_dtype == DT_F32)),
+                 "acan_attn_bwd_nhwc: value must be fp16 (as given to the forward), grad_ctx fp16 / bf16 / fp32");
   auto dt_ok = [](int d) { return d == DT_F32 || d == DT_F16 || d == DT_BF16; };
   ACAN_CHECK_ARG(dt_ok(gf_dtype) && (!agg || dt_ok(gv_dtype)), "acan_attn_bwd_nhwc: output dtype");
   if (int e = check_attn_shape("acan_attn_bwd_nhwc", B, N, dk, dv)) return e;
@@ -1820,30 +1839,43 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
   CUtensorMap ta, ta2, tb, to;
 
   if (agg) {
-    const void* go = grad_ctx;          // the 16-bit operand the GEMMs read
-    bool go_bf16 = go_dtype == DT_BF16;
+    // dO becomes the fp16 operand of two GEMMs (against the fp16 probabilities and the fp16 values: both operands of a kind::f16 MMA must
+    // share one format).  fp16 dO is read in place; bf16 / fp32 dO is packed to fp16 times the power of two s_op that brings max |dO| to
+    // 2^-2 (exact for bf16).  delta_i = sum_c dO_ic O_ic: from the values the GEMMs read -- for bf16 that is the bf16 tensor itself (the
+    // pack is exact), for fp32 the packed tensor (the pack rounds).
+    const void* go = grad_ctx;
     ACAN_CUDA(cudaMemsetAsync(x.amax_bits, 0, 4, st));
     const int delta_grid = static_cast<int>((rows + 7) / 8);
+    const int64_t n = rows * dv;
+    int64_t pblocks = (n / 8 + 255) / 256;
+    if (pblocks > kNumSMs * 16) pblocks = kNumSMs * 16;
+    const float4* o4 = reinterpret_cast<const float4*>(ctx32);
     if (go_dtype == DT_F32) {
-      const int64_t n = rows * dv;
-      int64_t blocks = (n / 4 + 255) / 256;
-      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-      amax_f32_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const float4*>(grad_ctx), n / 4, x.amax_bits);
+      amax_f32_kernel<<<static_cast<int>(pblocks), 256, 0, st>>>(static_cast<const float4*>(grad_ctx), n / 4, x.amax_bits);
       if (int e = launch_status("amax_f32_kernel")) return e;
-      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 1, nullptr, inv_bn, x.gscale);
+      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 1, 1, nullptr, inv_bn, x.gscale);
       if (int e = launch_status("gscale4_kernel")) return e;
-      if (int e = cast_launch(static_cast<const float*>(grad_ctx), x.doh, n, x.gscale, st, "pack dO (channels-last fp16)")) return e;
-      go = x.doh; go_bf16 = false;
-      delta_nhwc_kernel<false><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), reinterpret_cast<const float4*>(ctx32), x.delta, nullptr, rows, dv);
+      to_half_kernel<false><<<static_cast<int>(pblocks), 256, 0, st>>>(grad_ctx, reinterpret_cast<uint4*>(x.doh), n / 8, x.gscale);
+      if (int e = launch_status("pack dO (fp32 -> fp16)")) return e;
+      go = x.doh;
+      delta_nhwc_kernel<false><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), o4, x.delta, nullptr, rows, dv);
       if (int e = launch_status("delta_nhwc_kernel")) return e;
+    } else if (go_dtype == DT_BF16) {
+      delta_nhwc_kernel<true><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(grad_ctx), o4, x.delta, x.amax_bits, rows, dv);
+      if (int e = launch_status("delta_nhwc_kernel")) return e;
+      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 1, 0, nullptr, inv_bn, x.gscale);
+      if (int e = launch_status("gscale4_kernel")) return e;
+      to_half_kernel<true><<<static_cast<int>(pblocks), 256, 0, st>>>(grad_ctx, reinterpret_cast<uint4*>(x.doh), n / 8, x.gscale);
+      if (int e = launch_status("pack dO (bf16 -> fp16)")) return e;
+      go = x.doh;
     } else {
-      if (go_bf16) delta_nhwc_kernel<true><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), reinterpret_cast<const float4*>(ctx32), x.delta, x.amax_bits, rows, dv);
-      else         delta_nhwc_kernel<false><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), reinterpret_cast<const float4*>(ctx32), x.delta, x.amax_bits, rows, dv);
+      delta_nhwc_kernel<false><<<delta_grid, 256, 0, st>>>(static_cast<const uint4*>(go), o4, x.delta, x.amax_bits, rows, dv);
       if (int e = launch_status("delta_nhwc_kernel")) return e;
-      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 0, nullptr, inv_bn, x.gscale);
+      gscale4_kernel<<<1, 1, 0, st>>>(x.amax_bits, 0, 0, nullptr, inv_bn, x.gscale);
       if (int e = launch_status("gscale4_kernel")) return e;
     }
-    const bool vb = value_dtype == DT_BF16;
+    const bool go_bf16 = false;
+    const bool vb = false;
     {  // dV[j, c] = 2^-10 / s_op * sum_i P^[i, j] dO[i, c]: A = P^ read MN-major (j contiguous), B = dO in place MN-major (c contiguous)
       const int bn = choose_bn(dv, B * m_tiles, cg, 64 * cg, 64 * cg);
       const int ob = gv_dtype == DT_F32 ? 4 : 2;
@@ -1866,7 +1898,7 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
       if (int e = launch_gemm<MODE_DS, 0, false>(ta, tb, to, g, st, cg)) return e;
     }
   } else {
-    gscale4_kernel<<<1, 1, 0, st>>>(nullptr, 0, grad_loss, inv_bn, x.gscale);
+    gscale4_kernel<<<1, 1, 0, st>>>(nullptr, 0, 0, grad_loss, inv_bn, x.gscale);
     if (int e = launch_status("gscale4_kernel")) return e;
     kl_ds_kernel<<<static_cast<int>(rows), 256, 0, st>>>(w.p, w.logbin, w.lnz, w.klT, x.ds, grad_loss, inv_bn, x.gscale, N, w.lsum);
     if (int e = launch_status("kl_ds_kernel")) return e;

@@ -32,7 +32,7 @@ inline int launch_status(const char* what) {
 }
 
 // optional CUDA-event brackets around kernel groups (acan_profile_begin / acan_profile_end)
-enum ProfKind { PROF_PACK = 0, PROF_STATS = 1, PROF_PROBS = 2, PROF_PV = 3, PROF_HEAD = 4, PROF_POOL = 5, PROF_KL = 6, PROF_KINDS = 7 };
+enum ProfKind { PROF_PACK = 0, PROF_STATS = 1, PROF_PROBS = 2, PROF_PV = 3, PROF_HEAD = 4, PROF_POOL = 5, PROF_KL = 6, PROF_CORE = 7, PROF_KINDS = 8 };
 void prof_mark(int kind, bool begin, cudaStream_t st);
 struct ProfScope {
   int kind; cudaStream_t st;
@@ -280,7 +280,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
 }
 
 // kind::f16 instruction descriptor: fp16 (or bf16) A/B, fp32 accumulate, M = m, N = n; each operand K-major or MN-major
-// (the two operand formats are independent descriptor fields: an fp16 A with a bf16 B is one legal kind::f16 instruction)
+// (one format field per operand, but they must agree: fp16 x bf16 traps as an illegal instruction on sm_100a)
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = 128, bool b_mn_major = false, bool a_mn_major = false, bool a_bf16 = false, bool b_bf16 = false) {
   return (1u << 4)                                         // c_format = F32
        | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) // a_format, b_format: F16 (0) / BF16 (1)

@@ -25,12 +25,15 @@ void note_launch() { ++g_launches; }
 // ---- event profiling: begin/end marks per kind, resolved at acan_profile_end
 struct ProfPair { cudaEvent_t a, b; int kind; };
 static bool g_prof_on = false;
+static bool g_prof_coarse = false;   // coarse: one bracket around a whole attention call (PROF_CORE) instead of one per pass -- events between
+                                     // the passes keep them from overlapping (programmatic dependent launch), so the two views are separate runs
 static ProfPair* g_pairs = nullptr;
 static int g_pairs_cap = 0, g_pairs_n = 0;
 static int g_open[PROF_KINDS];
 
 void prof_mark(int kind, bool begin, cudaStream_t st) {
   if (!g_prof_on) return;
+  if (g_prof_coarse ? (kind <= PROF_PV) : (kind == PROF_CORE)) return;
   if (begin) {
     if (g_pairs_n >= g_pairs_cap) { g_open[kind] = -1; return; }
     ProfPair& p = g_pairs[g_pairs_n];
@@ -59,7 +62,14 @@ extern "C" int acan_profile_begin(int max_marks) {
   }
   g_pairs_n = 0;
   for (int k = 0; k < PROF_KINDS; ++k) g_open[k] = -1;
+  g_prof_coarse = false;
   g_prof_on = true;
+  return 0;
+}
+
+extern "C" int acan_profile_begin_coarse(int max_marks) {
+  if (int e = acan_profile_begin(max_marks)) return e;
+  acan::g_prof_coarse = true;
   return 0;
 }
 

@@ -32,12 +32,15 @@ def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
 
 
 class FusedConv(nn.Module):
-    """conv + bias (+ residual) (+ ReLU) as one cuDNN call on fp16 channels_last tensors."""
+    """conv + bias (+ residual) (+ ReLU) as one cuDNN call on channels_last tensors (fp16 by default; fp32 for the parity arm)."""
 
-    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, stride, padding, dilation, relu: bool):
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor, stride, padding, dilation, relu: bool, dtype: torch.dtype = torch.float16):
         super().__init__()
-        self.register_buffer("weight", weight.to(torch.float16).contiguous(memory_format=torch.channels_last))
-        self.register_buffer("bias", bias.to(torch.float16).contiguous())
+        # fp32 stays NCHW: on this stack (torch 2.11 / cuDNN 9) an fp32 3x3 convolution with channels_last weights and TF32 disabled
+        # returns garbage (DESIGN.md section 4, deviation 3); channels_last is used in half precision only
+        fmt = torch.channels_last if dtype == torch.float16 else torch.contiguous_format
+        self.register_buffer("weight", weight.to(dtype).contiguous(memory_format=fmt))
+        self.register_buffer("bias", bias.to(dtype).contiguous())
         self.stride, self.padding, self.dilation, self.relu = tuple(stride), tuple(padding), tuple(dilation), relu
         self._fused_ok = True
 
@@ -56,11 +59,11 @@ class FusedConv(nn.Module):
 
 
 class FusedBottleneck(nn.Module):
-    def __init__(self, blk: Bottleneck):
+    def __init__(self, blk: Bottleneck, dtype: torch.dtype = torch.float16):
         super().__init__()
         def fc(conv, bn, relu):
             w, b = fold_conv_bn(conv, bn)
-            return FusedConv(w, b, conv.stride, conv.padding, conv.dilation, relu)
+            return FusedConv(w, b, conv.stride, conv.padding, conv.dilation, relu, dtype)
         self.c1, self.c2 = fc(blk.conv1, blk.bn1, True), fc(blk.conv2, blk.bn2, True)
         w3, b3 = fold_conv_bn(blk.conv3, blk.bn3)
         self.project = None
@@ -69,9 +72,9 @@ class FusedBottleneck(nn.Module):
             # itself runs bias-free -- a convolution without a fused activation would otherwise pay a separate broadcast-add pass
             wp, bp = fold_conv_bn(blk.downsample[0], blk.downsample[1])
             b3 = b3 + bp
-            self.project = FusedConv(wp, bp, blk.downsample[0].stride, blk.downsample[0].padding, blk.downsample[0].dilation, False)
+            self.project = FusedConv(wp, bp, blk.downsample[0].stride, blk.downsample[0].padding, blk.downsample[0].dilation, False, dtype)
             self.project.bias = None
-        self.c3 = FusedConv(w3, b3, blk.conv3.stride, blk.conv3.padding, blk.conv3.dilation, True)
+        self.c3 = FusedConv(w3, b3, blk.conv3.stride, blk.conv3.padding, blk.conv3.dilation, True, dtype)
 
     def forward(self, x):
         skip = x if self.project is None else self.project(x)
@@ -79,17 +82,29 @@ class FusedBottleneck(nn.Module):
 
 
 class InferenceNet(nn.Module):
-    """frozen fp16 channels_last network: fused backbone -> SADecoder (half-precision kernel path) -> fused tail."""
+    """frozen channels_last network: fused backbone -> SADecoder -> fused tail.  dtype fp16 (default): the benched configuration, the CAM on
+    its half-precision in-place kernel path.  dtype fp32: the PARITY arm -- the same folded convolutions in strict fp32 (run it with TF32
+    off), the CAM through the drop-in module's generic path (fp16 tensor-core operands, fp32 in / out): <= 1e-3 on depth against the
+    reference at the benched configuration, where 101 layers of fp16 activations cannot be."""
 
-    def __init__(self, net: ResNet):
+    def __init__(self, net: ResNet, dtype: torch.dtype = torch.float16):
         super().__init__()
         if net.use_inter:
             raise NotImplementedError("optimize_for_inference: the auxiliary (alpha != 0) branch is a training-time output")
+        self.dtype = dtype
         w, b = fold_conv_bn(net.conv1, net.bn1)
-        self.stem = FusedConv(w, b, net.conv1.stride, net.conv1.padding, net.conv1.dilation, True)
+        self.stem = FusedConv(w, b, net.conv1.stride, net.conv1.padding, net.conv1.dilation, True, dtype)
         self.maxpool = net.maxpool
-        self.blocks = nn.Sequential(*[FusedBottleneck(blk) for layer in (net.layer1, net.layer2, net.layer3, net.layer4) for blk in layer])
+        self.blocks = nn.Sequential(*[FusedBottleneck(blk, dtype) for layer in (net.layer1, net.layer2, net.layer3, net.layer4) for blk in layer])
         self.decoder = copy.deepcopy(net.decoder)
+        if dtype != torch.float16:
+            self.classifier_conv = copy.deepcopy(net.classifier.conv)
+            self.min_depth, self.max_depth, self.num_classes = net.min_depth, net.max_depth, net.num_classes
+            self.classifierType, self.inferenceType = net.classifierType, net.inferenceType
+            self.eval()
+            for p in self.parameters():
+                p.requires_grad_(False)
+            return
         key = self.decoder.saconv.f_key                 # F = ReLU(BN(conv(x))) -> one fused call as well
         wk, bk = fold_conv_bn(key.conv, key.bn)
         self.decoder.saconv.fused_key = FusedConv(wk, bk, key.conv.stride, key.conv.padding, key.conv.dilation, True)
@@ -105,10 +120,10 @@ class InferenceNet(nn.Module):
             p.requires_grad_(False)
 
     def _features(self, x):
-        x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last if self.dtype == torch.float16 else torch.contiguous_format)
         x = self.stem(x)
         mp = self.maxpool
-        if (mp.kernel_size, mp.stride, mp.padding, mp.dilation, mp.ceil_mode) == (3, 2, 1, 1, False) and x.shape[1] % 8 == 0:
+        if self.dtype == torch.float16 and (mp.kernel_size, mp.stride, mp.padding, mp.dilation, mp.ceil_mode) == (3, 2, 1, 1, False) and x.shape[1] % 8 == 0:
             from . import ops
             x = ops.maxpool3x3s2_cl(x)                      # 3x3 / 2 max pooling of the channels_last stem output in one HBM pass
         else:
@@ -154,11 +169,14 @@ class InferenceNet(nn.Module):
         return self.inference(self.forward(x))
 
 
-def optimize_for_inference(net: ResNet) -> InferenceNet:
-    """frozen, BN-folded, fused-epilogue fp16 copy of ``net`` (which must hold calibrated / trained BN statistics)."""
+def optimize_for_inference(net: ResNet, dtype: torch.dtype = torch.float16) -> InferenceNet:
+    """frozen, BN-folded, fused-epilogue copy of ``net`` (which must hold calibrated / trained BN statistics): fp16 (the benched
+    configuration) or fp32 (the parity arm, see InferenceNet)."""
     if not isinstance(net, ResNet):
         raise TypeError("optimize_for_inference expects an acan_b200.network.ResNet")
-    return InferenceNet(net.eval())
+    if dtype not in (torch.float16, torch.float32):
+        raise ValueError("optimize_for_inference: dtype must be torch.float16 or torch.float32")
+    return InferenceNet(net.eval(), dtype)
 
 
 class StreamedPredictor:

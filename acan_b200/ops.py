@@ -400,7 +400,8 @@ def _nhwc_dense(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.T
 def attention_forward_train(feat: torch.Tensor, value: torch.Tensor, dis_label: Optional[torch.Tensor] = None):
     """Training-mode attention (acan_attn_fwd_nhwc, keep = 1) on whatever the projections produced:
       feat  [B,dk,h,w]  fp16 channels_last is read in place; bf16 / fp32 take one pass into the workspace's fp16 pack
-      value [B,dv,h,w]  fp16 / bf16 channels_last is read in place (bf16 stays bf16: mixed-format MMA); fp32 is rounded to fp16
+      value [B,dv,h,w]  fp16 channels_last is read in place; bf16 (the autocast step: exact) / fp32 take one cast (+ transpose) copy to
+                        fp16 -- both operands of a kind::f16 MMA must share one format, and the probabilities need fp16's 11 bits
     Returns dict(ctx32 [B,h,w,dv] fp32, row_stats, loss | None, ws, feat_pack [B,h,w,dk] fp16 | None, value16 [B,h,w,dv]).
     The workspace is NEW for every call and belongs to the caller's autograd node: it keeps the probabilities for the backward pass."""
     if not (feat.is_cuda and value.is_cuda):
@@ -409,7 +410,7 @@ def attention_forward_train(feat: torch.Tensor, value: torch.Tensor, dis_label: 
     dv = value.shape[1]
     n = h * w
     f = _nhwc_dense(feat.detach(), None if feat.dtype in (torch.float16, torch.bfloat16) else torch.float16)
-    v = _nhwc_dense(value.detach(), value.dtype if value.dtype in (torch.float16, torch.bfloat16) else torch.float16)
+    v = _nhwc_dense(value.detach(), torch.float16)
     ws = AttnWorkspace(b, n, dk, dv, f.device)
     ws.scale = float(dk) ** -0.5
     ctx32 = torch.empty((b, h, w, dv), device=f.device, dtype=torch.float32)

@@ -50,9 +50,13 @@ long long   acan_launch_count(void);
 /* Measurement hooks: between acan_profile_begin and acan_profile_end every kernel group is bracketed by a pair of
  * CUDA events recorded on the caller's stream.  acan_profile_end waits for them and returns, per group,
  * the summed device time in ms and the number of brackets.  Groups (ACAN_PROF_*): 0 operand pack, 1 affinity
- * statistics pass, 2 probability pass, 3 aggregation (P.V) pass, 4 head, 5 pooling branch, 6 materialised KL. */
-#define ACAN_PROF_KINDS 7
+ * statistics pass, 2 probability pass, 3 aggregation (P.V) pass, 4 head, 5 pooling branch, 6 materialised KL, 7 a whole
+ * channels-last attention forward call.  acan_profile_begin brackets groups 0-6; acan_profile_begin_coarse brackets groups 4-7,
+ * i.e. the attention call as ONE region: events between its passes would serialise them (they are chained by programmatic
+ * dependent launch), so the per-pass and the whole-call views are taken in separate runs. */
+#define ACAN_PROF_KINDS 8
 int acan_profile_begin(int max_marks);
+int acan_profile_begin_coarse(int max_marks);
 int acan_profile_end(float* ms_by_kind_host, int* count_by_kind_host);
 
 /* ---------------------------------------------------------------- depth head ---------- */
@@ -234,8 +238,8 @@ int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h,
 
 /* General channels-last form (the training step's entry; acan_attn_fwd_nhwc_f16 is this call with fp16 everywhere and keep = 0).
  * Element types (ACAN_DT_*): feat fp16 (read in place), bf16 or fp32 (one elementwise pass into the workspace's fp16 pack);
- * value fp16 or bf16, read in place (the two operand formats of a kind::f16 MMA are independent: fp16 probabilities x bf16 values
- * is one instruction); ctx fp16, bf16 or fp32.
+ * value fp16, read in place (an fp16 x bf16 kind::f16 MMA traps as an illegal instruction on sm_100a although the descriptor has one
+ * format field per operand, and the probabilities need fp16's 11 bits: a bf16 pipeline converts V once, exactly); ctx fp16, bf16 or fp32.
  *   keep = 0  inference: statistics-free probability pass when neither sim_map nor the loss is requested.
  *   keep = 1  training (autograd through sadecoder.py:42-49, 80-90): exact two-pass row statistics; the normalised probabilities stay
  *             in the workspace as fp16(P * 2^10) together with the row sums of those rounded values, which is the divisor used by
@@ -255,9 +259,9 @@ int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* value, int 
  *               acan_attention_loss_fused (or a forward with a label) left there: ln(bin), ln Z, the in-window target mass T_i
  *   scratch     acan_attn_bwd_nhwc_scratch_bytes(), 1024-byte aligned (dS, an fp16 pack of an fp32 grad_ctx, delta, scales)
  *   feat_h      [B,N,dk] fp16 as given to the forward (NULL: the workspace pack, when the forward converted bf16 / fp32 features)
- *   value       [B,N,dv] fp16 / bf16 as given to the forward, ctx32 [B,N,dv] fp32 the forward's output
- *   grad_ctx    [B,N,dv] fp16 / bf16 (read in place as an MMA operand) or fp32 (packed to fp16 with a power-of-two scale chosen on
- *               the device); NULL when only the attention loss is differentiated
+ *   value       [B,N,dv] fp16 as given to the forward (value_dtype must be ACAN_DT_F16), ctx32 [B,N,dv] fp32 the forward's output
+ *   grad_ctx    [B,N,dv] fp16 (read in place as an MMA operand), or bf16 / fp32 (packed to fp16 times a power of two chosen on the
+ *               device from max |dO|: exact for bf16); NULL when only the attention loss is differentiated
  *   have_loss   adds *grad_loss (DEVICE scalar) * d(attention loss)/dF
  *   grad_feat   [B,N,dk], grad_value [B,N,dv]; fp32 / fp16 / bf16 each.
  * delta_i is computed from the very operand the dP GEMM reads and dS is formed with p = P^/lsum, so sum_j dS_ij = 0 holds for the

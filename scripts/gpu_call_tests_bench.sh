@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-P=gpurun_out/r02_c2
+P=gpurun_out/r02_c3
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -rA -k "training_path or row_sums or legacy_fp32" > ${P}_train_tests.log 2>&1; echo "exit $?" >> ${P}_train_tests.log
 timeout 1200 python -m pytest tests/test_gpu_reference.py -m gpu -q -rA -s > ${P}_ref_tests.log 2>&1; echo "exit $?" >> ${P}_ref_tests.log
 timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -q -rA -s > ${P}_full_tests.log 2>&1; echo "exit $?" >> ${P}_full_tests.log

@@ -483,8 +483,9 @@ def _oracle_grads(f, v, go, dis, gl):
 @pytest.mark.parametrize("b,h,w,dk,dv", [(2, 4, 6, 128, 256), (1, 28, 38, 512, 2048), (2, 16, 16, 512, 2048), (1, 32, 44, 512, 2048)])
 def test_attention_training_path_against_oracle_autograd(b, h, w, dk, dv, v_dtype):
     """Channels-last training path (acan_attn_fwd_nhwc keep=1 + acan_attention_loss_fused + acan_attn_bwd_nhwc), operands read in place
-    (fp16 F, bf16 or fp16 V / dO: the bf16 case is a mixed-format MMA against the fp16 probabilities), vs fp64 autograd through the
-    oracle on the same values: context and all gradients <= 1e-3 max-norm relative, at the reference's channel counts and at a toy size."""
+    (fp16 F; fp16 V / dO read in place, or bf16 V / dO as the autocast step hands them over: converted to fp16 exactly -- dO with a
+    device-chosen power-of-two scale), vs fp64 autograd through the oracle on the same values: context and all gradients <= 1e-3
+    max-norm relative, at the reference's channel counts and at a toy size."""
     from acan_b200 import functions as fn
     from acan_b200.modules import AttentionLoss2d, LazySimMap, _Holder
     f, v, go, dis = _train_inputs(b, h, w, dk, dv, torch.float16, v_dtype)
