@@ -134,10 +134,18 @@ def test_install_on_reference_built_network_forward_backward():
         # which amplify the attention core's fp16-operand rounding (measured worst case: conv1.weight 9.4e-3)
         assert e <= (5e-3 if name.startswith(("decoder", "classifier")) else 2e-2), (name, e)
     print(f"\ninstall() on a reference-built ResNet-50: worst parameter-gradient error vs the reference on the same GPU {worst:.2e}")
-    # eval: the lazy head / fused tail against the reference's full-resolution path
+    # eval: the lazy head / fused tail against the reference's full-resolution path -- on CALIBRATED running statistics (SURVEY section 8d:
+    # with the synthetic ones the logits exceed 88 and the reference's unstabilised decode_ord returns NaN)
+    for m in list(rnet.modules()) + list(net.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+    with torch.no_grad():
+        rnet(x), net(x)
     rnet.eval(), net.eval()
     with torch.no_grad():
-        close(net.inference(net(x)), rnet.inference(rnet(x)))
+        want_d = rnet.inference(rnet(x))
+        assert bool(torch.isfinite(want_d).all())
+        close(net.inference(net(x)), want_d)
 
 
 def _load(module, g):
