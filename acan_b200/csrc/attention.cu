@@ -340,7 +340,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint8_t* const buf = out_stage + group * kOutChunkBytes;
     const int bar_id = 1 + group;
     uint32_t acc = 0, acc_phase = 0;
-    if (MODE == MODE_PROBS && g.unnorm) {                 // per-image diagonal maxima, once per CTA (epilogue warps only)
+    if (MODE == MODE_PROBS && g.unnorm == 1) {            // per-image diagonal maxima, once per CTA (epilogue warps only)
       const int t = threadIdx.x - 64;
       if (t < g.batch && t < kDmaxSlots) dmax_s[t] = image_dmax(g.dpart, g.n_dpart, t);
       named_bar_sync(3, 256);
@@ -388,7 +388,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       } else if constexpr (MODE == MODE_PROBS) {
         float m2 = 0.f, inv_l = 0.f, la_i = 0.f, lnz_i = 0.f, log2_l = 0.f;
         const size_t brow = static_cast<size_t>(b) * g.m_rows + (row_ok ? row : 0);
-        if (g.unnorm) {
+        if (g.unnorm == 2) {
+          // training path: exact statistics are known; folding the normalisation into the shift, p^ = exp2(S c - (m + log2 l - log2 p_scale)),
+          // gives fp16(P * p_scale) through the same light epilogue as the inference path (no per-element multiply, no second branch)
+          inv_l = 1.0f;
+          const float2 st = g.stats[brow];
+          m2 = st.x + lg2_approx(st.y) - lg2_approx(g.p_scale);
+        } else if (g.unnorm) {
           // Cauchy-Schwarz shift (see diag_kernel); images above the safe bound take the exact row maximum the fallback
           // statistics pass left in `part` (same tile width, so the same 2 * n_tiles partials per row)
           inv_l = 1.0f;
@@ -690,6 +696,288 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ fused inference forward (one persistent launch)
+// The probability pass is bound by its epilogue (one ex2 per element on the quarter-rate pipe, ~7 k cycles per 128 x 256 tile against a
+// ~5 k-cycle mainloop), the aggregation pass by the L2 -> SM operand feed (light epilogue).  As two launches each pays for its own
+// bottleneck and for its own wave quantisation (7.8 -> 8 and 10.4 -> 11 waves at configs[1]).  Here ONE persistent grid of CTA pairs
+// walks a static list in which the probability tiles of image b+1 are interleaved with the aggregation tiles of image b: while a pair's
+// epilogue warps chew on a probability tile, its MMA warp is already feeding the next (aggregation) tile, so the ex2 work hides under the
+// operand feed, and there is one tail instead of two.  P~ still makes its fp16 round trip through L2 (the aggregation accumulator of a
+// query tile, 128 x 2048 fp32, is four times the TMEM of an SM: see the header), but nothing returns to the host in between.
+//
+// Ordering: an aggregation tile (b, mt) reads the 256 rows of P~ that the probability tiles (b, mt, *) wrote -- from other SMs.  Every
+// epilogue group of a probability tile, once its TMA stores have COMPLETED (cp.async.bulk.wait_group 0, not .read) and its row-sum
+// partials are written, bumps done[b][mt] with a release; the TMA producer of an aggregation tile spins (acquire, bounded) until the
+// count is nP x 2 groups x 2 CTAs, then crosses to the async proxy and loads.  The list is walked in increasing order by every pair and
+// every dependency points backwards in it, so the wait cannot cycle (the grid is co-resident: <= 1 CTA per SM, clusters of 2).
+struct FusedArgs {
+  int batch, n, dv;
+  int mP, nP, nV;          // tiles per image: probability mP x nP (256 x 256), aggregation mP x nV
+  int kP, kV;              // 64-deep k-steps: dk / 64, ceil(N / 64)
+  int stages;
+  uint32_t idesc_p, idesc_v;
+  float c;
+  const float* dpart; int n_dpart;
+  const float* diag;
+  const float2* part;      // exact per-(key tile, group) maxima of images above the safe bound (fallback statistics pass)
+  float2* stats_w; float2* stats_w2;
+  float* lpart;            // [B, 2 nP, N]
+  int* done;               // [B, mP] zeroed by the host before the launch
+  int out_bf16;
+};
+
+struct FusedTile { int type, b, mt, nt; };   // type 0: probability tile, 1: aggregation tile
+
+__device__ __forceinline__ FusedTile fused_decode(const FusedArgs& g, int t) {
+  const int TP = g.mP * g.nP, TV = g.mP * g.nV, TS = TP + TV;
+  FusedTile r;
+  int idx;
+  if (t < TP) { r.type = 0; r.b = 0; idx = t; }
+  else {
+    const int u = t - TP;
+    const int s = u / TS, j = u - s * TS;            // segment s + 1: aggregation tiles of image s, probability tiles of image s + 1
+    if (s < g.batch - 1) {
+      const int cp1 = ((j + 1) * TP) / TS, cp0 = (j * TP) / TS;   // probability tiles spread evenly through the segment
+      if (cp1 > cp0) { r.type = 0; r.b = s + 1; idx = cp0; }
+      else { r.type = 1; r.b = s; idx = j - cp0; }
+    } else { r.type = 1; r.b = g.batch - 1; idx = u - (g.batch - 1) * TS; }
+  }
+  const int nn = r.type == 0 ? g.nP : g.nV;
+  r.mt = idx / nn;
+  r.nt = idx - r.mt * nn;
+  return r;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_v,
+                 const __grid_constant__ CUtensorMap tmap_o, const FusedArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr uint32_t a_bytes = BM * BK * 2, b_bytes = 128 * BK * 2, stage_bytes = a_bytes + b_bytes;   // BN = 256: each CTA stages half of B
+  constexpr int BN = 256;
+  uint8_t* out_stage = smem + static_cast<size_t>(g.stages) * stage_bytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(out_stage + kOutBuffers * kOutChunkBytes);
+  float* const dmax_s = bars->dmax;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+  const uint32_t cta_rank = cluster_ctarank();
+  const int total_tiles = g.batch * g.mP * (g.nP + g.nV);
+  const int first_tile = blockIdx.x / 2, tile_step = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_f); tma_prefetch_desc(&tmap_p); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_o); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars->tmem_full[s], 1); mbar_init(&bars->tmem_empty[s], 16); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const FusedTile T = fused_decode(g, tile);
+        const int a_row = (T.mt * 2 + static_cast<int>(cta_rank)) * BM;
+        const int b_row = T.nt * BN + static_cast<int>(cta_rank) * 128;
+        if (T.type == 1) {     // the probabilities of this row block must be in L2, written by other SMs' TMA stores
+          const int* flag = g.done + T.b * g.mP + T.mt;
+          const int want = g.nP * 4;
+          if (ld_acquire_gpu(flag) < want) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(flag) < want) {
+              __nanosleep(64);
+              if (clock64() - t0 > 4000000000LL) { printf("acan: fused forward: dependency timeout (image %d row block %d)\n", T.b, T.mt); __trap(); }
+            }
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy acquire -> the async-proxy (TMA) loads that follow
+        }
+        const int ksteps = T.type == 0 ? g.kP : g.kV;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          if (cta_rank == 0) mbar_expect_tx(&bars->full[stage], stage_bytes * 2);
+          const uint32_t leader_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+          if (T.type == 0) {
+            tma_load_3d_2sm(sa, &tmap_f, leader_bar, ks * BK, a_row, T.b);
+            tma_load_3d_2sm(sa + a_bytes, &tmap_f, leader_bar, ks * BK, b_row, T.b);
+          } else {
+            tma_load_3d_2sm(sa, &tmap_p, leader_bar, ks * BK, a_row, T.b);
+            tma_load_3d_2sm(sa + a_bytes, &tmap_v, leader_bar, b_row, ks * BK, T.b);
+            tma_load_3d_2sm(sa + a_bytes + 8192, &tmap_v, leader_bar, b_row + 64, ks * BK, T.b);
+          }
+          if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta_rank == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const FusedTile T = fused_decode(g, tile);
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+        const int ksteps = T.type == 0 ? g.kP : g.kV;
+        const uint32_t idesc = T.type == 0 ? g.idesc_p : g.idesc_v;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_k_sw128(sa + k * UMMA_K * 2);
+            const uint64_t db = T.type == 0 ? umma_desc_k_sw128(sb + k * UMMA_K * 2) : umma_desc_mn_sw128(sb + k * UMMA_K * 128, 8192);
+            umma_f16_2sm(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&bars->empty[stage], 3);
+          if (++stage == static_cast<uint32_t>(g.stages)) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&bars->tmem_full[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3, group = (warp - 2) >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    const bool store_leader = ((threadIdx.x - 64) & 127) == 0;
+    uint8_t* const buf = out_stage + group * kOutChunkBytes;
+    const int bar_id = 1 + group;
+    uint32_t acc = 0, acc_phase = 0;
+    {
+      const int t = threadIdx.x - 64;
+      if (t < g.batch && t < kDmaxSlots) dmax_s[t] = image_dmax(g.dpart, g.n_dpart, t);
+      named_bar_sync(3, 256);
+    }
+    const uint32_t leader_empty0 = mapa_u32(smem_u32(&bars->tmem_empty[0]), 0), leader_empty1 = mapa_u32(smem_u32(&bars->tmem_empty[1]), 0);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const FusedTile T = fused_decode(g, tile);
+      const int row0 = (T.mt * 2 + static_cast<int>(cta_rank)) * BM;
+      const int row = row0 + row_in_tile;
+      const bool row_ok = row < g.n;
+      const int col0 = T.nt * BN;
+      const int ncols = T.type == 0 ? g.n : g.dv;
+      const int nvalid = min(BN, ncols - col0);
+      const int chunks = (nvalid + 31) >> 5;
+      const size_t brow = static_cast<size_t>(T.b) * g.n + (row_ok ? row : 0);
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kMaxBN;
+      if (T.type == 0) {
+        float m2;
+        const float dmax = T.b < kDmaxSlots ? dmax_s[T.b] : image_dmax(g.dpart, g.n_dpart, T.b);
+        if (dmax <= kSafeDiagMax) {
+          m2 = sqrtf(g.diag[brow] * dmax) - kShiftHeadroom;
+        } else {
+          m2 = -INFINITY;
+          const float2* pp = g.part + static_cast<size_t>(T.b) * (2 * g.nP) * g.n + (row_ok ? row : 0);
+          for (int t = 0; t < 2 * g.nP; ++t) m2 = fmaxf(m2, pp[static_cast<size_t>(t) * g.n].x);
+        }
+        if (row_ok && T.nt == 0 && group == 0) {
+          g.stats_w[brow].x = m2;
+          if (g.stats_w2) g.stats_w2[brow].x = m2;
+        }
+        float l_acc = 0.f;
+        for (int ch = 2 * group; ch < chunks; ch += 4) {
+          float v0[32], v1[32];
+          const bool two = ch + 1 < chunks;
+          tmem_ld_32x32(taddr + ch * 32, v0);
+          if (two) tmem_ld_32x32(taddr + (ch + 1) * 32, v1);
+          if (store_leader) tma_store_wait_read<0>();
+          tmem_ld_wait();
+          named_bar_sync(bar_id, 128);
+          l_acc += probs_unnorm_half(v0, nvalid - ch * 32, g.c, m2, buf, row_in_tile, 0);
+          if (two) l_acc += probs_unnorm_half(v1, nvalid - (ch + 1) * 32, g.c, m2, buf, row_in_tile, 1);
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (store_leader) {
+            tma_store_3d(&tmap_p, buf, col0 + ch * 32, row0, T.b);
+            tma_store_commit();
+          }
+        }
+        if (row_ok) g.lpart[(static_cast<size_t>(T.b) * (2 * g.nP) + 2 * T.nt + group) * g.n + row] = l_acc;
+        // accumulator can go back to the MMA warp before the stores have landed
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);
+        // publish: stores complete -> (group barrier: every thread's row-sum partial is written) -> release
+        if (store_leader) tma_store_wait_all();
+        named_bar_sync(bar_id, 128);
+        if (store_leader) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          red_release_gpu_add(g.done + T.b * g.mP + T.mt, 1);
+        }
+      } else {
+        const int l_parts = 2 * g.nP;
+        const float* lp = g.lpart + static_cast<size_t>(T.b) * l_parts * g.n + (row_ok ? row : 0);
+        float l = 0.f;
+        for (int t = 0; t < l_parts; ++t) l += __ldcg(lp + static_cast<size_t>(t) * g.n);     // written by other SMs in this launch: L2, not L1
+        const float rs = 1.0f / l;
+        if (row_ok && T.nt == 0 && group == 0) {
+          g.stats_w[brow].y = l;
+          if (g.stats_w2) g.stats_w2[brow].y = l;
+        }
+        for (int ch = 2 * group; ch < chunks; ch += 4) {
+          float v[2][32];
+          const bool two = ch + 1 < chunks;
+          tmem_ld_32x32(taddr + ch * 32, v[0]);
+          if (two) tmem_ld_32x32(taddr + (ch + 1) * 32, v[1]);
+          if (store_leader) tma_store_wait_read<0>();
+          tmem_ld_wait();
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (half == 0 || two) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *staged_chunk(buf, row_in_tile, half * 4 + q) =
+                    make_uint4(pack16(v[half][q * 8 + 0] * rs, v[half][q * 8 + 1] * rs, g.out_bf16), pack16(v[half][q * 8 + 2] * rs, v[half][q * 8 + 3] * rs, g.out_bf16),
+                               pack16(v[half][q * 8 + 4] * rs, v[half][q * 8 + 5] * rs, g.out_bf16), pack16(v[half][q * 8 + 6] * rs, v[half][q * 8 + 7] * rs, g.out_bf16));
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (store_leader) {
+            tma_store_3d(&tmap_o, buf, col0 + ch * 32, row0, T.b);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (store_leader) tma_store_wait_all();
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
@@ -1178,6 +1466,7 @@ struct Workspace {
   float* lsum;     // [B, N]  their total: the divisor that makes the stored rows sum to exactly 1 (aggregation, backward)
   float* klw_part; // [B, 2*ceil(N/kMinBN), N]  partial in-window target mass (attention loss)
   float* klT;      // [B, N]  T_i = sum_j W_ij [W_ij / Q_ij inside the clamp window]: left by the loss forward for the backward
+  int* done;       // [B, ceil(N/256)]  fused forward: completed probability-tile epilogues per 256-row block
   size_t bytes;
 };
 
@@ -1204,6 +1493,7 @@ Workspace carve(void* base, int B, int N, int dk, int dv) {
   w.lsum = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
   w.klw_part = reinterpret_cast<float*>(take(static_cast<size_t>(B) * nt_max * N * 4));
   w.klT = reinterpret_cast<float*>(take(static_cast<size_t>(B) * N * 4));
+  w.done = reinterpret_cast<int*>(take(static_cast<size_t>(B) * ((N + 255) / 256) * 4));
   w.bytes = off;
   return w;
 }
@@ -1293,7 +1583,10 @@ int run_affinity(const Workspace& w, const __half* fh, float2* stats, bool want_
     g.lnz = w.lnz;
     g.kl_part = w.kl_part;
     g.klw_part = klw_part;
-    if (keep && want_p) { g.p_scale = kKeepScale; g.lpart = w.lpart; }
+    if (keep && want_p) {
+      g.p_scale = kKeepScale; g.lpart = w.lpart;
+      if (!kl && !sim_map) { g.unnorm = 2; g.pdl = 1; }     // plain probability pass: the light epilogue, chained to the statistics kernels
+    }
 #ifdef ACAN_EXPERIMENT
     static long long* trace_buf = nullptr;
     if (env_int("ACAN_TRACE", 0) && !trace_buf) cudaMalloc(&trace_buf, 512 * sizeof(long long));
@@ -1366,6 +1659,74 @@ int run_affinity_fast(const Workspace& w, const __half* fh, float2* stats, int B
   }
   *l_parts = 2 * g.n_tiles;
   return 0;
+}
+
+// Inference forward as ONE persistent launch behind the diagonal / fallback-statistics kernels (fused_fwd_kernel): probability and
+// aggregation tiles interleaved, CTA pairs, 256 x 256 tiles.  V and O are channels-last 16-bit, dv a multiple of 256.
+int run_fused_forward(const Workspace& w, const __half* fh, const void* value, void* ctx, bool out_bf16, float2* stats, int B, int N, int dk, int dv,
+                      float scale, cudaStream_t st) {
+  constexpr int BN = 256;
+  const int mP = (N + 255) / 256, nP = (N + BN - 1) / BN, nV = dv / BN;
+  CUtensorMap tf, tfb, tp, tv, to;
+  if (int e = make_tmap(&tf, fh, 2, dk, N, B, static_cast<size_t>(dk) * 2, static_cast<size_t>(N) * dk * 2, BM)) return e;
+  if (int e = make_tmap(&tp, w.p, 2, N, N, B, static_cast<size_t>(N) * 2, static_cast<size_t>(N) * N * 2, BM)) return e;
+  if (int e = make_tmap(&tv, value, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, 64)) return e;
+  if (int e = make_tmap(&to, ctx, 2, dv, N, B, static_cast<size_t>(dv) * 2, static_cast<size_t>(N) * dv * 2, BM, out_bf16)) return e;
+  tfb = tf;
+  const float c = scale * kLog2e;
+  const int n_dpart = (N + kDiagRows - 1) / kDiagRows;
+  {
+    ProfScope ps(PROF_STATS, st);
+    ACAN_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(B) * mP * sizeof(int), st));
+    diag_kernel<<<dim3(n_dpart, B), kDiagThreads, 0, st>>>(fh, w.diag, w.dpart, N, dk, c);
+    if (int e = launch_status("diag_kernel")) return e;
+    // fallback statistics (exact row maxima of images whose diagonal exceeds the safe bound): same 256-wide key tiles as the fused kernel
+    GemmArgs g;
+    std::memset(&g, 0, sizeof(g));
+    g.batch = B; g.m_tiles = mP; g.n_tiles = nP; g.k_steps = dk / BK;
+    g.m_rows = N; g.n_cols = N; g.bn = BN; g.idesc = umma_idesc_f16(BN, BM * 2); g.c = c;
+    g.part = w.part; g.dpart = w.dpart; g.n_dpart = n_dpart; g.pdl = 1;
+    if (int e = launch_gemm<MODE_STATS>(tf, tfb, tp, g, st, 2)) return e;
+  }
+  FusedArgs f;
+  std::memset(&f, 0, sizeof(f));
+  f.batch = B; f.n = N; f.dv = dv; f.mP = mP; f.nP = nP; f.nV = nV; f.kP = dk / BK; f.kV = (N + BK - 1) / BK;
+  f.idesc_p = umma_idesc_f16(BN, BM * 2); f.idesc_v = umma_idesc_f16(BN, BM * 2, true);
+  f.c = c; f.dpart = w.dpart; f.n_dpart = n_dpart; f.diag = w.diag; f.part = w.part;
+  f.stats_w = stats; f.stats_w2 = stats != w.stats ? w.stats : nullptr;
+  f.lpart = w.kl_part; f.done = w.done; f.out_bf16 = out_bf16 ? 1 : 0;
+  const size_t stage_bytes = static_cast<size_t>(BM) * BK * 2 + 128 * BK * 2;
+  int stages = static_cast<int>((kSmemBudget - kOutBuffers * kOutChunkBytes) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  f.stages = stages;
+  const size_t smem = stages * stage_bytes + kOutBuffers * kOutChunkBytes + sizeof(PipeBarriers) + 1024;
+  {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    ACAN_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+      ACAN_CUDA((cudaFuncSetAttribute(fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+      done.fetch_or(bit, std::memory_order_release);
+    }
+  }
+  const int tiles = B * mP * (nP + nV), slots = kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((tiles < slots ? tiles : slots) * 2));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
+  ProfScope ps(PROF_PV, st);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fused_fwd_kernel, tf, tp, tv, to, f);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail((int)e, "fused_fwd_kernel launch: %s", cudaGetErrorString(e)); }
+  return launch_status("fused_fwd_kernel");
 }
 
 int prepare_target(const Workspace& w, const float* dis_label, int B, int H, int Wd, cudaStream_t st) {
@@ -1499,7 +1860,11 @@ extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* 
   if (dis_label)
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
   int nt = 0;
-  const bool fast = !keep && value && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  const bool fast = keep != 1 && value && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
+  if (keep == 1) keep = 1; else if (keep != 2) keep = 0;
+  if (fast && keep == 0 && cta_group() == 2 && dv % 256 == 0 && ctx_dtype != DT_F32 && B <= 4096)
+    return run_fused_forward(w, fh, value, ctx, ctx_dtype == DT_BF16, stats, B, N, dk, dv, scale, st);
+  if (keep == 2) keep = 0;                 // inference as separate probability / aggregation launches (A/B partner of the fused launch)
   int l_parts = 0;
   if (fast) {
     if (int e = run_affinity_fast(w, fh, stats, B, N, dk, scale, st, false, &l_parts)) return e;
@@ -1884,6 +2249,7 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
       if (int e = make_tmap(&to, grad_value, ob, dv, N, B, static_cast<size_t>(dv) * ob, static_cast<size_t>(N) * dv * ob, BM, gv_dtype == DT_BF16)) return e;
       GemmArgs g = gemm_args(B, N, dv, N, bn, cg, umma_idesc_f16(bn, BM * cg, true, true, false, go_bf16));
       g.out_scale = 1.0f / kKeepScale; g.out_gscale = x.gscale + 3;
+      g.pdl = 1;
       if (int e = launch_rowmajor<1>(ta, tb, to, g, st, cg, gv_dtype)) return e;
     }
     {  // dP[i, j] = sum_c dO[i, c] V[j, c]: both operands K-major in place -> dS epilogue, fp16(dS * s_ds) out
@@ -1895,6 +2261,7 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
       g.ds_new = 1; g.ds_delta = x.delta; g.ds_p = w.p; g.ds_lsum = w.lsum; g.gscale = x.gscale;
       g.ds_klT = w.klT; g.ds_gl = have_loss ? grad_loss : nullptr; g.ds_inv_bn = inv_bn;
       g.logbin = have_loss ? w.logbin : nullptr; g.lnz = w.lnz;
+      g.pdl = 1;
       if (int e = launch_gemm<MODE_DS, 0, false>(ta, tb, to, g, st, cg)) return e;
     }
   } else {
@@ -1916,6 +2283,7 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
     g.k_steps *= 2;
     g.idesc2 = umma_idesc_f16(bn, BM * cg, true, true);
     g.out_scale = scale; g.out_gscale = x.gscale + 1;
+    g.pdl = 1;
     if (int e = launch_rowmajor<2>(ta, tb, to, g, st, cg, gf_dtype, &ta2)) return e;
   }
   return 0;

@@ -648,6 +648,30 @@ def test_attention_channels_last_half(b, h, w):
     assert abs(float(ops.attention_loss_fused(out["ws"], dis.to(DEV))) - want) <= TOL * abs(want)
 
 
+@pytest.mark.parametrize("b,h,w,gain", [(2, 4, 6, 1.0), (2, 32, 44, 1.0), (3, 20, 64, 1.0), (16, 32, 44, 1.0), (3, 8, 16, 2.5)])
+def test_fused_forward_launch_equals_two_launch_path(b, h, w, gain):
+    """Inference forward as ONE persistent launch (probability tiles of image b+1 interleaved with aggregation tiles of image b, ordered
+    through per-row-block completion counters) == the same tiles as two launches, bit for bit: same operands, same k order, same epilogue
+    arithmetic.  Includes the configs[1] size and an image above the Cauchy-Schwarz safe bound (exact-maximum fallback)."""
+    from acan_b200 import ops
+    n, dk, dv = h * w, 512, 2048
+    f = synth.feature_map(f"ff.f.{b}.{n}", b, dk, h, w)
+    if gain != 1.0:
+        f[0] = f[0] * gain
+    v = synth.feature_map(f"ff.v.{b}.{n}", b, dv, h, w)
+    fd = f.half().to(DEV).contiguous(memory_format=torch.channels_last)
+    vd = v.half().to(DEV).contiguous(memory_format=torch.channels_last)
+    one = ops.attention_forward_cl(fd, vd, fused=True)
+    two = ops.attention_forward_cl(fd, vd, fused=False)
+    assert torch.equal(one["ctx"], two["ctx"])
+    assert torch.equal(one["row_stats"], two["row_stats"])
+    for _ in range(3):                                            # replays: the completion counters are reset by every call
+        again = ops.attention_forward_cl(fd, vd, ws=one["ws"], fused=True)
+        assert torch.equal(again["ctx"], one["ctx"])
+    if b <= 3:
+        close(one["ctx"].float(), O.aggregate(O.affinity(f.half().double()), v.half().double()))
+
+
 def test_pool_branch_channels_last_half():
     from acan_b200 import ops
     sd = synth.fill_state_dict({"linear1.weight": torch.empty(512, 2048), "linear1.bias": torch.empty(512),
