@@ -731,19 +731,31 @@ struct FusedArgs {
 
 struct FusedTile { int type, b, mt, nt; };   // type 0: probability tile, 1: aggregation tile
 
+// Tile t of the static list.  The list is a sequence of segments; segment s holds the probability tiles of image s (s < B) and the
+// aggregation tiles of image s - kFusedLag (s >= kFusedLag), spread evenly through each other.  The lag keeps every dependency (an
+// aggregation tile needs the probability tiles of its row block COMPLETED, epilogue and stores included) more than two waves of the
+// 74 resident pairs behind its consumer: with a lag of one segment the producers found their row block still in flight and the
+// pipeline drained at every tile (measured: 189 us against 146 us for two launches).
+constexpr int kFusedLag = 2;
 __device__ __forceinline__ FusedTile fused_decode(const FusedArgs& g, int t) {
-  const int TP = g.mP * g.nP, TV = g.mP * g.nV, TS = TP + TV;
+  const int TP = g.mP * g.nP, TV = g.mP * g.nV;
   FusedTile r;
-  int idx;
-  if (t < TP) { r.type = 0; r.b = 0; idx = t; }
-  else {
-    const int u = t - TP;
-    const int s = u / TS, j = u - s * TS;            // segment s + 1: aggregation tiles of image s, probability tiles of image s + 1
-    if (s < g.batch - 1) {
-      const int cp1 = ((j + 1) * TP) / TS, cp0 = (j * TP) / TS;   // probability tiles spread evenly through the segment
-      if (cp1 > cp0) { r.type = 0; r.b = s + 1; idx = cp0; }
-      else { r.type = 1; r.b = s; idx = j - cp0; }
-    } else { r.type = 1; r.b = g.batch - 1; idx = u - (g.batch - 1) * TS; }
+  r.type = 1; r.b = g.batch - 1;
+  int idx = 0, t0 = 0;
+  for (int s = 0; s < g.batch + kFusedLag; ++s) {
+    const int np = s < g.batch ? TP : 0, nv = s >= kFusedLag ? TV : 0, size = np + nv;
+    if (t < t0 + size) {
+      const int j = t - t0;
+      if (np == 0) { r.type = 1; r.b = s - kFusedLag; idx = j; }
+      else if (nv == 0) { r.type = 0; r.b = s; idx = j; }
+      else {
+        const int cp1 = ((j + 1) * TP) / size, cp0 = (j * TP) / size;      // probability tiles spread evenly through the segment
+        if (cp1 > cp0) { r.type = 0; r.b = s; idx = cp0; }
+        else { r.type = 1; r.b = s - kFusedLag; idx = j - cp0; }
+      }
+      break;
+    }
+    t0 += size;
   }
   const int nn = r.type == 0 ? g.nP : g.nV;
   r.mt = idx / nn;
