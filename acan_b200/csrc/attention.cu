@@ -700,13 +700,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------ fused inference forward (one persistent launch)
-// The probability pass is bound by its epilogue (one ex2 per element on the quarter-rate pipe, ~7 k cycles per 128 x 256 tile against a
-// ~5 k-cycle mainloop), the aggregation pass by the L2 -> SM operand feed (light epilogue).  As two launches each pays for its own
-// bottleneck and for its own wave quantisation (7.8 -> 8 and 10.4 -> 11 waves at configs[1]).  Here ONE persistent grid of CTA pairs
-// walks a static list in which the probability tiles of image b+1 are interleaved with the aggregation tiles of image b: while a pair's
-// epilogue warps chew on a probability tile, its MMA warp is already feeding the next (aggregation) tile, so the ex2 work hides under the
-// operand feed, and there is one tail instead of two.  P~ still makes its fp16 round trip through L2 (the aggregation accumulator of a
-// query tile, 128 x 2048 fp32, is four times the TMEM of an SM: see the header), but nothing returns to the host in between.
+// EXPERIMENT KEPT AS AN OPT-IN (keep = 2), NOT THE DEFAULT.  Hypothesis: the probability pass is bound by its epilogue (ex2, staging), the
+// aggregation pass by its operand feed; one persistent grid of CTA pairs walking a list in which the probability tiles of image b+2 are
+// interleaved with the aggregation tiles of image b would hide the first under the second and pay one tail instead of two.  P~ still makes
+// its fp16 round trip through L2 (the aggregation accumulator of a query tile, 128 x 2048 fp32, is four times the TMEM of an SM).
+// Measured (B200, configs[1], profiles/r02_notes.md): results bit-identical to the two launches, 165 us against 148 us.  Why it loses:
+// BOTH passes are bound by the same resource -- shared-memory bandwidth: per 64-deep k-step a CTA's shared memory takes 32 KB of TMA fill
+// and serves 48 KB of UMMA operand reads (its A, and the whole B tile: half for its own tensor core, half for its partner's), 80 KB at
+// 128 B/clock = 640 cycles against 512 cycles of MMA (the 80 % both passes and cuBLAS itself reach); the probability epilogue's staging
+// traffic (128 KB per tile) lands on the same port.  Nothing complementary is left to overlap, and tiles of two sizes (8 vs 22 k-steps)
+// balance worse over 74 pairs than two homogeneous launches do.
 //
 // Ordering: an aggregation tile (b, mt) reads the 256 rows of P~ that the probability tiles (b, mt, *) wrote -- from other SMs.  Every
 // epilogue group of a probability tile, once its TMA stores have COMPLETED (cp.async.bulk.wait_group 0, not .read) and its row-sum
@@ -1873,10 +1876,11 @@ extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* 
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
   int nt = 0;
   const bool fast = keep != 1 && value && !sim_map && !dis_label && !env_int("ACAN_EXACT_STATS", 0);   // inference: no statistics pass
-  if (keep == 1) keep = 1; else if (keep != 2) keep = 0;
-  if (fast && keep == 0 && cta_group() == 2 && dv % 256 == 0 && ctx_dtype != DT_F32 && B <= 4096)
+  // keep = 2: the single persistent launch (fused_fwd_kernel).  Bit-identical results, measured SLOWER than the two launches (165 vs 148 us
+  // at configs[1]: both passes are bound by the same resource, see the kernel's header), so it is opt-in, not the default.
+  if (fast && keep == 2 && cta_group() == 2 && dv % 256 == 0 && ctx_dtype != DT_F32 && B <= 4096)
     return run_fused_forward(w, fh, value, ctx, ctx_dtype == DT_BF16, stats, B, N, dk, dv, scale, st);
-  if (keep == 2) keep = 0;                 // inference as separate probability / aggregation launches (A/B partner of the fused launch)
+  if (keep != 1) keep = 0;
   int l_parts = 0;
   if (fast) {
     if (int e = run_affinity_fast(w, fh, stats, B, N, dk, scale, st, false, &l_parts)) return e;

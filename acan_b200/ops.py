@@ -359,11 +359,11 @@ def _nhwc_half(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def attention_forward_cl(feat: torch.Tensor, value: Optional[torch.Tensor], want_sim_map: bool = False,
-                         dis_label: Optional[torch.Tensor] = None, ws: Optional[AttnWorkspace] = None, fused: bool = True):
+                         dis_label: Optional[torch.Tensor] = None, ws: Optional[AttnWorkspace] = None, fused: bool = False):
     """Channels-last half-precision attention: feat [B,dk,h,w] / value [B,dv,h,w] as the convolutions left them
     (fp16, channels_last memory -> consumed in place, no pack); ctx comes back [B,dv,h,w] fp16 channels_last.
-    fused (inference, no sim_map / loss): probability and aggregation tiles in ONE persistent launch; False runs them as two launches
-    (same arithmetic; the A/B partner of the fused launch in tests and measurements)."""
+    fused (inference, no sim_map / loss): probability and aggregation tiles in ONE persistent launch instead of two -- same arithmetic,
+    bit-identical results, measured slower (both passes are shared-memory-bandwidth bound: csrc/attention.cu), hence off by default."""
     f = _nhwc_half(feat, "feat")
     b, h, w, dk = f.shape
     n = h * w
@@ -381,7 +381,7 @@ def attention_forward_cl(feat: torch.Tensor, value: Optional[torch.Tensor], want
     loss = torch.empty((), device=f.device, dtype=torch.float32) if lab is not None else None
     with torch.cuda.device(f.device):
         _lib.check(_lib.load().acan_attn_fwd_nhwc(f.data_ptr(), 1, _lib.ptr(v), 1, _lib.ptr(ctx), 1, _lib.ptr(sim), stats.data_ptr(), _lib.ptr(lab), hh, ww,
-                                                  _lib.ptr(loss), ws.ptr, ws.bytes, b, n, dk, dv, scale, 0 if fused else 2, _lib.current_stream()), "acan_attn_fwd_nhwc")
+                                                  _lib.ptr(loss), ws.ptr, ws.bytes, b, n, dk, dv, scale, 2 if fused else 0, _lib.current_stream()), "acan_attn_fwd_nhwc")
     ws.feat_pack = f
     return {"ctx": ctx.permute(0, 3, 1, 2) if ctx is not None else None, "sim_map": sim, "row_stats": stats, "loss": loss, "ws": ws}
 

@@ -240,9 +240,11 @@ int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h,
  * Element types (ACAN_DT_*): feat fp16 (read in place), bf16 or fp32 (one elementwise pass into the workspace's fp16 pack);
  * value fp16, read in place (an fp16 x bf16 kind::f16 MMA traps as an illegal instruction on sm_100a although the descriptor has one
  * format field per operand, and the probabilities need fp16's 11 bits: a bf16 pipeline converts V once, exactly); ctx fp16, bf16 or fp32.
- *   keep = 0  inference: statistics-free probability pass when neither sim_map nor the loss is requested; with dv % 256 == 0 and a 16-bit
- *             ctx the probability and aggregation tiles run interleaved in ONE persistent launch (the ex2-bound epilogue of the first
- *             hides under the operand feed of the second).  keep = 2: the same as two launches (A/B partner, same arithmetic).
+ *   keep = 0  inference: statistics-free probability pass when neither sim_map nor the loss is requested (diagonal, early-exit
+ *             statistics, probability and aggregation launches chained by programmatic dependent launch).
+ *   keep = 2  inference with the probability and aggregation tiles interleaved in ONE persistent launch (dv % 256 == 0, 16-bit ctx):
+ *             bit-identical, measured slower than keep = 0 on B200 (both passes are shared-memory-bandwidth bound); kept as the
+ *             documented experiment it is.
  *   keep = 1  training (autograd through sadecoder.py:42-49, 80-90): exact two-pass row statistics; the normalised probabilities stay
  *             in the workspace as fp16(P * 2^10) together with the row sums of those rounded values, which is the divisor used by
  *             the aggregation here and by acan_attn_bwd_nhwc -- the rows the tensor cores read then sum to exactly 1, which is what

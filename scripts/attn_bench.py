@@ -42,9 +42,9 @@ for tag, (b, h, w) in (("C2 B16 N1408", (16, 32, 44)), ("C3 B32 N1280", (32, 20,
     n = h * w
     ws = ops.attention_forward_cl(f, v)["ws"]
     us = ev(lambda: ops.attention_forward_cl(f, v, ws=ws))
-    line(f"inference core {tag} (fused launch)", us, b * 5120.0 * n * n)
-    us2 = ev(lambda: ops.attention_forward_cl(f, v, ws=ws, fused=False))
-    line(f"inference core {tag} (two launches)", us2, b * 5120.0 * n * n)
+    line(f"inference core {tag} (default: PDL-chained launches)", us, b * 5120.0 * n * n)
+    us2 = ev(lambda: ops.attention_forward_cl(f, v, ws=ws, fused=True))
+    line(f"inference core {tag} (single fused launch, opt-in)", us2, b * 5120.0 * n * n)
     _lib.check(lib.acan_profile_begin(256), "pb")
     for _ in range(10): ops.attention_forward_cl(f, v, ws=ws, fused=False)
     torch.cuda.synchronize()
