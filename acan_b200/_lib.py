@@ -65,6 +65,8 @@ SIGNATURES = {
     "acan_attn_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "acan_attention_loss": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_int, c_void_p]),
     "acan_gt_sim_map": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "acan_sgd_flat_chunk": (c_int, []),
+    "acan_sgd_flat": (c_int, [c_void_p] * 7 + [c_int, c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p]),
     "acan_attention_loss_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p]),
 }
 

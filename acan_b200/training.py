@@ -7,16 +7,21 @@ Nothing on the path synchronises with the host (the attention backward takes its
 step is capturable as is.  The reference's trainer (depthest_trainer.py:118-131) calls ``net(images)``, ``criterion(...)``,
 ``loss.backward()``, ``optimizer.step()`` every iteration; ``GraphedTrainStep(...)(images, labels)`` is that sequence with static buffers.
 
-Graphs of one step:
-  world = 1   [forward + losses + backward]                                   [optimizer]
-  world > 1   [forward + losses + backward of the LATE layers]  -> all-reduce(late gradients) on the NCCL stream
-              [backward of the EARLY layers]                     -> all-reduce(early gradients)           -> [optimizer]
-The late segment (layer4, decoder, classifier: ~70 % of the gradient bytes) is averaged while the second backward graph replays; only
-the early segment's collective (~30 %) sits between the backward and the optimizer.  All gradients live in ONE flat fp32 buffer whose
-slices ARE the ``.grad`` tensors the optimizer reads (no gather / scatter copies).  The optimizer has its own graph so that a learning
-rate changed by the reference's schedulers (creator/scheduler.py: step / poly / plateau / cosine rewrite ``param_groups``) is honoured:
-``__call__`` compares the hyper-parameters with the captured ones and re-captures the optimizer graph when they differ; a schedule that
-changes them every step switches the optimizer to eager launches (a handful of multi-tensor kernels, hidden behind the replay).
+One step:
+  world = 1   [graph: forward + losses + backward]  ->  optimizer
+  world > 1   [graph: forward + losses + backward]  ->  all-reduce(piece 0) all-reduce(piece 1) ... on the NCCL stream
+                                                         optimizer(piece 0) as soon as piece 0 has landed, optimizer(piece 1) ...
+All gradients live in ONE flat fp32 buffer whose slices ARE the ``.grad`` tensors (no gather / scatter copies).  With torch.optim.SGD
+(what the reference trains with, creator/optimizer.py:8-10) the parameters, momentum buffers and 16-bit shadow weights are bound to flat
+buffers as well and the update is ONE streaming kernel (acan_sgd_flat: 1.1 ms of multi-tensor passes -> 0.3 ms), launched per piece, so
+only the first piece's collective and the last piece's update are exposed.  Its hyper-parameters sit in a device table refreshed from
+``param_groups`` whenever a scheduler (creator/scheduler.py: step / poly / plateau / cosine) changed them -- no re-capture.  Any other
+optimizer keeps ``optimizer.step()`` in its own CUDA graph, re-captured when the hyper-parameters change (eager after three changes).
+
+``overlap=True`` instead splits the backward at the output of layer3 into two graphs and averages the late layers' gradients while the
+second replays.  Measured on 2 B200s (scripts/ddp_overlap_probe.py, profiles/r02_notes.md): the collective does run concurrently, but the
+step is no faster -- the cooperative BatchNorm kernels of the second graph need every SM and cannot be co-scheduled with NCCL's resident
+CTAs, so the graph stalls for as long as the collective runs.  Kept as an option, off by default.
 """
 from __future__ import annotations
 
@@ -49,7 +54,7 @@ class GraphedTrainStep:
 
     def __init__(self, net, criterion, optimizer, images: torch.Tensor, labels: torch.Tensor, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  reducer=None, epoch: int = 1, warmup: int = 3, graph: bool = True, after_backward: Optional[Callable[[], None]] = None,
-                 shadow_weights: Optional[bool] = None, overlap: bool = True):
+                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4):
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors: acan_b200 has no CPU path")
         self.net, self.criterion, self.optimizer, self.reducer = net, criterion, optimizer, reducer
@@ -74,6 +79,9 @@ class GraphedTrainStep:
         self.library_launches_per_step = None
         self.opt_eager = False
         self._opt_sig, self._sig_changes = None, 0
+        self._flat_sgd = False
+        self._never_grad = set()
+        self._pieces = max(int(pieces), 1)
         self._split = graph and self.world > 1 and overlap and hasattr(net, "layer3")
         self._boundary = None
         self._hook = None
@@ -93,6 +101,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._bind_flat_gradients()
+        self._bind_flat_sgd()
         optimizer.zero_grad(set_to_none=True)                  # the captured backward must CREATE its gradients (no in-place accumulation)
         for s_ in self._shadows:
             s_.grad = None
@@ -111,6 +120,10 @@ class GraphedTrainStep:
             self.graphs.append(g2)
             self._hook.remove()
         self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0)        # kernels of libacan_b200 in one replay
+        if self._flat_sgd and self._never_grad:
+            # parameters autograd never reached: torch.optim.SGD skips them (no weight decay, no momentum); the frozen table row does the same
+            self._seg_group_host = [self._frozen_row if id(p) in self._never_grad else g for p, g in zip(self._flat_params, self._seg_group_host)]
+            self._build_sgd_tables()
         self._capture_optimizer()
 
     # ------------------------------------------------------------------ gradients: one flat buffer, .grad = its slices
@@ -148,6 +161,96 @@ class GraphedTrainStep:
         self._late_ids = late
         shadowed = {id(p) for p in self._shadow_params}
         self._plain_params = [p for p in params if id(p) not in shadowed]      # gradients produced by autograd directly (fp32, small)
+
+    def _layout_view(self, flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+        seg = flat[off:off + p.numel()]
+        if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+            return seg.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
+        return seg.view(p.shape)
+
+    def _bind_flat_sgd(self) -> None:
+        """torch.optim.SGD without nesterov / dampening: parameters, momentum buffers and 16-bit shadows become slices of flat buffers (same
+        order and memory layout as the gradient buffer) and the update becomes acan_sgd_flat.  The optimizer object keeps working as the
+        owner of the state (``state_dict`` / ``load_state_dict`` see the same tensors) and of the hyper-parameters."""
+        opt = self.optimizer
+        if type(opt) is not torch.optim.SGD:
+            return
+        group_of = {}
+        for gi, g in enumerate(opt.param_groups):
+            if g.get("nesterov") or g.get("dampening", 0) != 0 or g.get("maximize") or g.get("differentiable"):
+                return
+            for p in g["params"]:
+                group_of[id(p)] = gi
+        if any(id(p) not in group_of or p.dtype != torch.float32 for p in self._flat_params):
+            return
+        dev = self._flat.device
+        n = self._flat.numel()
+        self._flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self._flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self._flat_s = torch.zeros(n, device=dev, dtype=self.amp_dtype) if (self._shadows and self.amp_dtype == torch.bfloat16) else None
+        shadow_of = {id(p): i for i, p in enumerate(self._shadow_params)}
+        seg_end, seg_group, off = [], [], 0
+        frozen = len(opt.param_groups)                        # extra table row (lr 0, momentum 1, wd 0): parameters autograd never reaches
+        with torch.no_grad():
+            for p in self._flat_params:
+                v = self._layout_view(self._flat_p, off, p)
+                v.copy_(p.data)
+                p.data = v
+                st = opt.state.get(p)
+                mv = self._layout_view(self._flat_m, off, p)
+                if st is not None and st.get("momentum_buffer") is not None:
+                    mv.copy_(st["momentum_buffer"])
+                    st["momentum_buffer"] = mv
+                if self._flat_s is not None and id(p) in shadow_of:
+                    sv = self._layout_view(self._flat_s, off, p)
+                    sv.copy_(p.data)
+                    self._shadows[shadow_of[id(p)]] = sv.requires_grad_(True)
+                off += p.numel()
+                seg_end.append(off)
+                seg_group.append(group_of[id(p)])
+        self._seg_end_host, self._seg_group_host = seg_end, seg_group
+        self._hyper = torch.zeros(frozen + 1, 4, device=dev, dtype=torch.float32)
+        self._frozen_row = frozen
+        self._build_sgd_tables()
+        self._flat_sgd = True
+        self._refresh_hyper()
+
+    def _build_sgd_tables(self) -> None:
+        """device tables of acan_sgd_flat: per parameter slice its end offset and parameter group, per chunk of elements its group (or -1)."""
+        import numpy as np
+        from . import _lib
+        dev, n = self._flat.device, self._flat.numel()
+        ch = int(_lib.load().acan_sgd_flat_chunk())
+        self._sgd_chunk = ch
+        n_chunks = (n + ch - 1) // ch
+        ends = np.asarray(self._seg_end_host, dtype=np.int64)
+        grp = np.asarray(self._seg_group_host, dtype=np.int32)
+        starts = np.arange(n_chunks, dtype=np.int64) * ch
+        first = np.searchsorted(ends, starts, side="right")
+        last = np.searchsorted(ends, np.minimum(starts + ch, n) - 1, side="right")
+        cg = np.full(n_chunks, -1, dtype=np.int8)
+        for c in range(n_chunks):
+            gs = grp[first[c]:last[c] + 1]
+            if gs.size and (gs == gs[0]).all():
+                cg[c] = gs[0]
+        self._seg_end = torch.from_numpy(ends).to(dev)
+        self._seg_grp = torch.from_numpy(grp).to(dev)
+        self._chunk_group = torch.from_numpy(cg).to(dev)
+        self._n_sgd_chunks = n_chunks
+
+    def _refresh_hyper(self) -> None:
+        rows = [[float(g["lr"]), float(g.get("momentum", 0.0)), float(g.get("weight_decay", 0.0)), 0.0] for g in self.optimizer.param_groups]
+        rows.append([0.0, 1.0, 0.0, 0.0])
+        self._hyper.copy_(torch.tensor(rows, dtype=torch.float32))
+        self._opt_sig = _hyper_signature(self.optimizer)
+
+    def _sgd_range(self, first_chunk: int, n_chunks: int) -> None:
+        from . import _lib
+        with torch.cuda.device(self._flat.device):
+            _lib.check(_lib.load().acan_sgd_flat(self._flat_p.data_ptr(), self._flat.data_ptr(), self._flat_m.data_ptr(), _lib.ptr(self._flat_s),
+                                                 self._chunk_group.data_ptr(), self._seg_end.data_ptr(), self._seg_grp.data_ptr(), int(self._seg_end.numel()),
+                                                 self._hyper.data_ptr(), int(first_chunk), int(n_chunks), int(self._flat.numel()), _lib.current_stream()),
+                       "acan_sgd_flat")
 
     def _grab_boundary(self, module, inputs, output):
         self._boundary = output
@@ -208,6 +311,7 @@ class GraphedTrainStep:
                     src.append(p.grad)
                 else:
                     zero.append(self._views[id(p)])
+                    self._never_grad.add(id(p))
         if dst:
             torch._foreach_copy_(dst, src)
         if zero:
@@ -237,6 +341,12 @@ class GraphedTrainStep:
     def _optimizer_part(self) -> None:
         if self.after_backward is not None:
             self.after_backward()
+        if self._flat_sgd:
+            self._sgd_range(0, self._n_sgd_chunks)               # parameters, momentum and 16-bit shadows in one pass
+            if self._flat_s is None and self._shadows:
+                with torch.no_grad():
+                    torch._foreach_copy_(self._shadows, self._shadow_params)
+            return
         self.optimizer.step()
         if self._shadows:
             with torch.no_grad():
@@ -244,7 +354,7 @@ class GraphedTrainStep:
 
     def _capture_optimizer(self) -> None:
         self._opt_sig = _hyper_signature(self.optimizer)
-        if self.opt_eager:
+        if self.opt_eager or (self._flat_sgd and self.world > 1):          # the multi-GPU flat path launches its pieces itself
             self.opt_graph = None
             return
         g = torch.cuda.CUDAGraph()
@@ -258,6 +368,20 @@ class GraphedTrainStep:
         if self._shadows:
             with torch.no_grad():
                 torch._foreach_copy_(self._shadows, self._shadow_params)
+
+    def _piece_ranges(self):
+        """[(element range, chunk range)]: the flat buffer cut into `pieces` runs of whole optimizer chunks -- with the split backward
+        the late layers' runs first (their gradients are complete when the first graph ends)."""
+        ch, n, nch = self._sgd_chunk, self._flat.numel(), self._n_sgd_chunks
+        def cut(c0, c1, k):
+            k = max(1, min(k, c1 - c0))
+            edges = [c0 + (c1 - c0) * i // k for i in range(k + 1)]
+            return [((a * ch, min(b * ch, n)), (a, b - a)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        if self._split:
+            cb = min((self._n_early + ch - 1) // ch, nch)
+            late, early = cut(cb, nch, max(self._pieces - 1, 1)), cut(0, cb, 1)
+            return late, early
+        return cut(0, nch, self._pieces), []
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """one training step; returns the total loss (a device scalar; static across steps when graphed)."""
@@ -277,22 +401,39 @@ class GraphedTrainStep:
             return self.losses[3]
         sig = _hyper_signature(self.optimizer)
         if sig != self._opt_sig:                                # a scheduler rewrote lr / momentum / ...: honour it
-            self._sig_changes += 1
-            if self._sig_changes >= 3 and not self.opt_eager:
-                self.opt_eager = True                           # changes every few steps (poly / cosine): stop re-capturing
-            torch.cuda.current_stream(self.static_x.device).synchronize()
-            self._capture_optimizer()
+            if self._flat_sgd:
+                self._refresh_hyper()                           # device table: nothing to re-capture
+            else:
+                self._sig_changes += 1
+                if self._sig_changes >= 3 and not self.opt_eager:
+                    self.opt_eager = True                       # changes every few steps (poly / cosine): stop re-capturing
+                torch.cuda.current_stream(self.static_x.device).synchronize()
+                self._capture_optimizer()
         if self.world > 1:
             import torch.distributed as dist
+            ar = lambda lo, hi: dist.all_reduce(self._flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)   # noqa: E731
             self.graphs[0].replay()
+            if self._flat_sgd and self.after_backward is None:
+                first, second = self._piece_ranges()
+                works = [(ar(*er), cr) for er, cr in first]      # queued on the NCCL stream, one after the other
+                if self._split:
+                    self.graphs[1].replay()
+                    works += [(ar(*er), cr) for er, cr in second]
+                for w, (c0, nc) in works:
+                    w.wait()                                     # the compute stream waits for THIS piece only
+                    self._sgd_range(c0, nc)
+                if self._flat_s is None and self._shadows:
+                    with torch.no_grad():
+                        torch._foreach_copy_(self._shadows, self._shadow_params)
+                return self.losses[3]
             if self._split:
-                wa = dist.all_reduce(self._flat[self._n_early:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)   # overlaps the second graph
+                wa = ar(self._n_early, self._flat.numel())        # runs beside the second graph
                 self.graphs[1].replay()
-                wb = dist.all_reduce(self._flat[:self._n_early], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                wb = ar(0, self._n_early)
                 wa.wait()
                 wb.wait()
             else:
-                dist.all_reduce(self._flat, op=dist.ReduceOp.AVG, group=self.group)
+                ar(0, self._flat.numel()).wait()
         else:
             self.graphs[0].replay()
         if self.opt_graph is not None:

@@ -307,6 +307,21 @@ int acan_gt_sim_map(const float* dis_label, float* gt, float* bins_ws, int B, in
 int acan_attention_loss_fused(void* workspace, const void* feat_pack, const float* dis_label, float* loss_out,
                               int B, int H, int W, int dk, int dv, float scale, void* stream);
 
+/* ---------------------------------------------------------------- optimizer step ------ */
+
+/* torch.optim.SGD (momentum, weight decay; nesterov = False, dampening = 0: what creator/optimizer.py:8-10 builds) over flat fp32
+ * buffers in ONE pass: g' = g + wd p;  m = mu m + g';  p = p - lr m;  optionally the bf16 shadow of p is written in the same pass.
+ * The training driver (acan_b200/training.py) binds every parameter, gradient and momentum buffer of the network to slices of such
+ * buffers, in net.parameters() order; per-group hyper-parameters come from a DEVICE table, so a learning-rate schedule needs no re-capture.
+ *   seg_end[n_seg] (int64) / seg_group[n_seg] (int32): end offset (exclusive) and parameter-group index of each parameter's slice
+ *   chunk_group[ceil(n / acan_sgd_flat_chunk())] (int8): the group of a chunk of elements when it lies in one group, -1 when it spans several
+ *   hyper[n_groups][4] fp32: (lr, momentum, weight_decay, unused)
+ *   first_chunk, n_chunks: the range of chunks to update (the multi-GPU driver updates a range as soon as its all-reduce has landed) */
+int acan_sgd_flat_chunk(void);
+int acan_sgd_flat(float* param, const float* grad, float* momentum_buf, void* shadow_bf16, const signed char* chunk_group,
+                  const long long* seg_end, const int* seg_group, int n_seg, const float* hyper,
+                  long long first_chunk, long long n_chunks, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -353,6 +353,57 @@ def test_graphed_train_step_matches_eager():
         assert float((final[True][k] - final[False][k]).abs().max()) <= 0.35 * float(upd) + 1e-7, k
 
 
+def test_flat_sgd_kernel_matches_torch_sgd():
+    """acan_sgd_flat (one pass over flat parameter / gradient / momentum buffers, per-group hyper-parameters from a device table, bf16 shadow
+    written on the way) == torch.optim.SGD with momentum and weight decay over the same tensors in three parameter groups, step after step,
+    bit for bit; a group boundary inside a chunk and a ragged tail included."""
+    from acan_b200 import _lib
+    lib = _lib.load()
+    ch = int(lib.acan_sgd_flat_chunk())
+    sizes = [5000, 7, 4096, 1, 2048 * 3 + 5, 160, 333]
+    groups = [0, 1, 2, 1, 0, 2, 1]
+    hyper = [(1e-2, 0.9, 5e-4), (1e-1, 0.9, 5e-4), (2e-1, 0.8, 0.0)]
+    n = sum(sizes)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    flat_p = torch.randn(n, generator=g).to(DEV)
+    flat_m = torch.zeros(n, device=DEV)
+    flat_g = torch.empty(n, device=DEV)
+    flat_s = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    params, off = [], 0
+    for sz in sizes:
+        params.append(torch.nn.Parameter(flat_p[off:off + sz].clone()))
+        off += sz
+    opt = torch.optim.SGD([{"params": [p for p, gi in zip(params, groups) if gi == k], "lr": h[0], "momentum": h[1], "weight_decay": h[2]} for k, h in enumerate(hyper)], lr=1.0)
+    ends = np.cumsum(sizes).astype(np.int64)
+    n_chunks = (n + ch - 1) // ch
+    cg = np.full(n_chunks, -1, dtype=np.int8)
+    for c in range(n_chunks):
+        a, b = np.searchsorted(ends, c * ch, side="right"), np.searchsorted(ends, min((c + 1) * ch, n) - 1, side="right")
+        gs = np.asarray(groups)[a:b + 1]
+        if (gs == gs[0]).all():
+            cg[c] = gs[0]
+    assert (cg == -1).any() and (cg >= 0).any()
+    seg_end, seg_grp, chunk_group = T(ends).to(DEV), T(np.asarray(groups, dtype=np.int32)).to(DEV), T(cg).to(DEV)
+    table = torch.tensor([[h[0], h[1], h[2], 0.0] for h in hyper], device=DEV)
+    for step in range(3):
+        grads = torch.randn(n, generator=g).to(DEV)
+        flat_g.copy_(grads)
+        off = 0
+        for p, sz in zip(params, sizes):
+            p.grad = grads[off:off + sz].clone()
+            off += sz
+        opt.step()
+        half = n_chunks // 2                        # two ranges, as the multi-GPU driver launches them
+        for c0, nc in ((0, half), (half, n_chunks - half)):
+            _lib.check(lib.acan_sgd_flat(flat_p.data_ptr(), flat_g.data_ptr(), flat_m.data_ptr(), flat_s.data_ptr(), chunk_group.data_ptr(), seg_end.data_ptr(),
+                                         seg_grp.data_ptr(), len(sizes), table.data_ptr(), c0, nc, n, torch.cuda.current_stream().cuda_stream), "acan_sgd_flat")
+        want = torch.cat([p.detach().reshape(-1) for p in params])
+        assert torch.equal(flat_p, want), float((flat_p - want).abs().max())
+        assert torch.equal(flat_s, want.to(torch.bfloat16))
+        want_m = torch.cat([opt.state[p]["momentum_buffer"].reshape(-1) for p in params])
+        assert torch.equal(flat_m, want_m)
+
+
 # ------------------------------------------------------------------------------------ pooling branch
 
 def test_pool_branch_against_oracle():
