@@ -264,7 +264,7 @@ def run_train(args, rank, world, device, lib):
     graph_note = None
     try:
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
-                                graph=not args.no_graph, overlap=not args.no_overlap)
+                                graph=not args.no_graph, overlap=args.split_backward, pieces=args.pieces)
     except Exception as e:          # same kernels either way: a failed capture must not cost the measurement
         torch.cuda.synchronize()
         graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]})"
@@ -387,10 +387,10 @@ def run_train(args, rank, world, device, lib):
     t_bn_b = graph_time([lambda k=k: ops.bn_train_backward(xs[k], ys_[k], gs[k], wgt, mean_, invstd_, False) for k in range(n_rot)])
     bn_elems = float(B * bc * bh * bw)
     if world > 1:
-        sched = ("dp%d: batch-sharded replicas; backward split at layer3 into two CUDA graphs, the late layers' slice of the flat fp32 gradient buffer "
-                 "all-reduced on the (high-priority) NCCL stream while the second graph replays, the early slice after it, then the optimizer graph" % world
-                 if getattr(step, "_split", False) else
-                 "dp%d: batch-sharded replicas; one backward graph, one in-place NCCL all-reduce of the flat fp32 gradient buffer, optimizer graph" % world)
+        sched = ("dp%d: batch-sharded replicas; forward + losses + backward graph, then the flat fp32 gradient buffer is averaged in %d pieces on the (high-priority) "
+                 "NCCL stream, the one-pass SGD kernel updating piece k while piece k+1 is in flight" % (world, args.pieces))
+        if getattr(step, "_split", False):
+            sched += "; backward split at layer3 into two graphs, the late layers' pieces all-reduced beside the second"
     else:
         sched = "dp1"
     return {
@@ -400,7 +400,7 @@ def run_train(args, rank, world, device, lib):
         "timed_1s": {"steps": long_steps, "seconds": elapsed_long, "ms_per_step": elapsed_long / long_steps * 1e3, "value": world * B * long_steps / elapsed_long},
         "config": {"workload": TRAIN_WORKLOAD, "parallelism": sched,
                    "precision": "bf16 autocast channels_last cuDNN convolutions; fused BN/ReLU kernels bf16 in / fp32 statistics; attention fwd/bwd on the channels-last path: fp16 probabilities x bf16 values / gradients read in place, fp32 accumulate; losses fp32; SGD momentum on fp32 weights",
-                   "launch": graph_note or ("eager" if args.no_graph else "step replayed from CUDA graphs (acan_b200.training.GraphedTrainStep): forward + losses + backward, optimizer graph re-captured when a scheduler changes lr"),
+                   "launch": graph_note or ("eager" if args.no_graph else "step replayed from CUDA graphs (acan_b200.training.GraphedTrainStep): forward + losses + backward; SGD as one flat streaming kernel (acan_sgd_flat) with its hyper-parameters in a device table"),
                    "l2": f"{8} rotating input batches; activations (> 10 GB per step) exceed the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
@@ -548,7 +548,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying their CUDA graphs")
-    ap.add_argument("--no-overlap", action="store_true", help="train, N > 1: one backward graph + one all-reduce (A/B against the split schedule)")
+    ap.add_argument("--split-backward", action="store_true", help="train, N > 1: split the backward at layer3 and all-reduce the late layers beside the second graph (A/B)")
+    ap.add_argument("--pieces", type=int, default=4, help="train, N > 1: pieces of the flat gradient buffer (all-reduce of piece k+1 runs beside the update of piece k)")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[3]/[4] training sub-record")
     ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 extras (reference on the GPU, configs[2] line)")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],

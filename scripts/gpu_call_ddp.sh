@@ -4,15 +4,12 @@ mkdir -p gpurun_out
 P=gpurun_out/r02_ddp
 run() { # name, extra env, extra args
   name=$1; shift
-  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload train --steps 20 --warmup 5 ${EXTRA} > ${P}_${name}.json 2> ${P}_${name}.err
+  env "$@" timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload train --steps 20 --warmup 5 ${EXTRA} > ${P}_${name}.json 2> ${P}_${name}.err
   echo "$name exit $?"; tail -c 600 ${P}_${name}.json | head -c 300; echo
 }
-EXTRA="" run overlap NCCL_DEBUG=WARN
-EXTRA="--no-overlap" run single NCCL_DEBUG=WARN
-EXTRA="" run overlap_cga0 NCCL_CGA_CLUSTER_SIZE=0
-EXTRA="" run overlap_ch8 NCCL_MAX_NCHANNELS=8
-NCCL_DEBUG=INFO timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/ddp_check.py > ${P}_nccl_info.log 2>&1
-grep -i -E "NVLS|channels|Connected|via" ${P}_nccl_info.log | head -20 > ${P}_nccl_topology.txt
+EXTRA="" run pipelined NCCL_DEBUG=WARN
+EXTRA="--pieces 1" run single NCCL_DEBUG=WARN
+EXTRA="--split-backward" run split NCCL_DEBUG=WARN
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r02_ddp_*.json')):
