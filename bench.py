@@ -551,6 +551,7 @@ def main():
     ap.add_argument("--split-backward", action="store_true", help="train, N > 1: split the backward at layer3 and all-reduce the late layers beside the second graph (A/B)")
     ap.add_argument("--pieces", type=int, default=4, help="train, N > 1: pieces of the flat gradient buffer (all-reduce of piece k+1 runs beside the update of piece k)")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[3]/[4] training sub-record")
+    ap.add_argument("--no-long", action="store_true", help="skip the >= 1 s repetition of the timed region (runs under ncu)")
     ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 extras (reference on the GPU, configs[2] line)")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer (default): BASELINE.json configs[1], the headline (+ the train sub-record).  train: only configs[3]/[4]")
@@ -633,7 +634,8 @@ def main():
     barrier()
     _lib.check(lib.acan_profile_begin(args.steps * 16 + 64), "acan_profile_begin")
     for i in range(args.steps):
-        step_device(net, dev_in[i % n_rot])
+        with torch.cuda.nvtx.range("acan_step"):          # what the committed ncu launch list is filtered on (profiles/)
+            step_device(net, dev_in[i % n_rot])
     barrier()
     ms = (ctypes.c_float * 8)()
     cnt = (ctypes.c_int * 8)()
@@ -649,7 +651,7 @@ def main():
 
     # ---- the device-resident measurement again over a region of at least one second (the K-step region is ~0.1 s: too short for the clock
     #      sampler, and short enough to run at boost clocks); after the per-kernel brackets, which are taken on the still-cool device
-    long_steps = max(args.steps, int(math.ceil(1.2 / max(elapsed / args.steps, 1e-4))))
+    long_steps = args.steps if args.no_long else max(args.steps, int(math.ceil(1.2 / max(elapsed / args.steps, 1e-4))))
     sampler = ClockSampler(local)
     e0.record()
     for i in range(long_steps):
