@@ -1849,8 +1849,8 @@ extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* 
   ACAN_CHECK_ARG(feat_dtype == DT_F16 || feat_dtype == DT_BF16 || feat_dtype == DT_F32, "acan_attn_fwd_nhwc: feat_dtype %d", feat_dtype);
   // (an fp16 A with a bf16 B is NOT a legal kind::f16 MMA on sm_100a although the descriptor has one format field per operand: measured,
   //  the instruction traps as illegal -- so V shares the probabilities' format)
-  ACAN_CHECK_ARG(!value || (value_dtype == DT_F16 && (ctx_dtype == DT_F16 || ctx_dtype == DT_BF16 || ctx_dtype == DT_F32)),
-                 "acan_attn_fwd_nhwc: value must be fp16 (got %d), ctx fp16 / bf16 / fp32 (got %d)", value_dtype, ctx_dtype);
+  ACAN_CHECK_ARG(!value || ((value_dtype == DT_F16 || value_dtype == DT_BF16) && (ctx_dtype == DT_F16 || ctx_dtype == DT_BF16 || ctx_dtype == DT_F32)),
+                 "acan_attn_fwd_nhwc: value must be fp16 / bf16 (got %d), ctx fp16 / bf16 / fp32 (got %d)", value_dtype, ctx_dtype);
   if (int e = check_attn_shape("acan_attn_fwd_nhwc", B, N, dk, value ? dv : 0)) return e;
   ACAN_CHECK_ARG(!(dis_label) || (loss_out && (H / 8) * (Wd / 8) == N && H % 8 == 0 && Wd % 8 == 0), "acan_attn_fwd_nhwc: label [B,1,%d,%d] does not match N=%d", H, Wd, N);
   ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0 && reinterpret_cast<uintptr_t>(feat) % 16 == 0 &&
@@ -1871,6 +1871,15 @@ extern "C" int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* 
     else                       to_half_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(feat, reinterpret_cast<uint4*>(w.fh), n8);
     if (int e = launch_status("to_half_kernel")) return e;
     fh = w.fh;
+  }
+  if (value && value_dtype == DT_BF16) {   // bf16 values (the autocast step): one exact conversion pass into the workspace's fp16 slot
+    const int64_t n8 = static_cast<int64_t>(B) * N * dv / 8;
+    int64_t blocks = (n8 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    to_half_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(value, reinterpret_cast<uint4*>(w.vh), n8);
+    if (int e = launch_status("to_half_kernel (V)")) return e;
+    value = w.vh;
+    value_dtype = DT_F16;
   }
   if (dis_label)
     if (int e = prepare_target(w, dis_label, B, H, Wd, st)) return e;
@@ -2193,11 +2202,11 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
                                   int B, int N, int dk, int dv, float scale, void* stream) {
   ACAN_CHECK_ARG(workspace && scratch && grad_feat, "acan_attn_bwd_nhwc: null pointer");
   const bool agg = grad_ctx != nullptr;
-  ACAN_CHECK_ARG(!agg || (value && ctx32 && grad_value), "acan_attn_bwd_nhwc: value, ctx and grad_value are required with grad_ctx");
+  ACAN_CHECK_ARG(!agg || (ctx32 && grad_value), "acan_attn_bwd_nhwc: ctx and grad_value are required with grad_ctx");
   ACAN_CHECK_ARG(agg || have_loss, "acan_attn_bwd_nhwc: nothing to differentiate (no grad_ctx, no loss)");
   ACAN_CHECK_ARG(!have_loss || grad_loss, "acan_attn_bwd_nhwc: the loss term needs grad_loss (device scalar)");
   ACAN_CHECK_ARG(!agg || (value_dtype == DT_F16 && (go_dtype == DT_F16 || go_dtype == DT_BF16 || go_dtype == DT_F32)),
-                 "acan_attn_bwd_nhwc: value must be fp16 (as given to the forward), grad_ctx fp16 / bf16 / fp32");
+                 "acan_attn_bwd_nhwc: value must be fp16 (as given to the forward; NULL = the workspace's fp16 copy of a bf16 V), grad_ctx fp16 / bf16 / fp32");
   auto dt_ok = [](int d) { return d == DT_F32 || d == DT_F16 || d == DT_BF16; };
   ACAN_CHECK_ARG(dt_ok(gf_dtype) && (!agg || dt_ok(gv_dtype)), "acan_attn_bwd_nhwc: output dtype");
   if (int e = check_attn_shape("acan_attn_bwd_nhwc", B, N, dk, dv)) return e;
@@ -2213,6 +2222,7 @@ extern "C" int acan_attn_bwd_nhwc(void* workspace, size_t workspace_bytes, void*
   const int cg = cta_group();
   const int64_t rows = static_cast<int64_t>(B) * N;
   const __half* fh = feat_h ? static_cast<const __half*>(feat_h) : w.fh;
+  if (value == nullptr) value = w.vh;        // the forward converted a bf16 V into the workspace
   const float inv_bn = 1.0f / (static_cast<float>(B) * static_cast<float>(N));
   const size_t pitchP = static_cast<size_t>(N) * 2, batchP = static_cast<size_t>(N) * N * 2;
   const size_t pitchV = static_cast<size_t>(dv) * 2, batchV = static_cast<size_t>(N) * dv * 2;

@@ -194,7 +194,7 @@ class Attention(torch.autograd.Function):
         holder.ws, holder.row_stats = ws, out["row_stats"]
         holder.gen = getattr(holder, "gen", 0) + 1
         ctx.ws, ctx.feat_dtype, ctx.value_dtype = ws, feat.dtype, value.dtype
-        ctx.save_for_backward(out["value16"], out["ctx32"])
+        ctx.save_for_backward(out["value16"] if out["value16"] is not None else torch.empty(0, device=feat.device), out["ctx32"])
         ctx.set_materialize_grads(False)
         o = out["ctx32"]
         if value.dtype in (torch.float16, torch.bfloat16):
@@ -205,6 +205,8 @@ class Attention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_ctx, grad_token):
         value16, ctx32 = ctx.saved_tensors
+        if value16.numel() == 0:
+            value16 = None                       # bf16 V: its fp16 copy lives in the forward's workspace
         ws = ctx.ws
         grad_loss = ws.pending_loss_grad if grad_token is not None else None
         ws.pending_loss_grad = None

@@ -238,8 +238,9 @@ int acan_attn_fwd_nhwc_f16(const void* feat_h, const void* value_h, void* ctx_h,
 
 /* General channels-last form (the training step's entry; acan_attn_fwd_nhwc_f16 is this call with fp16 everywhere and keep = 0).
  * Element types (ACAN_DT_*): feat fp16 (read in place), bf16 or fp32 (one elementwise pass into the workspace's fp16 pack);
- * value fp16, read in place (an fp16 x bf16 kind::f16 MMA traps as an illegal instruction on sm_100a although the descriptor has one
- * format field per operand, and the probabilities need fp16's 11 bits: a bf16 pipeline converts V once, exactly); ctx fp16, bf16 or fp32.
+ * value fp16, read in place, or bf16, converted exactly into the workspace by one pass (an fp16 x bf16 kind::f16 MMA traps as an
+ * illegal instruction on sm_100a although the descriptor has one format field per operand, and the probabilities need fp16's 11 bits);
+ * ctx fp16, bf16 or fp32.
  *   keep = 0  inference: statistics-free probability pass when neither sim_map nor the loss is requested (diagonal, early-exit
  *             statistics, probability and aggregation launches chained by programmatic dependent launch).
  *   keep = 2  inference with the probability and aggregation tiles interleaved in ONE persistent launch (dv % 256 == 0, 16-bit ctx):
@@ -263,7 +264,8 @@ int acan_attn_fwd_nhwc(const void* feat, int feat_dtype, const void* value, int 
  *               acan_attention_loss_fused (or a forward with a label) left there: ln(bin), ln Z, the in-window target mass T_i
  *   scratch     acan_attn_bwd_nhwc_scratch_bytes(), 1024-byte aligned (dS, an fp16 pack of an fp32 grad_ctx, delta, scales)
  *   feat_h      [B,N,dk] fp16 as given to the forward (NULL: the workspace pack, when the forward converted bf16 / fp32 features)
- *   value       [B,N,dv] fp16 as given to the forward (value_dtype must be ACAN_DT_F16), ctx32 [B,N,dv] fp32 the forward's output
+ *   value       [B,N,dv] fp16 as given to the forward (value_dtype ACAN_DT_F16), or NULL when the forward was given bf16 values (their fp16
+ *               copy is in the workspace); ctx32 [B,N,dv] fp32 the forward's output
  *   grad_ctx    [B,N,dv] fp16 (read in place as an MMA operand), or bf16 / fp32 (packed to fp16 times a power of two chosen on the
  *               device from max |dO|: exact for bf16); NULL when only the attention loss is differentiated
  *   have_loss   adds *grad_loss (DEVICE scalar) * d(attention loss)/dF
