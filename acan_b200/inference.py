@@ -93,12 +93,8 @@ class InferenceNet(nn.Module):
             raise NotImplementedError("optimize_for_inference: the auxiliary (alpha != 0) branch is a training-time output")
         self.dtype = dtype
         w, b = fold_conv_bn(net.conv1, net.bn1)
-        self.stem_pad = 0
-        if dtype == torch.float16 and w.shape[1] % 8 != 0:
-            # 3 input channels send cuDNN to an sm_80 implicit-GEMM kernel without shared-memory staging (160 us at configs[1], 3.6 % of the
-            # step in the ncu launch list); zero-padded to 8 channels the stem runs on the sm_100 tensor-core kernels like every other layer
-            self.stem_pad = 8 - w.shape[1] % 8
-            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, self.stem_pad))
+        # (the 3-channel stem runs on an sm_80 implicit-GEMM kernel, 88 us at configs[1]; zero-padding the input to 4 channels makes the
+        #  convolution 64 us but costs 35 us of padding, to 8 channels 323 us: measured with scripts/stem_bench.py, left as it is)
         self.stem = FusedConv(w, b, net.conv1.stride, net.conv1.padding, net.conv1.dilation, True, dtype)
         self.maxpool = net.maxpool
         self.blocks = nn.Sequential(*[FusedBottleneck(blk, dtype) for layer in (net.layer1, net.layer2, net.layer3, net.layer4) for blk in layer])
@@ -126,12 +122,7 @@ class InferenceNet(nn.Module):
             p.requires_grad_(False)
 
     def _features(self, x):
-        if self.stem_pad:
-            xp = torch.zeros((x.shape[0], x.shape[1] + self.stem_pad, x.shape[2], x.shape[3]), device=x.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
-            xp[:, :x.shape[1]].copy_(x)                        # cast + interleave in one strided copy
-            x = xp
-        else:
-            x = x.to(self.dtype).contiguous(memory_format=torch.channels_last if self.dtype == torch.float16 else torch.contiguous_format)
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last if self.dtype == torch.float16 else torch.contiguous_format)
         x = self.stem(x)
         mp = self.maxpool
         if self.dtype == torch.float16 and (mp.kernel_size, mp.stride, mp.padding, mp.dilation, mp.ceil_mode) == (3, 2, 1, 1, False) and x.shape[1] % 8 == 0:
