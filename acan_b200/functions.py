@@ -111,6 +111,36 @@ class BatchNormAct(torch.autograd.Function):
 FUSED_BN = True          # A/B switch: False routes every BatchNorm through the framework's own kernels
 
 
+class deferred_bn_counters:
+    """``with deferred_bn_counters():`` -- the ``num_batches_tracked += 1`` of every fused BatchNorm inside the block is collected and applied
+    by ONE multi-tensor add on exit instead of one 2-us kernel per layer (106 of them in a ResNet-101 step: 0.19 ms of a 13.7 ms step)."""
+    active = None
+
+    def __enter__(self):
+        self._outer = deferred_bn_counters.active
+        deferred_bn_counters.active = []
+        return self
+
+    def __exit__(self, *exc):
+        pending, deferred_bn_counters.active = deferred_bn_counters.active, self._outer
+        if pending:
+            counts = {}
+            for t in pending:                                  # the shared f_key / f_query BatchNorm is bumped twice per forward: one add of 2,
+                counts.setdefault(id(t), [t, 0])[1] += 1       # not two racing adds of 1 in the same multi-tensor launch
+            with torch.no_grad():
+                for k in sorted({c for _, c in counts.values()}):
+                    torch._foreach_add_([t for t, c in counts.values() if c == k], k)
+        return False
+
+
+def _bump(counter: torch.Tensor) -> None:
+    if deferred_bn_counters.active is not None:
+        deferred_bn_counters.active.append(counter)
+    else:
+        with torch.no_grad():
+            counter += 1
+
+
 def bn_act(bn, x, relu: bool, residual=None, momentum=None):
     """``[relu](bn(x) [+ residual])`` for an ``nn.BatchNorm2d``: the fused kernels when ``bn`` is in train() on channels_last
     half-precision CUDA activations (the autocast training step), the framework's own ops otherwise (fp32 / NCHW / eval)."""
@@ -119,8 +149,7 @@ def bn_act(bn, x, relu: bool, residual=None, momentum=None):
         if bn.track_running_stats:
             if m is None:                                     # cumulative moving average (momentum=None)
                 m = 1.0 / float(bn.num_batches_tracked + 1)
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
+            _bump(bn.num_batches_tracked)
             rm, rv = bn.running_mean, bn.running_var
         else:
             rm, rv, m = None, None, 0.0

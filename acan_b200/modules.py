@@ -353,8 +353,7 @@ class PixelAttentionBlock_(nn.Module):
         # batch-statistics kernels (fn.bn_act), otherwise as the framework's own ops
         feat = fn.bn_act(bn, self.f_key.conv(x), relu=True, momentum=bn.momentum * (2.0 - bn.momentum) if twice else None)
         if twice:
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
+            fn._bump(bn.num_batches_tracked)
         return feat
 
     def forward_att(self, x):

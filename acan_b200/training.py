@@ -263,7 +263,8 @@ class GraphedTrainStep:
         late_only = lambda ps: [p for p in ps if id(p) in self._late_ids]            # noqa: E731
         early_only = lambda ps: [p for p in ps if id(p) not in self._late_ids]       # noqa: E731
         if phase in (0, 1):
-            with torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
+            from .functions import deferred_bn_counters
+            with deferred_bn_counters(), torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
                 if self._shadows:
                     # tie_weights=False: f_query IS f_key (one module object, so one name reaches both), and with tie_weights=True the
                     # ORIGINAL parameter is handed a gradient as well -- under capture that left its .grad out of the optimizer graph
