@@ -557,9 +557,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   if (kl_row) {
                     const float lw0 = -fabsf(la_i - __ldg(la_cols + chh * 32 + j)) - lnz_i, lw1 = -fabsf(la_i - __ldg(la_cols + chh * 32 + j + 1)) - lnz_i;
                     const float w0 = ex2_approx(lw0 * kLog2e), w1 = ex2_approx(lw1 * kLog2e);
-                    const float lq0 = lg2_approx(pp.x) * kLn2, lq1 = lg2_approx(pp.y) * kLn2;
-                    const float in0 = (w0 > 0.f && fabsf(lw0 - lq0) < 18.420680744f) ? w0 : 0.f;
-                    const float in1 = (w1 > 0.f && fabsf(lw1 - lq1) < 18.420680744f) ? w1 : 0.f;
+                    // inside the clamp window 1e-8 < W / Q < 1e8 (losses.py:12,30), tested without a logarithm: Q 1e-8 < W < Q 1e8
+                    const float in0 = (w0 > pp.x * 1e-8f && w0 < pp.x * 1e8f) ? w0 : 0.f;
+                    const float in1 = (w1 > pp.y * 1e-8f && w1 < pp.y * 1e8f) ? w1 : 0.f;
                     d0 -= gks * (in0 - pp.x * t_i);
                     d1 -= gks * (in1 - pp.y * t_i);
                   } else if (kl) {
