@@ -16,6 +16,7 @@
 // against ~4 launches x several passes each of the framework's generic channels-last kernels.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cstdlib>
 
 namespace acan {
@@ -500,6 +501,144 @@ bn_fwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residu
   }
 }
 
+// ---------------------------------------------------------------- forward, activations staged in shared memory by TMA
+// When a block's share of the layer fits its shared memory (148 x ~190 KB = 28 MB: every layer of a ResNet at the configs[3] batch), the
+// block pulls its rows in with a handful of tensor-map copies (64 rows x one channel slab each: nothing passes through registers, and
+// all of the block's bytes are in flight at once instead of 8 loads per thread per round trip), takes the statistics from shared
+// memory as the boxes land, and after the slab barrier normalises the SAME shared-memory copy: x is read from HBM / L2 exactly once.
+// Rows are contiguous per block here ([row_lo, row_hi)); lanes map to channels and rows as in the kernels above.
+constexpr int kBnBoxRows = 64;        // rows per TMA box (a multiple of kBnRedY * rows_per_warp for every slab width)
+constexpr int kBnMaxBoxes = 24;
+constexpr int kBnTmaSmemMax = 190 * 1024;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(32 * kBnRedY, 1)
+bn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __restrict__ residual, uint4* __restrict__ y,
+                  const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ partial, int* __restrict__ counters,
+                  float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ running_mean, float* __restrict__ running_var,
+                  float momentum, float eps, int relu, int64_t M, int C, int slab_groups, int rows_per_block) {
+  extern __shared__ uint8_t bn_dyn_smem[];
+  uint8_t* cache = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bn_dyn_smem) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(16) float sm[kBnRedY * 32 * 16];
+  __shared__ float sc_s[kBnSlab], sh_s[kBnSlab];
+  __shared__ __align__(8) uint64_t bars[kBnMaxBoxes];
+  ColGeom g = col_geom(C, slab_groups);
+  if (g.rows_per_warp > 4) g.rows_per_warp = 4;                        // slabs of 1, 2 or 4 channel groups: a sweep must not exceed a box (64 rows)
+  const bool active = static_cast<int>(threadIdx.x) < g.groups * g.rows_per_warp;
+  const int c8 = C >> 3;
+  const int pitch = slab_groups * 16;                                  // bytes per staged row (the box is slab_groups * 8 channels wide)
+  const uint32_t box_bytes = static_cast<uint32_t>(kBnBoxRows) * pitch;
+  const int64_t row_lo = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t row_hi = (row_lo + rows_per_block < M) ? row_lo + rows_per_block : M;
+  const int nbox = static_cast<int>((row_hi - row_lo + kBnBoxRows - 1) / kBnBoxRows);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int j = 0; j < nbox; ++j) mbar_init(&bars[j], 1);
+    fence_barrier_init();
+    for (int j = 0; j < nbox; ++j) {
+      mbar_expect_tx(&bars[j], box_bytes);                             // rows beyond M arrive as zeros and count all the same
+      tma_load_2d(cache + static_cast<size_t>(j) * box_bytes, &tmap_x, &bars[j], blockIdx.x * slab_groups * 8,
+                  static_cast<int>(row_lo) + j * kBnBoxRows);
+    }
+  }
+  __syncthreads();
+  const int ri = kBnRedY * g.rows_per_warp;                            // rows one sweep of the block covers: 16, 32 or 64
+  const int sweeps = kBnBoxRows / ri;
+  const int my_row = threadIdx.y * g.rows_per_warp + g.rsub;           // row of this thread inside a sweep
+  const uint8_t* my_cache = cache + static_cast<size_t>(my_row) * pitch + g.cg * 16;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  for (int j = 0; j < nbox; ++j) {
+    mbar_wait(&bars[j], 0);
+    if (active) {
+      for (int k = 0; k < sweeps; ++k) {
+        const int i = j * kBnBoxRows + k * ri;
+        if (row_lo + i + my_row < row_hi) {
+          const uint4 u = *reinterpret_cast<const uint4*>(my_cache + static_cast<size_t>(i) * pitch);
+          float f[8];
+          unpack8<BF16>(u, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+        }
+      }
+    }
+  }
+  block_col_reduce(s, q, g, active, sm);
+  if (threadIdx.y == 0 && static_cast<int>(threadIdx.x) < g.groups) {
+    float* p = partial + (static_cast<size_t>(blockIdx.y) * C + (blockIdx.x * slab_groups + threadIdx.x) * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { p[2 * e] = s[e]; p[2 * e + 1] = q[e]; }
+  }
+  slab_barrier(counters + 2 * blockIdx.x, gridDim.y);
+  double S, Q;
+  const int nch = g.groups * 8, c0 = blockIdx.x * slab_groups * 8;
+  final_col_sum(partial, gridDim.y, C, c0, nch, reinterpret_cast<double*>(sm), S, Q);
+  if (tid < nch) {
+    const int c = c0 + tid;
+    const double mean = S / static_cast<double>(M);
+    double var = Q / static_cast<double>(M) - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float scv = __ldg(weight + c) * invstd;
+    sc_s[tid] = scv;
+    sh_s[tid] = __ldg(bias + c) - static_cast<float>(mean) * scv;
+    if (blockIdx.y == 0) {
+      save_mean[c] = static_cast<float>(mean);
+      save_invstd[c] = invstd;
+      if (running_mean != nullptr) {
+        const double unbiased = M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+      }
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = sc_s[g.cg * 8 + e]; sh[e] = sh_s[g.cg * 8 + e]; }
+  const int64_t off = blockIdx.x * slab_groups + g.cg;
+  const int total_sweeps = nbox * sweeps;
+  for (int t0 = 0; t0 < total_sweeps; t0 += 4) {                       // four rows per thread in flight (the residual comes from global memory)
+    uint4 ur[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t rr = row_lo + static_cast<int64_t>(t0 + i) * ri + my_row;
+      ur[i] = (residual != nullptr && rr < row_hi) ? ldg_nc_u4(residual + rr * c8 + off) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t rr = row_lo + static_cast<int64_t>(t0 + i) * ri + my_row;
+      if (rr < row_hi) {
+        const uint4 ux = *reinterpret_cast<const uint4*>(my_cache + static_cast<size_t>(t0 + i) * ri * pitch);
+        float f[8], rv[8];
+        unpack8<BF16>(ux, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
+        if (residual != nullptr) {
+          unpack8<BF16>(ur[i], rv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += rv[e];
+        }
+        if (relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+        }
+        y[rr * c8 + off] = pack8<BF16>(f);
+      }
+    }
+  }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(32 * kBnRedY)
 bn_bwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ gy, const float* __restrict__ weight,
@@ -679,6 +818,33 @@ int row_blocks_for(int64_t M, int C, int per_sm, int by, int rows_per_thread, in
   return static_cast<int>(rb);
 }
 
+// [M, C] activations as a 2-D tensor map: boxes of kBnBoxRows rows x box_ch channels, dense in shared memory, rows / channels beyond
+// the tensor read as zeros
+typedef CUresult (*BnEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_bn_tmap(CUtensorMap* m, const void* base, bool bf16, int64_t M, int C, int box_ch) {
+  static std::atomic<void*> fn_cache{nullptr};
+  void* p = fn_cache.load(std::memory_order_acquire);
+  if (!p) {
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      (void)cudaGetLastError();
+      return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    }
+    fn_cache.store(p, std::memory_order_release);
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(M)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_ch), static_cast<cuuint32_t>(kBnBoxRows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<BnEncodeTiledFn>(p)(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base),
+                                                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ACAN_ERR_DRIVER, "cuTensorMapEncodeTiled (BN activations) failed with CUresult %d (M=%lld C=%d box=%d)", (int)r, (long long)M, C, box_ch);
+  return 0;
+}
+
 int check_bn(const char* who, int64_t M, int C, int dtype) {
   if (M <= 0 || C <= 0 || (C % 8) != 0) return fail(ACAN_ERR_BAD_ARG, "%s: need M > 0 and C a positive multiple of 8 (M=%lld C=%d)", who, (long long)M, C);
   if (dtype != 0 && dtype != 1) return fail(ACAN_ERR_BAD_ARG, "%s: dtype %d (0 = fp16, 1 = bf16)", who, dtype);
@@ -717,8 +883,34 @@ extern "C" int acan_bn_train_fwd(const void* x, int dtype, const float* weight, 
   const uint4* rr = static_cast<const uint4*>(residual);
   if (bn_use_coop(C)) {
     CoopGrid cg = coop_grid(M, C, 8);
-    const dim3 cgrid(cg.slabs, cg.row_blocks);
     uint4* yw = static_cast<uint4*>(y);
+    {  // the layer fits the shared memory of the grid: stage it there by TMA and read x once (bn_fwd_tma_kernel)
+      int sg = cg.slab_groups < C / 8 ? cg.slab_groups : C / 8;
+      const int pitch = sg * 16;
+      int64_t R = (M + cg.row_blocks - 1) / cg.row_blocks;
+      R = (R + kBnBoxRows - 1) / kBnBoxRows * kBnBoxRows;
+      if (R * pitch <= kBnTmaSmemMax && R / kBnBoxRows <= kBnMaxBoxes && M < (1ll << 31) - 65536) {
+        CUtensorMap tm;
+        if (int e = make_bn_tmap(&tm, x, dtype == 1, M, C, sg * 8)) return e;
+        int rows_per_block = static_cast<int>(R);
+        const dim3 tgrid(cg.slabs, static_cast<unsigned>((M + R - 1) / R));
+        const size_t smem = static_cast<size_t>(R) * pitch + 1024;
+        const void* fn = dtype == 1 ? reinterpret_cast<const void*>(bn_fwd_tma_kernel<true>) : reinterpret_cast<const void*>(bn_fwd_tma_kernel<false>);
+        static std::atomic<uint64_t> done[2];
+        int dev = 0;
+        ACAN_CUDA(cudaGetDevice(&dev));
+        const uint64_t bit = 1ull << (dev & 63);
+        if (!(done[dtype].load(std::memory_order_acquire) & bit)) {
+          ACAN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBnTmaSmemMax + 1024));
+          done[dtype].fetch_or(bit, std::memory_order_release);
+        }
+        void* args[] = {&tm, &rr, &yw, &weight, &bias, &partial, &counters, &save_mean, &save_invstd, &running_mean, &running_var,
+                        &momentum, &eps, &relu, &M, &C, &sg, &rows_per_block};
+        ACAN_CUDA(cudaLaunchCooperativeKernel(fn, tgrid, rblock, args, smem, st));
+        return launch_status("bn_fwd_tma_kernel");
+      }
+    }
+    const dim3 cgrid(cg.slabs, cg.row_blocks);
     void* args[] = {&xr, &rr, &yw, &weight, &bias, &partial, &counters, &save_mean, &save_invstd, &running_mean, &running_var,
                     &momentum, &eps, &relu, &M, &C, &cg.slab_groups};
     const void* fn = dtype == 1 ? reinterpret_cast<const void*>(bn_fwd_coop_kernel<true>) : reinterpret_cast<const void*>(bn_fwd_coop_kernel<false>);

@@ -229,12 +229,14 @@ def test_decode_ord_backward_matches_autograd():
 # ------------------------------------------------------------------------------------ training-mode BN (+ ReLU, + residual)
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("b,c,h,w", [(2, 64, 16, 24), (2, 128, 8, 12), (3, 256, 8, 12), (2, 512, 4, 6), (2, 2048, 4, 6), (1, 24, 5, 7), (2, 320, 4, 4), (8, 64, 128, 176)])
+@pytest.mark.parametrize("b,c,h,w", [(2, 64, 16, 24), (2, 128, 8, 12), (3, 256, 8, 12), (2, 512, 4, 6), (2, 2048, 4, 6), (1, 24, 5, 7), (2, 320, 4, 4), (8, 64, 128, 176),
+                                     (8, 256, 64, 88), (8, 1024, 32, 44), (12, 64, 128, 176)])
 def test_fused_batchnorm_against_torch_fp64(b, c, h, w, dtype):
     """acan_bn_train_fwd / _bwd (nn.BatchNorm2d in train() + residual + ReLU on channels_last half activations) vs
     F.batch_norm + autograd in fp64 on the same (half-rounded) inputs: outputs and dx to half-precision rounding,
     dgamma / dbeta / running statistics to fp32 accuracy.  Widths cover 8-channel groups that fill a warp (>= 256), that
-    tile it (64, 128), that do not (24) and a ragged last slab (320)."""
+    tile it (64, 128), that do not (24) and a ragged last slab (320).  The forward stages a layer in shared memory by TMA when the
+    grid's shared memory holds it (bn_fwd_tma_kernel: every shape here but the last, 35 MB, which takes the two-pass cooperative kernel)."""
     from acan_b200 import functions as fn
     tol_half = 2e-3 if dtype == torch.float16 else 1.2e-2
     for relu, with_res in ((True, False), (False, False), (True, True)):
