@@ -41,6 +41,7 @@ SIGNATURES = {
     "acan_tail_loss_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "acan_tail_loss_bwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "acan_bn_ws_floats": (c_size_t, [c_int]),
+    "acan_bn_set_sm_limit": (c_int, [c_int]),
     "acan_bn_train_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_float, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "acan_bn_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_int64, c_int, c_void_p]),
     "acan_depth_metrics_ws_floats": (c_int, []),

@@ -77,7 +77,10 @@ __device__ __forceinline__ ColGeom col_geom(int C, int slab_groups = 32) {
   return g;
 }
 
-// block-level reduction of per-thread (a[8], b[8]) over the row dimension -> red[2][kBnSlab] valid for threads (y=0, rsub=0)
+// block-level reduction of per-thread (a[8], b[8]) over the row dimension -> valid for threads (y=0, x < groups).
+// Two steps, both with all 512 threads: thread (value v, lane x) sums the 16 warps' entries, then the <= 4 row sub-groups of a warp
+// are added by the receiving threads (the serial version -- 16 x rows_per_warp x 16 loads by `groups` threads -- cost ~1 us of the
+// ~10 us latency chain of a cooperative BN kernel).
 __device__ __forceinline__ void block_col_reduce(float (&a)[8], float (&b)[8], const ColGeom& g, bool active, float* sm /* [16][kBnRedY][32] */) {
   // element-major layout: the 32 lanes of a warp touch 32 consecutive words in every access (no bank conflicts)
 #pragma unroll
@@ -86,15 +89,24 @@ __device__ __forceinline__ void block_col_reduce(float (&a)[8], float (&b)[8], c
     sm[((8 + e) * kBnRedY + threadIdx.y) * 32 + threadIdx.x] = active ? b[e] : 0.f;
   }
   __syncthreads();
+  static_assert(kBnRedY == 16, "one thread per (value, lane) pair");
+  float t = 0.f;
+  {
+    const float* col = sm + (threadIdx.y * kBnRedY) * 32 + threadIdx.x;      // value index = threadIdx.y (0..15), lane = threadIdx.x
+#pragma unroll
+    for (int y = 0; y < kBnRedY; ++y) t += col[y * 32];
+  }
+  __syncthreads();
+  sm[threadIdx.y * 32 + threadIdx.x] = t;
+  __syncthreads();
   if (threadIdx.y == 0 && threadIdx.x < g.groups) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
-    for (int y = 0; y < kBnRedY; ++y)
-      for (int r = 0; r < g.rows_per_warp; ++r) {
-        const int lane = r * g.groups + threadIdx.x;
+    for (int r = 0; r < g.rows_per_warp; ++r) {
+      const int lane = r * g.groups + threadIdx.x;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { a[e] += sm[(e * kBnRedY + y) * 32 + lane]; b[e] += sm[((8 + e) * kBnRedY + y) * 32 + lane]; }
-      }
+      for (int e = 0; e < 8; ++e) { a[e] += sm[e * 32 + lane]; b[e] += sm[(8 + e) * 32 + lane]; }
+    }
   }
 }
 
@@ -182,7 +194,7 @@ bn_stats_kernel(const uint4* __restrict__ x, const float* __restrict__ weight, c
     const double mean = S / static_cast<double>(M);
     double var = Q / static_cast<double>(M) - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float invstd = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
     save_mean[c] = static_cast<float>(mean);
     save_invstd[c] = invstd;
     const float sc = weight[c] * invstd;
@@ -380,21 +392,29 @@ bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, co
 // slab's partials itself (in parallel, same fixed order -> identical results) and walks its rows again -- now L2 hits --
 // to write the output.  The grid is at most one block per SM (checked by the cooperative launch), so the barrier cannot
 // deadlock; a bounded spin traps instead of hanging if that is ever violated.
-__device__ __forceinline__ void slab_barrier(int* cnt /* [2]: arrive, depart; zero between launches */, int nblocks) {
+// Sense-reversing: `arrive` counts the blocks of the slab and is reset by the last one, `gen` flips once per barrier and is never reset
+// (any start value works).  One release-atomic and acquire-loads on the critical path; the version with an arrive and a depart counter
+// and two full fences cost ~2 us more per kernel.
+__device__ __forceinline__ void slab_barrier(int* arrive, int* gen, int nblocks) {
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
-    __threadfence();
-    atomicAdd(cnt, 1);
-    const long long t0 = clock64();
-    while (atomicAdd(cnt, 0) < nblocks) {
-      __nanosleep(40);
-      if (clock64() - t0 > 4000000000LL) {                  // ~2 s: blocks were not co-resident
-        printf("acan: BN slab barrier timeout (slab %d block %d of %d)\n", blockIdx.x, blockIdx.y, nblocks);
-        __trap();
-      }
+    int g0, old;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(g0) : "l"(gen) : "memory");       // cannot flip before this block has arrived
+    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(arrive) : "memory");
+    if (old == nblocks - 1) {
+      asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(arrive), "r"(0) : "memory");
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(gen), "r"(g0 + 1) : "memory");
+    } else {
+      const long long t0 = clock64();
+      int gn;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(gn) : "l"(gen) : "memory");
+        if (gn == g0 && clock64() - t0 > 4000000000LL) {      // ~2 s: blocks were not co-resident
+          printf("acan: BN slab barrier timeout (slab %d block %d of %d)\n", blockIdx.x, blockIdx.y, nblocks);
+          __trap();
+        }
+      } while (gn == g0);
     }
-    __threadfence();
-    if (atomicAdd(cnt + 1, 1) == nblocks - 1) { cnt[0] = 0; cnt[1] = 0; }      // the last block to leave resets both words
   }
   __syncthreads();
 }
@@ -440,7 +460,7 @@ bn_fwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residu
 #pragma unroll
     for (int e = 0; e < 8; ++e) { p[2 * e] = s[e]; p[2 * e + 1] = q[e]; }
   }
-  slab_barrier(counters + 2 * blockIdx.x, gridDim.y);
+  slab_barrier(counters + blockIdx.x, counters + kBnCounterSlots + blockIdx.x, gridDim.y);
   double S, Q;
   const int nch = g.groups * 8, c0 = blockIdx.x * slab_groups * 8;
   final_col_sum(partial, gridDim.y, C, c0, nch, reinterpret_cast<double*>(sm), S, Q);
@@ -450,7 +470,7 @@ bn_fwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residu
     const double mean = S / static_cast<double>(M);
     double var = Q / static_cast<double>(M) - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float invstd = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
     const float scv = __ldg(weight + c) * invstd;
     sc_s[tid] = scv;
     sh_s[tid] = __ldg(bias + c) - static_cast<float>(mean) * scv;
@@ -578,7 +598,7 @@ bn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __res
 #pragma unroll
     for (int e = 0; e < 8; ++e) { p[2 * e] = s[e]; p[2 * e + 1] = q[e]; }
   }
-  slab_barrier(counters + 2 * blockIdx.x, gridDim.y);
+  slab_barrier(counters + blockIdx.x, counters + kBnCounterSlots + blockIdx.x, gridDim.y);
   double S, Q;
   const int nch = g.groups * 8, c0 = blockIdx.x * slab_groups * 8;
   final_col_sum(partial, gridDim.y, C, c0, nch, reinterpret_cast<double*>(sm), S, Q);
@@ -587,7 +607,7 @@ bn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint4* __res
     const double mean = S / static_cast<double>(M);
     double var = Q / static_cast<double>(M) - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float invstd = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
     const float scv = __ldg(weight + c) * invstd;
     sc_s[tid] = scv;
     sh_s[tid] = __ldg(bias + c) - static_cast<float>(mean) * scv;
@@ -692,7 +712,7 @@ bn_bwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, con
 #pragma unroll
     for (int e = 0; e < 8; ++e) { p[2 * e] = sg[e]; p[2 * e + 1] = sx[e]; }
   }
-  slab_barrier(counters + 2 * blockIdx.x, gridDim.y);
+  slab_barrier(counters + blockIdx.x, counters + kBnCounterSlots + blockIdx.x, gridDim.y);
   double S, Q;
   const int nch = g.groups * 8, c0 = blockIdx.x * slab_groups * 8;
   final_col_sum(partial, gridDim.y, C, c0, nch, reinterpret_cast<double*>(sm), S, Q);
@@ -750,19 +770,25 @@ bn_bwd_coop_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, con
 // cooperative grids: at most one block per SM in total, and no more row blocks than the finalisation sums per thread.
 // Narrow layers (C <= 512) get narrower channel slabs (8 or 16 lane groups instead of 32; the spare lanes of a warp take further
 // rows) so that the grid still covers the machine: with 256-channel slabs a C = 256 layer would run on 32 SMs.
+// SMs the single-launch kernels may cover (acan_bn_set_sm_limit): a cooperative grid only starts when ALL its blocks fit at once, so next
+// to a long-running kernel that keeps some SMs to itself (an NCCL collective overlapping the backward pass) a 148-block grid waits for
+// that kernel to END.  The multi-GPU training step leaves NCCL's SMs out of these grids instead.
+std::atomic<int> g_bn_sm_limit{kNumSMs};
+
 struct CoopGrid { int slab_groups, slabs, row_blocks; };
 CoopGrid coop_grid(int64_t M, int C, int rows_per_thread) {
+  const int sms = g_bn_sm_limit.load(std::memory_order_relaxed);
   CoopGrid best = {32, (C + kBnSlab - 1) / kBnSlab, 1};
   long best_blocks = -1;
   const int cands[3] = {32, 16, 8};
   for (int L : cands) {
     const int c8 = C / 8;
     const int slabs = (c8 + L - 1) / L;
-    if (slabs > kNumSMs || 2 * slabs > kBnCounterSlots) continue;
+    if (slabs > sms || slabs > kBnCounterSlots) continue;
     const int groups = c8 < L ? c8 : L;
     const int rpw = (32 % groups) == 0 ? 32 / groups : 1;
     const int64_t rows_per_block_min = static_cast<int64_t>(kBnRedY) * rpw * rows_per_thread;
-    int64_t rb = kNumSMs / slabs;
+    int64_t rb = sms / slabs;
     const int64_t max_rb = (M + rows_per_block_min - 1) / rows_per_block_min;
     const int nch = groups * 8;
     const int64_t fin = static_cast<int64_t>(kBnFinalDepth) * ((32 * kBnRedY) / nch);
@@ -795,7 +821,7 @@ bool bn_use_coop(int C) {
 #ifdef ACAN_EXPERIMENT
   { const char* e = getenv("ACAN_BN_COOP"); v = (e && e[0] == '0') ? 0 : 1; }
 #endif
-  return v == 1 && (C + kBnSlab - 1) / kBnSlab <= kNumSMs && 2 * ((C + kBnSlab - 1) / kBnSlab) <= kBnCounterSlots;   // the 32-group candidate always fits then
+  return v == 1 && (C + kBnSlab - 1) / kBnSlab <= g_bn_sm_limit.load(std::memory_order_relaxed) && (C + kBnSlab - 1) / kBnSlab <= kBnCounterSlots;   // the 32-group candidate always fits then
 }
 
 // row blocks so that the whole grid is ~`per_sm` blocks per SM, with at least `rows_per_thread` rows for every thread of a block
@@ -857,11 +883,18 @@ int check_bn(const char* who, int64_t M, int C, int dtype) {
 
 using namespace acan;
 
-// scratch layout (floats): [kBnCounterSlots arrival counters (ints), at a C-independent place so that one zero-initialised
-// buffer serves layers of every width] [row-block partials kBnMaxRowBlocks x C x 2] [(scale, shift) | (A, Bc, Cc): 3 x C]
+// scratch layout (floats): [kBnCounterSlots arrival counters (ints; zero between calls) + kBnCounterSlots barrier generation words, at a
+// C-independent place so that one zero-initialised buffer serves layers of every width] [row-block partials kBnMaxRowBlocks x C x 2]
+// [(scale, shift) | (A, Bc, Cc): 3 x C]
+extern "C" int acan_bn_set_sm_limit(int n_sms) {
+  const int prev = g_bn_sm_limit.load(std::memory_order_relaxed);
+  if (n_sms > 0) g_bn_sm_limit.store(n_sms < 32 ? 32 : (n_sms > kNumSMs ? kNumSMs : n_sms), std::memory_order_relaxed);
+  return prev;
+}
+
 extern "C" size_t acan_bn_ws_floats(int C) {
   if (C <= 0) return 0;
-  return static_cast<size_t>(kBnCounterSlots) + static_cast<size_t>(kBnMaxRowBlocks) * C * 2 + 3 * static_cast<size_t>(C);
+  return 2 * static_cast<size_t>(kBnCounterSlots) + static_cast<size_t>(kBnMaxRowBlocks) * C * 2 + 3 * static_cast<size_t>(C);
 }
 
 extern "C" int acan_bn_train_fwd(const void* x, int dtype, const float* weight, const float* bias, const void* residual, void* y,
@@ -874,7 +907,7 @@ extern "C" int acan_bn_train_fwd(const void* x, int dtype, const float* weight, 
                  reinterpret_cast<uintptr_t>(ws) % 16 == 0, "acan_bn_train_fwd: tensors must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int* counters = reinterpret_cast<int*>(ws);
-  float* partial = ws + kBnCounterSlots;
+  float* partial = ws + 2 * kBnCounterSlots;
   float* scale_shift = partial + static_cast<size_t>(kBnMaxRowBlocks) * C * 2;
   const int slabs = (C + kBnSlab - 1) / kBnSlab;
   const dim3 rgrid(slabs, row_blocks_for(M, C, 2, kBnRedY, 8, kBnMaxRowBlocks)), rblock(32, kBnRedY);
@@ -942,7 +975,7 @@ extern "C" int acan_bn_train_bwd(const void* x, const void* y, const void* grad_
                  "acan_bn_train_bwd: tensors must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int* counters = reinterpret_cast<int*>(ws);
-  float* partial = ws + kBnCounterSlots;
+  float* partial = ws + 2 * kBnCounterSlots;
   float* coef = partial + static_cast<size_t>(kBnMaxRowBlocks) * C * 2;
   const int slabs = (C + kBnSlab - 1) / kBnSlab;
   const dim3 rgrid(slabs, row_blocks_for(M, C, 1, kBnRedY, 4, kBnMaxRowBlocks)), rblock(32, kBnRedY);   // 94 registers x 512 threads: one block per SM

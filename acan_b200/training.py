@@ -19,9 +19,10 @@ only the first piece's collective and the last piece's update are exposed.  Its 
 optimizer keeps ``optimizer.step()`` in its own CUDA graph, re-captured when the hyper-parameters change (eager after three changes).
 
 ``overlap=True`` instead splits the backward at the output of layer3 into two graphs and averages the late layers' gradients while the
-second replays.  Measured on 2 B200s (scripts/ddp_overlap_probe.py, profiles/r02_notes.md): the collective does run concurrently, but the
-step is no faster -- the cooperative BatchNorm kernels of the second graph need every SM and cannot be co-scheduled with NCCL's resident
-CTAs, so the graph stalls for as long as the collective runs.  Kept as an option, off by default.
+second replays.  Measured on 2 B200s (scripts/ddp_overlap_probe.py, profiles/r02_notes.md): the collective does run concurrently, but
+cooperative BatchNorm grids that need every SM cannot start while NCCL's CTAs are resident, so the second graph stalled for as long as
+the collective ran.  The step therefore captures its BN grids over 148 - ``nccl_sms`` SMs and expects a communicator capped to
+``nccl_sms`` CTAs (``parallel.init_distributed(max_ctas=...)``).
 """
 from __future__ import annotations
 
@@ -54,7 +55,7 @@ class GraphedTrainStep:
 
     def __init__(self, net, criterion, optimizer, images: torch.Tensor, labels: torch.Tensor, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  reducer=None, epoch: int = 1, warmup: int = 3, graph: bool = True, after_backward: Optional[Callable[[], None]] = None,
-                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4):
+                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16):
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors: acan_b200 has no CPU path")
         self.net, self.criterion, self.optimizer, self.reducer = net, criterion, optimizer, reducer
@@ -107,18 +108,26 @@ class GraphedTrainStep:
             s_.grad = None
         from . import _lib
         n0 = _lib.load().acan_launch_count()
+        sm_limit = None
         if self._split:
             self._hook = net.layer3.register_forward_hook(self._grab_boundary)
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            self.losses = self._forward_backward(phase=1 if self._split else 0)
-        self.graphs = [g1]
-        if self._split:
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, pool=g1.pool()):
-                self._forward_backward(phase=2)
-            self.graphs.append(g2)
-            self._hook.remove()
+            # the cooperative BN grids captured below leave `nccl_sms` SMs to the collective that runs beside the second graph (a
+            # cooperative grid starts only when all of its blocks fit at once; the communicator is capped with init_distributed(max_ctas=))
+            sm_limit = _lib.load().acan_bn_set_sm_limit(148 - int(nccl_sms))
+        try:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self.losses = self._forward_backward(phase=1 if self._split else 0)
+            self.graphs = [g1]
+            if self._split:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g1.pool()):
+                    self._forward_backward(phase=2)
+                self.graphs.append(g2)
+                self._hook.remove()
+        finally:
+            if sm_limit is not None:
+                _lib.load().acan_bn_set_sm_limit(sm_limit)
         self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0)        # kernels of libacan_b200 in one replay
         if self._flat_sgd and self._never_grad:
             # parameters autograd never reached: torch.optim.SGD skips them (no weight decay, no momentum); the frozen table row does the same

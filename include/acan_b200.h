@@ -142,6 +142,10 @@ int acan_maxpool3x3s2_nhwc(const void* x, void* y, int dtype, int B, int H, int 
  *   backward: y = the forward output when a ReLU was fused (its sign is the mask), else NULL; grad_residual: NULL, or receives the
  *       masked upstream gradient (what flows into the residual branch); grad_weight / grad_bias [C] fp32. */
 size_t acan_bn_ws_floats(int C);
+/* SMs the single-launch (cooperative) BN grids may cover, 32..148 (default 148); returns the previous value, n_sms <= 0 only queries.
+ * A cooperative grid starts only when all its blocks fit at once: a training step that overlaps an NCCL collective with its backward
+ * pass leaves NCCL's SMs out (acan_b200.training.GraphedTrainStep(overlap=True)).  Process-wide; read at launch (so at graph capture). */
+int acan_bn_set_sm_limit(int n_sms);
 int acan_bn_train_fwd(const void* x, int dtype, const float* weight, const float* bias, const void* residual, void* y,
                       float* save_mean, float* save_invstd, float* running_mean, float* running_var,
                       float momentum, float eps, int relu, float* ws, int64_t M, int C, void* stream);

@@ -266,9 +266,13 @@ def test_fused_batchnorm_against_torch_fp64(b, c, h, w, dtype):
             yc = torch.relu(yc)
         yc.backward(go.double())
         close(y.float(), yc, tol_half)
-        close(xd.grad.float(), xc.grad, tol_half)
+        # the ReLU mask of an element within fp32 rounding of the threshold may differ from fp64's (one in ~1e7 elements at these
+        # magnitudes: the large shapes have some): its whole gradient flips, which is not an arithmetic error -- compare away from it
+        away = (yc.detach().abs() > 1e-5).to(DEV) if relu else torch.ones_like(xd.grad, dtype=torch.bool)
+        assert float((~away).float().mean()) < 1e-4
+        close(xd.grad.float() * away, xc.grad * away.cpu(), tol_half)
         if with_res:
-            close(rd.grad.float(), rc.grad, tol_half)
+            close(rd.grad.float() * away, rc.grad * away.cpu(), tol_half)
         close(bn.weight.grad, wc.grad, 2e-3 if dtype == torch.float16 else 1e-2)       # the ReLU mask is taken from the ROUNDED output
         close(bn.bias.grad, bc.grad, 2e-3 if dtype == torch.float16 else 1e-2)
         close(bn.running_mean, rm, 1e-5)
