@@ -644,85 +644,84 @@ tail_loss_fwd_kernel(const float* __restrict__ z, const int64_t* __restrict__ la
   }
 }
 
-// one thread per (b, sr, sc, k), k fastest: z loads / gradient stores of a warp are contiguous, label loads broadcast.
-// An output pixel (Y,X) touches source row sr either as its upper tap row (h1 == sr) or as its lower one (h1 == sr - 1); the
-// vertical blend of the three source columns is formed once per Y, the horizontal one per X with the two tap columns fixed by
-// the case -- no register-array indexing.  The lanes of a warp share (sr,sc) (a warp spans <= 2 source pixels), so the case
-// branches are uniform.  p is evaluated as 1 / (1 + exp(y0 - y1)) with the fast intrinsics: the gradient needs ~1e-6, not the
-// bit pattern of the reference's e1 / (e0 + e1) that the forward / inference kernels reproduce.
+// Backward of the fused tail loss.  The output pixels whose upper-left tap is source pixel (sr, sc) form that pixel's CELL (~8 x 8
+// outputs: floor(rh Y) == sr, floor(rw X) == sc with the forward's own arithmetic).  One thread per (cell, bin k) walks its cell once,
+// evaluates dL/dy1 of every output pixel ONCE and accumulates it towards the cell's four corners (the version with one thread per
+// SOURCE pixel gathered from the four cells around it and so evaluated every exp / reciprocal four times: 0.50 ms of a 13.7 ms
+// training step).  Corners are then combined without any order-dependent arithmetic: the cell to the left hands its right-hand
+// corners over through shared memory (lanes are consecutive cells; a block recomputes one halo cell), and the two cell ROWS that meet
+// in a source row each add once into the zero-initialised gradient -- two contributions, and fl(a + b) = fl(b + a).
+// p is evaluated as 1 / (1 + exp(y0 - y1)) with the fast intrinsics on the interpolated DIFFERENCE of the pair: the gradient needs
+// ~1e-6, not the bit pattern of the reference's e1 / (e0 + e1) that the forward / inference kernels reproduce.
+constexpr int kTlbCells = kThreads - 1;       // cells a block owns; thread 0 recomputes the cell in front of them
+
 __global__ void __launch_bounds__(kThreads)
 tail_loss_bwd_kernel(const float* __restrict__ z, const int64_t* __restrict__ label, const float* __restrict__ count,
-                     const float* __restrict__ grad_out, float* __restrict__ gz, int h, int w, int K, int64_t total, int ignore_index) {
-  const int64_t t = blockIdx.x * (int64_t)kThreads + threadIdx.x;
-  if (t >= total) return;
-  const int k = (int)(t % K);
-  const int64_t pix = t / K;
-  const int sc = (int)(pix % w), sr = (int)((pix / w) % h), b = (int)(pix / ((int64_t)w * h));
+                     const float* __restrict__ grad_out, float* __restrict__ gz, int B, int h, int w, int K, int ignore_index) {
+  __shared__ float s01[kThreads], s11[kThreads];
+  const int k = blockIdx.y;
+  const int64_t n_cells = (int64_t)B * h * w;
+  const int64_t cell = (int64_t)blockIdx.x * kTlbCells + (int)threadIdx.x - 1;
+  const bool valid = cell >= 0 && cell < n_cells;
   const int C = 2 * K, H = 8 * h, W = 8 * w;
-  const float g = __ldg(grad_out) / __ldg(count);
-  const float rh = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
-  const float rw = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  float2 zt[3][3];                                        // rows sr-1..sr+1, columns sc-1..sc+1 (clamped; clamped taps are never selected)
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int rr = min(max(sr - 1 + i, 0), h - 1), cc = min(max(sc - 1 + j, 0), w - 1);
-      zt[i][j] = __ldg(reinterpret_cast<const float2*>(z + (((int64_t)b * h + rr) * w + cc) * C) + k);
-    }
-  // candidate output rows / columns: rh * Y in [sr - 1, sr + 1); membership is re-checked with the forward's own arithmetic
-  const int Ylo = (h > 1) ? max(0, (int)((float)(sr - 1) / rh) - 1) : 0, Yhi = (h > 1) ? min(H - 1, (int)((float)(sr + 1) / rh) + 1) : H - 1;
-  const int Xlo = (w > 1) ? max(0, (int)((float)(sc - 1) / rw) - 1) : 0, Xhi = (w > 1) ? min(W - 1, (int)((float)(sc + 1) / rw) + 1) : W - 1;
-  const bool last_r = sr == h - 1, last_c = sc == w - 1;   // both taps of the last row / column coincide
-  const int64_t* lab_b = label + (int64_t)b * H * W;
-  float acc = 0.f;
-  for (int Y = Ylo; Y <= Yhi; ++Y) {
-    const float h1r = rh * (float)Y;
-    const int h1 = (int)h1r;
-    const float h1l = h1r - (float)h1, h0l = 1.f - h1l;
-    float2 v[3];
-    float wy;
-    if (h1 == sr - 1) {                                    // (sr - 1 < h - 1 always: the lower tap is row sr)
-      wy = h1l;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) v[j] = make_float2(h0l * zt[0][j].x + h1l * zt[1][j].x, h0l * zt[0][j].y + h1l * zt[1][j].y);
-    } else if (h1 == sr) {
-      wy = last_r ? 1.f : h0l;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float2 lo = last_r ? zt[1][j] : zt[2][j];
-        v[j] = make_float2(h0l * zt[1][j].x + h1l * lo.x, h0l * zt[1][j].y + h1l * lo.y);
+  float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+  int sc = 0, sr = 0, b = 0;
+  if (valid) {
+    sc = (int)(cell % w); sr = (int)((cell / w) % h); b = (int)(cell / ((int64_t)w * h));
+    const float rh = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    const float rw = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const bool last_r = sr == h - 1, last_c = sc == w - 1;       // both taps of the last row / column coincide
+    const int r1 = last_r ? sr : sr + 1, c1 = last_c ? sc : sc + 1;
+    auto pair_diff = [&](int rr, int cc) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(z + (((int64_t)b * h + rr) * w + cc) * C) + k);
+      return v.x - v.y;
+    };
+    const float d00 = pair_diff(sr, sc), d01 = pair_diff(sr, c1), d10 = pair_diff(r1, sc), d11 = pair_diff(r1, c1);
+    // candidate output rows / columns around the cell; membership is decided by the forward's own arithmetic
+    const int Ylo = (h > 1) ? max(0, (int)((float)sr / rh) - 1) : 0, Yhi = (h > 1) ? min(H - 1, (int)((float)(sr + 1) / rh) + 1) : H - 1;
+    const int Xlo = (w > 1) ? max(0, (int)((float)sc / rw) - 1) : 0, Xhi = (w > 1) ? min(W - 1, (int)((float)(sc + 1) / rw) + 1) : W - 1;
+    const int64_t* lab_b = label + (int64_t)b * H * W;
+    for (int Y = Ylo; Y <= Yhi; ++Y) {
+      const float h1r = rh * (float)Y;
+      const int h1 = (int)h1r;
+      if (h1 != sr) continue;
+      const float h1l = h1r - (float)h1, h0l = 1.f - h1l;
+      const float vl = h0l * d00 + h1l * d10, vr = h0l * d01 + h1l * d11;
+      const int64_t* lab_y = lab_b + (int64_t)Y * W;
+      float racc0 = 0.f, racc1 = 0.f;
+      for (int X = Xlo; X <= Xhi; ++X) {
+        const float w1r = rw * (float)X;
+        const int w1 = (int)w1r;
+        if (w1 != sc) continue;
+        const int l = (int)__ldg(lab_y + X);
+        if (l == ignore_index) continue;
+        const float w1l = w1r - (float)w1, w0l = 1.f - w1l;
+        const float dyl = w0l * vl + w1l * vr;                        // y0 - y1 at (Y, X)
+        const float p = __fdividef(1.0f, 1.0f + __expf(dyl)), q = 1.0f - p;
+        const float dy1 = (k < l) ? ((p > 1e-8f) ? -q : 0.f) : ((q > 1e-8f) ? p : 0.f);      // clamp windows of log(p) / log(1 - p)
+        racc0 = fmaf(last_c ? w0l + w1l : w0l, dy1, racc0);
+        racc1 = fmaf(last_c ? 0.f : w1l, dy1, racc1);
       }
-    } else {
-      continue;
+      const float wy0 = last_r ? h0l + h1l : h0l, wy1 = last_r ? 0.f : h1l;
+      c00 = fmaf(wy0, racc0, c00); c01 = fmaf(wy0, racc1, c01);
+      c10 = fmaf(wy1, racc0, c10); c11 = fmaf(wy1, racc1, c11);
     }
-    const float2 vr = last_c ? v[1] : v[2];
-    const int64_t* lab_y = lab_b + (int64_t)Y * W;
-    float rowacc = 0.f;
-    for (int X = Xlo; X <= Xhi; ++X) {
-      const float w1r = rw * (float)X;
-      const int w1 = (int)w1r;
-      const float w1l = w1r - (float)w1, w0l = 1.f - w1l;
-      float dyl, wx;                                       // y0 - y1 at (Y,X), weight of column sc in it
-      if (w1 == sc - 1) {
-        wx = w1l;
-        dyl = (w0l * v[0].x + w1l * v[1].x) - (w0l * v[0].y + w1l * v[1].y);
-      } else if (w1 == sc) {
-        wx = last_c ? 1.f : w0l;
-        dyl = (w0l * v[1].x + w1l * vr.x) - (w0l * v[1].y + w1l * vr.y);
-      } else {
-        continue;
-      }
-      const int l = (int)__ldg(lab_y + X);
-      if (l == ignore_index) continue;
-      const float p = __fdividef(1.0f, 1.0f + __expf(dyl)), q = 1.0f - p;
-      const float dy1 = (k < l) ? ((p > 1e-8f) ? -q : 0.f) : ((q > 1e-8f) ? p : 0.f);      // clamp windows of log(p) / log(1 - p)
-      rowacc = fmaf(wx, dy1, rowacc);
-    }
-    acc = fmaf(wy, rowacc, acc);
   }
-  acc *= g;
-  *reinterpret_cast<float2*>(gz + pix * C + 2 * k) = make_float2(-acc, acc);
+  s01[threadIdx.x] = c01;
+  s11[threadIdx.x] = c11;
+  __syncthreads();
+  if (!valid || threadIdx.x == 0) return;
+  // the cell to the left (lane - 1) owns the right-hand corners that land in this column; the last cell of the previous row has none
+  const float g = __ldg(grad_out) / __ldg(count);
+  const float top = (c00 + s01[threadIdx.x - 1]) * g, bot = (c10 + s11[threadIdx.x - 1]) * g;
+  float* dst = gz + (((int64_t)b * h + sr) * w + sc) * C + 2 * k;
+  atomicAdd(dst, -top);
+  atomicAdd(dst + 1, top);
+  if (sr < h - 1) {
+    dst += (int64_t)w * C;
+    atomicAdd(dst, -bot);
+    atomicAdd(dst + 1, bot);
+  }
 }
 
 }  // namespace
@@ -753,11 +752,13 @@ extern "C" int acan_tail_loss_bwd(const float* z_nhwc, const int64_t* label, con
   ACAN_CHECK_ARG(z_nhwc && label && count && grad_out && grad_z_nhwc, "acan_tail_loss_bwd: null pointer");
   ACAN_CHECK_ARG(B > 0 && h > 0 && w > 0 && K > 0, "acan_tail_loss_bwd: sizes must be positive");
   ACAN_CHECK_ARG(reinterpret_cast<uintptr_t>(z_nhwc) % 8 == 0 && reinterpret_cast<uintptr_t>(grad_z_nhwc) % 8 == 0, "acan_tail_loss_bwd: alignment");
-  const int64_t total = (int64_t)B * h * w * K;
-  const int64_t blocks = (total + kThreads - 1) / kThreads;
+  ACAN_CHECK_ARG(K <= 65535, "acan_tail_loss_bwd: K=%d too large", K);
+  const int64_t n_cells = (int64_t)B * h * w;
+  const int64_t blocks = (n_cells + kTlbCells - 1) / kTlbCells;
   ACAN_CHECK_ARG(blocks <= 0x7fffffffLL, "acan_tail_loss_bwd: problem too large");
-  tail_loss_bwd_kernel<<<(unsigned)blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(z_nhwc, label, count, grad_out, grad_z_nhwc, h, w, K, total,
-                                                                                            ignore_index);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ACAN_CUDA(cudaMemsetAsync(grad_z_nhwc, 0, static_cast<size_t>(n_cells) * 2 * K * sizeof(float), st));      // every element takes <= 2 additions
+  tail_loss_bwd_kernel<<<dim3((unsigned)blocks, (unsigned)K), kThreads, 0, st>>>(z_nhwc, label, count, grad_out, grad_z_nhwc, B, h, w, K, ignore_index);
   return launch_status("acan_tail_loss_bwd");
 }
 

@@ -262,13 +262,14 @@ def test_fused_batchnorm_against_torch_fp64(b, c, h, w, dtype):
         yc = torch.nn.functional.batch_norm(xc, rm, rv, wc, bc, True, 0.1, bn.eps)
         if with_res:
             yc = yc + rc
+        pre = yc.detach()
         if relu:
             yc = torch.relu(yc)
         yc.backward(go.double())
         close(y.float(), yc, tol_half)
         # the ReLU mask of an element within fp32 rounding of the threshold may differ from fp64's (one in ~1e7 elements at these
         # magnitudes: the large shapes have some): its whole gradient flips, which is not an arithmetic error -- compare away from it
-        away = (yc.detach().abs() > 1e-5).to(DEV) if relu else torch.ones_like(xd.grad, dtype=torch.bool)
+        away = (pre.abs() > 1e-5).to(DEV) if relu else torch.ones_like(xd.grad, dtype=torch.bool)
         assert float((~away).float().mean()) < 1e-4
         close(xd.grad.float() * away, xc.grad * away.cpu(), tol_half)
         if with_res:
@@ -277,6 +278,31 @@ def test_fused_batchnorm_against_torch_fp64(b, c, h, w, dtype):
         close(bn.bias.grad, bc.grad, 2e-3 if dtype == torch.float16 else 1e-2)
         close(bn.running_mean, rm, 1e-5)
         close(bn.running_var, rv, 1e-5)
+
+
+def test_batchnorm_grids_with_an_sm_limit_give_the_same_results():
+    """acan_bn_set_sm_limit: the single-launch BN grids sized for 100 SMs (what the overlapped multi-GPU step does to leave room for
+    NCCL) produce the same outputs, statistics and gradients as the full-machine grids, to summation-order rounding."""
+    from acan_b200 import _lib, ops
+    lib = _lib.load()
+    res = {}
+    for b, c, h, w in ((8, 256, 32, 44), (4, 1024, 16, 22), (2, 64, 64, 88)):
+        x = (1.5 * synth.randn(f"bnlim.{c}.x", b, c, h, w) + 0.3).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+        go = synth.randn(f"bnlim.{c}.g", b, c, h, w).to(torch.bfloat16).to(DEV).contiguous(memory_format=torch.channels_last)
+        wgt, bia = (1.0 + 0.2 * synth.randn(f"bnlim.{c}.w", c)).to(DEV), (0.1 * synth.randn(f"bnlim.{c}.b", c)).to(DEV)
+        for limit in (148, 100):
+            prev = lib.acan_bn_set_sm_limit(limit)
+            try:
+                rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+                y, mean, invstd = ops.bn_train_forward(x, wgt, bia, rm, rv, 0.1, 1e-5, True, None)
+                gx, _, gw, gb = ops.bn_train_backward(x, y, go, wgt, mean, invstd, False)
+                res[limit] = [t.float().clone() for t in (y, mean, invstd, rm, rv, gx, gw, gb)]
+            finally:
+                assert lib.acan_bn_set_sm_limit(prev) == limit
+        assert lib.acan_bn_set_sm_limit(0) == 148
+        for a, b_ in zip(res[148], res[100]):
+            close(a, b_, 1e-5 if a.dim() == 1 else 1e-2)
+        assert torch.equal(res[148][0] == 0, res[100][0] == 0) or float(((res[148][0] == 0) != (res[100][0] == 0)).float().mean()) < 1e-5
 
 
 def test_fused_batchnorm_training_step_matches_framework_bn():
