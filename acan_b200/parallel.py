@@ -14,12 +14,13 @@ import torch
 import torch.distributed as dist
 
 
-def init_distributed(backend: Optional[str] = None, high_priority: bool = True, max_ctas: Optional[int] = None) -> tuple:
+def init_distributed(backend: Optional[str] = None, high_priority: bool = True, max_ctas: Optional[int] = None, min_ctas: Optional[int] = None) -> tuple:
     """(rank, world_size, local_rank) from the torchrun environment; no-op for a single process.  ``high_priority``: the NCCL
     communicator's stream gets the high CUDA priority, so the CTAs of a gradient all-reduce are placed as soon as SMs free up under the
     backward pass that is still replaying (at equal priority they queue behind every pending CTA of the compute kernels).
     ``max_ctas``: upper bound on the CTAs (= SMs) a collective of this communicator occupies (ncclConfig_t.maxCTAs); the overlapped
-    training step (``GraphedTrainStep(overlap=True, nccl_sms=...)``) sizes its cooperative BatchNorm grids to the SMs left over."""
+    training step (``GraphedTrainStep(overlap=True, nccl_sms=...)``) sizes its cooperative BatchNorm grids to the SMs left over.
+    ``min_ctas``: lower bound (ncclConfig_t.minCTAs) -- an exposed all-reduce has the GPU to itself and may use more channels."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -30,11 +31,13 @@ def init_distributed(backend: Optional[str] = None, high_priority: bool = True, 
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
-            if high_priority or max_ctas:
+            if high_priority or max_ctas or min_ctas:
                 opts = dist.ProcessGroupNCCL.Options()
                 opts.is_high_priority_stream = bool(high_priority)
                 if max_ctas:
                     opts.config.max_ctas = int(max_ctas)
+                if min_ctas:
+                    opts.config.min_ctas = int(min_ctas)
                 kw["pg_options"] = opts
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local

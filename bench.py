@@ -550,6 +550,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying their CUDA graphs")
     ap.add_argument("--split-backward", action="store_true", help="train, N > 1: split the backward at layer3 and all-reduce the late layers beside the second graph (A/B)")
     ap.add_argument("--nccl-sms", type=int, default=16, help="with --split-backward: CTAs of the NCCL communicator = SMs the BN grids of the step leave free")
+    ap.add_argument("--nccl-min-ctas", type=int, default=0, help="N > 1: lower bound on the CTAs of a collective (ncclConfig_t.minCTAs); 0 = NCCL's default")
     ap.add_argument("--pieces", type=int, default=4, help="train, N > 1: pieces of the flat gradient buffer (all-reduce of piece k+1 runs beside the update of piece k)")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[3]/[4] training sub-record")
     ap.add_argument("--no-long", action="store_true", help="skip the >= 1 s repetition of the timed region (runs under ncu)")
@@ -576,7 +577,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    init_distributed("nccl" if world > 1 else None, max_ctas=args.nccl_sms if args.split_backward else None)
+    init_distributed("nccl" if world > 1 else None, max_ctas=args.nccl_sms if args.split_backward else None,
+                     min_ctas=args.nccl_min_ctas or None)
     lib = _lib.load()
     _lib.check(lib.acan_device_check(), "acan_device_check")
     torch.backends.cudnn.benchmark = True                 # as depthest_main.py:65

@@ -11,7 +11,8 @@ from acan_b200.network import ResNet, OrdinalRegression2d
 from acan_b200.modules import AttentionLoss2d
 from acan_b200.training import GraphedTrainStep
 
-rank, world, local = init_distributed("nccl")
+NCCL_SMS = int(os.environ.get("PROBE_NCCL_SMS", "16"))
+rank, world, local = init_distributed("nccl", max_ctas=NCCL_SMS)
 dev = torch.device("cuda", local)
 torch.backends.cudnn.benchmark = True
 H, W, B, K = 256, 352, 8, 80
@@ -22,7 +23,7 @@ opt = torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9, weight_decay=5e-4
 red = GradAllReducer(net.parameters())
 x = torch.rand(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
 y = (torch.rand(B, 1, H, W, device=dev) * 10 + 0.5)
-step = GraphedTrainStep(net, crit, opt, x, y, amp_dtype=torch.bfloat16, reducer=red)
+step = GraphedTrainStep(net, crit, opt, x, y, amp_dtype=torch.bfloat16, reducer=red, overlap=True, nccl_sms=NCCL_SMS)
 assert step._split
 for _ in range(5):
     step(x, y)
@@ -30,6 +31,14 @@ torch.cuda.synchronize(); dist.barrier()
 main = torch.cuda.current_stream(dev)
 comm = torch.cuda.Stream(dev, priority=-1)
 ev = lambda: torch.cuda.Event(enable_timing=True)
+# the two graphs back to back with no collective in between: what the split itself costs
+for _ in range(3):
+    a, b_ = ev(), ev()
+    a.record(main); step.graphs[0].replay(); m_ = ev(); m_.record(main); step.graphs[1].replay(); b_.record(main)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(f"no collective: first graph {a.elapsed_time(m_):.3f} ms, second graph {m_.elapsed_time(b_):.3f} ms, both {a.elapsed_time(b_):.3f} ms", flush=True)
+dist.barrier()
 rows = []
 for it in range(8):
     e = {k: ev() for k in ("t0", "g1", "ar1s", "ar1e", "g2", "ar2e", "opt")}
@@ -48,7 +57,7 @@ for it in range(8):
         dist.all_reduce(step._flat[:step._n_early], op=dist.ReduceOp.AVG)
         e["ar2e"].record(comm)
     main.wait_stream(comm)
-    step.opt_graph.replay()
+    step._sgd_range(0, step._n_sgd_chunks)
     e["opt"].record(main)
     torch.cuda.synchronize()
     rows.append({k: e["t0"].elapsed_time(v) for k, v in e.items() if k != "t0"})
