@@ -38,9 +38,22 @@ def init_distributed(backend: Optional[str] = None, high_priority: bool = True, 
                     opts.config.max_ctas = int(max_ctas)
                 if min_ctas:
                     opts.config.min_ctas = int(min_ctas)
+                    if not max_ctas:
+                        opts.config.max_ctas = max(int(min_ctas), 32)      # NCCL rejects a lower bound without an upper one
                 kw["pg_options"] = opts
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
+
+
+def capped_group(max_ctas: int, high_priority: bool = True):
+    """A second NCCL communicator over all ranks whose collectives occupy at most ``max_ctas`` SMs: the one an overlapped step issues
+    the collective that runs BESIDE compute kernels on (the default communicator keeps its full width for the exposed collectives)."""
+    if not (dist.is_initialized() and dist.get_backend() == "nccl"):
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = bool(high_priority)
+    opts.config.max_ctas = int(max_ctas)
+    return dist.new_group(ranks=list(range(dist.get_world_size())), backend="nccl", pg_options=opts)
 
 
 def shard_bounds(n_items: int, rank: int, world: int) -> tuple:

@@ -21,8 +21,9 @@ optimizer keeps ``optimizer.step()`` in its own CUDA graph, re-captured when the
 ``overlap=True`` instead splits the backward at the output of layer3 into two graphs and averages the late layers' gradients while the
 second replays.  Measured on 2 B200s (scripts/ddp_overlap_probe.py, profiles/r02_notes.md): the collective does run concurrently, but
 cooperative BatchNorm grids that need every SM cannot start while NCCL's CTAs are resident, so the second graph stalled for as long as
-the collective ran.  The step therefore captures its BN grids over 148 - ``nccl_sms`` SMs and expects a communicator capped to
-``nccl_sms`` CTAs (``parallel.init_distributed(max_ctas=...)``).
+the collective ran.  The step therefore captures the BN grids of the second graph over 148 - ``nccl_sms`` SMs and issues that collective on
+``overlap_group``, a communicator capped to ``nccl_sms`` CTAs (``parallel.capped_group``); the exposed collective of the early layers
+keeps the default communicator's full width.
 """
 from __future__ import annotations
 
@@ -55,7 +56,7 @@ class GraphedTrainStep:
 
     def __init__(self, net, criterion, optimizer, images: torch.Tensor, labels: torch.Tensor, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  reducer=None, epoch: int = 1, warmup: int = 3, graph: bool = True, after_backward: Optional[Callable[[], None]] = None,
-                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16):
+                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16, overlap_group=None):
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors: acan_b200 has no CPU path")
         self.net, self.criterion, self.optimizer, self.reducer = net, criterion, optimizer, reducer
@@ -64,6 +65,7 @@ class GraphedTrainStep:
         self.static_y = labels.clone()
         self.world = getattr(reducer, "world", 1) if reducer is not None else 1
         self.group = getattr(reducer, "group", None)
+        self.overlap_group = overlap_group if overlap_group is not None else self.group     # communicator of the collective that runs beside graph 2
         if shadow_weights is None:
             shadow_weights = amp_dtype in (torch.float16, torch.bfloat16)
         self._shadow_names, self._shadow_params, self._shadows = [], [], []
@@ -108,26 +110,24 @@ class GraphedTrainStep:
             s_.grad = None
         from . import _lib
         n0 = _lib.load().acan_launch_count()
-        sm_limit = None
         if self._split:
             self._hook = net.layer3.register_forward_hook(self._grab_boundary)
-            # the cooperative BN grids captured below leave `nccl_sms` SMs to the collective that runs beside the second graph (a
-            # cooperative grid starts only when all of its blocks fit at once; the communicator is capped with init_distributed(max_ctas=))
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self.losses = self._forward_backward(phase=1 if self._split else 0)
+        self.graphs = [g1]
+        if self._split:
+            # the cooperative BN grids of the SECOND graph leave `nccl_sms` SMs to the collective that runs beside it (a cooperative grid
+            # starts only when all of its blocks fit at once; that collective's communicator is capped: parallel.capped_group)
             sm_limit = _lib.load().acan_bn_set_sm_limit(148 - int(nccl_sms))
-        try:
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self.losses = self._forward_backward(phase=1 if self._split else 0)
-            self.graphs = [g1]
-            if self._split:
+            try:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, pool=g1.pool()):
                     self._forward_backward(phase=2)
                 self.graphs.append(g2)
-                self._hook.remove()
-        finally:
-            if sm_limit is not None:
+            finally:
                 _lib.load().acan_bn_set_sm_limit(sm_limit)
+                self._hook.remove()
         self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0)        # kernels of libacan_b200 in one replay
         if self._flat_sgd and self._never_grad:
             # parameters autograd never reached: torch.optim.SGD skips them (no weight decay, no momentum); the frozen table row does the same
@@ -421,11 +421,12 @@ class GraphedTrainStep:
                 self._capture_optimizer()
         if self.world > 1:
             import torch.distributed as dist
-            ar = lambda lo, hi: dist.all_reduce(self._flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)   # noqa: E731
+            ar = lambda lo, hi, grp=None: dist.all_reduce(self._flat[lo:hi], op=dist.ReduceOp.AVG, group=grp if grp is not None else self.group, async_op=True)   # noqa: E731
             self.graphs[0].replay()
             if self._flat_sgd and self.after_backward is None:
                 first, second = self._piece_ranges()
-                works = [(ar(*er), cr) for er, cr in first]      # queued on the NCCL stream, one after the other
+                late_grp = self.overlap_group if self._split else None
+                works = [(ar(*er, late_grp), cr) for er, cr in first]      # queued on the NCCL stream, one after the other
                 if self._split:
                     self.graphs[1].replay()
                     works += [(ar(*er), cr) for er, cr in second]
@@ -437,7 +438,7 @@ class GraphedTrainStep:
                         torch._foreach_copy_(self._shadows, self._shadow_params)
                 return self.losses[3]
             if self._split:
-                wa = ar(self._n_early, self._flat.numel())        # runs beside the second graph
+                wa = ar(self._n_early, self._flat.numel(), self.overlap_group)        # runs beside the second graph
                 self.graphs[1].replay()
                 wb = ar(0, self._n_early)
                 wa.wait()

@@ -245,7 +245,7 @@ def run_train(args, rank, world, device, lib):
     from acan_b200 import ops
     from acan_b200.modules import AttentionLoss2d
     from acan_b200.network import OrdinalRegression2d, ResNet
-    from acan_b200.parallel import GradAllReducer
+    from acan_b200.parallel import GradAllReducer, capped_group
     from acan_b200.training import GraphedTrainStep
     B = TRAIN_BATCH
     torch.manual_seed(2019)
@@ -264,7 +264,8 @@ def run_train(args, rank, world, device, lib):
     graph_note = None
     try:
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
-                                graph=not args.no_graph, overlap=args.split_backward, pieces=args.pieces, nccl_sms=args.nccl_sms)
+                                graph=not args.no_graph, overlap=args.split_backward, pieces=args.pieces, nccl_sms=args.nccl_sms,
+                                overlap_group=capped_group(args.nccl_sms) if (args.split_backward and world > 1) else None)
     except Exception as e:          # same kernels either way: a failed capture must not cost the measurement
         torch.cuda.synchronize()
         graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]})"
@@ -577,8 +578,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    init_distributed("nccl" if world > 1 else None, max_ctas=args.nccl_sms if args.split_backward else None,
-                     min_ctas=args.nccl_min_ctas or None)
+    init_distributed("nccl" if world > 1 else None, min_ctas=args.nccl_min_ctas or None)
     lib = _lib.load()
     _lib.check(lib.acan_device_check(), "acan_device_check")
     torch.backends.cudnn.benchmark = True                 # as depthest_main.py:65

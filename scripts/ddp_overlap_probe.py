@@ -6,13 +6,14 @@ import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.distributed as dist
-from acan_b200.parallel import init_distributed, GradAllReducer
+from acan_b200.parallel import init_distributed, GradAllReducer, capped_group
 from acan_b200.network import ResNet, OrdinalRegression2d
 from acan_b200.modules import AttentionLoss2d
 from acan_b200.training import GraphedTrainStep
 
 NCCL_SMS = int(os.environ.get("PROBE_NCCL_SMS", "16"))
-rank, world, local = init_distributed("nccl", max_ctas=NCCL_SMS)
+rank, world, local = init_distributed("nccl")
+late_group = capped_group(NCCL_SMS)
 dev = torch.device("cuda", local)
 torch.backends.cudnn.benchmark = True
 H, W, B, K = 256, 352, 8, 80
@@ -23,7 +24,7 @@ opt = torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9, weight_decay=5e-4
 red = GradAllReducer(net.parameters())
 x = torch.rand(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
 y = (torch.rand(B, 1, H, W, device=dev) * 10 + 0.5)
-step = GraphedTrainStep(net, crit, opt, x, y, amp_dtype=torch.bfloat16, reducer=red, overlap=True, nccl_sms=NCCL_SMS)
+step = GraphedTrainStep(net, crit, opt, x, y, amp_dtype=torch.bfloat16, reducer=red, overlap=True, nccl_sms=NCCL_SMS, overlap_group=late_group)
 assert step._split
 for _ in range(5):
     step(x, y)
@@ -48,7 +49,7 @@ for it in range(8):
     comm.wait_stream(main)
     with torch.cuda.stream(comm):
         e["ar1s"].record(comm)
-        dist.all_reduce(step._flat[step._n_early:], op=dist.ReduceOp.AVG)
+        dist.all_reduce(step._flat[step._n_early:], op=dist.ReduceOp.AVG, group=late_group)
         e["ar1e"].record(comm)
     step.graphs[1].replay()
     e["g2"].record(main)

@@ -262,18 +262,20 @@ def test_fused_batchnorm_against_torch_fp64(b, c, h, w, dtype):
         yc = torch.nn.functional.batch_norm(xc, rm, rv, wc, bc, True, 0.1, bn.eps)
         if with_res:
             yc = yc + rc
-        pre = yc.detach()
         if relu:
-            yc = torch.relu(yc)
+            # the ReLU mask of an element within rounding of the threshold may differ from fp64's (about one in 1e7 elements: the large
+            # shapes have some) and flips that element's whole gradient -- not an arithmetic error.  The reference therefore takes the
+            # kernel's mask, after checking that it differs from the exact one only at the threshold.
+            pre = yc.detach()
+            mask = (y.detach() > 0).cpu()
+            differs = mask != (pre > 0)
+            assert int(differs.sum()) <= 2 + pre.numel() // 1_000_000 and (not bool(differs.any()) or float(pre[differs].abs().max()) < 1e-3), int(differs.sum())
+            yc = yc * mask
         yc.backward(go.double())
         close(y.float(), yc, tol_half)
-        # the ReLU mask of an element within fp32 rounding of the threshold may differ from fp64's (one in ~1e7 elements at these
-        # magnitudes: the large shapes have some): its whole gradient flips, which is not an arithmetic error -- compare away from it
-        away = (pre.abs() > 1e-5).to(DEV) if relu else torch.ones_like(xd.grad, dtype=torch.bool)
-        assert float((~away).float().mean()) < 1e-4
-        close(xd.grad.float() * away, xc.grad * away.cpu(), tol_half)
+        close(xd.grad.float(), xc.grad, tol_half)
         if with_res:
-            close(rd.grad.float() * away, rc.grad * away.cpu(), tol_half)
+            close(rd.grad.float(), rc.grad, tol_half)
         close(bn.weight.grad, wc.grad, 2e-3 if dtype == torch.float16 else 1e-2)       # the ReLU mask is taken from the ROUNDED output
         close(bn.bias.grad, bc.grad, 2e-3 if dtype == torch.float16 else 1e-2)
         close(bn.running_mean, rm, 1e-5)
