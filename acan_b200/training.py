@@ -11,6 +11,11 @@ One step:
   world = 1   [graph: forward + losses + backward]  ->  optimizer
   world > 1   [graph: forward + losses + backward]  ->  all-reduce(piece 0) all-reduce(piece 1) ... on the NCCL stream
                                                          optimizer(piece 0) as soon as piece 0 has landed, optimizer(piece 1) ...
+  world > 1, overlap=True
+              [graph 1: forward + losses + backward of layer4 / decoder / classifier] -> all-reduce(stage 0) beside
+              [graph 2: backward of layer3]                                           -> all-reduce(stage 1) beside
+              [graph 3: backward of layer2, layer1, the stem]                         -> all-reduce(stage 2: 6 MB, the only exposed one)
+              optimizer(stage 0), optimizer(stage 1), optimizer(stage 2)
 All gradients live in ONE flat fp32 buffer whose slices ARE the ``.grad`` tensors (no gather / scatter copies).  With torch.optim.SGD
 (what the reference trains with, creator/optimizer.py:8-10) the parameters, momentum buffers and 16-bit shadow weights are bound to flat
 buffers as well and the update is ONE streaming kernel (acan_sgd_flat: 1.1 ms of multi-tensor passes -> 0.3 ms), launched per piece, so
@@ -18,8 +23,8 @@ only the first piece's collective and the last piece's update are exposed.  Its 
 ``param_groups`` whenever a scheduler (creator/scheduler.py: step / poly / plateau / cosine) changed them -- no re-capture.  Any other
 optimizer keeps ``optimizer.step()`` in its own CUDA graph, re-captured when the hyper-parameters change (eager after three changes).
 
-``overlap=True`` instead splits the backward at the output of layer3 into two graphs and averages the late layers' gradients while the
-second replays.  Measured on 2 B200s (scripts/ddp_overlap_probe.py, profiles/r02_notes.md): the collective does run concurrently, but
+``overlap=True`` splits the backward at the outputs of layer3 and layer2 into three graphs and averages each stage's gradients while
+the next graph replays.  Measured on 2 B200s (scripts/ddp_overlap_probe.py, profiles/r02_notes.md): the collective does run concurrently, but
 cooperative BatchNorm grids that need every SM cannot start while NCCL's CTAs are resident, so the second graph stalled for as long as
 the collective ran.  The step therefore captures the BN grids of the second graph over 148 - ``nccl_sms`` SMs and issues that collective on
 ``overlap_group``, a communicator capped to ``nccl_sms`` CTAs (``parallel.capped_group``); the exposed collective of the early layers
@@ -56,7 +61,7 @@ class GraphedTrainStep:
 
     def __init__(self, net, criterion, optimizer, images: torch.Tensor, labels: torch.Tensor, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  reducer=None, epoch: int = 1, warmup: int = 3, graph: bool = True, after_backward: Optional[Callable[[], None]] = None,
-                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16, overlap_group=None):
+                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16, overlap_group=None, _force_split: bool = False):
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors: acan_b200 has no CPU path")
         self.net, self.criterion, self.optimizer, self.reducer = net, criterion, optimizer, reducer
@@ -85,9 +90,11 @@ class GraphedTrainStep:
         self._flat_sgd = False
         self._never_grad = set()
         self._pieces = max(int(pieces), 1)
-        self._split = graph and self.world > 1 and overlap and hasattr(net, "layer3")
-        self._boundary = None
-        self._hook = None
+        self._split = graph and (self.world > 1 or _force_split) and overlap and hasattr(net, "layer3") and hasattr(net, "layer2")
+        # stages of the split backward, in the order their gradients complete: 0 = layer4 / decoder / classifier, 1 = layer3, 2 = the rest;
+        # the output of _bound_modules[k] is the boundary between stage k and stage k + 1
+        self._bound_modules = [net.layer3, net.layer2] if self._split else []
+        self._boundaries, self._boundary_grads, self._hooks = {}, {}, []
         if not graph:
             return
         if reducer is not None:
@@ -110,24 +117,29 @@ class GraphedTrainStep:
             s_.grad = None
         from . import _lib
         n0 = _lib.load().acan_launch_count()
-        if self._split:
-            self._hook = net.layer3.register_forward_hook(self._grab_boundary)
+        if self._split and not self._stages_contiguous():
+            self._split, self._bound_modules = False, []       # parameter order does not follow the stages: one backward graph
+        for k, m in enumerate(self._bound_modules):
+            self._hooks.append(m.register_forward_hook(lambda mod, inp, out, k=k: self._boundaries.__setitem__(k, out)))
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             self.losses = self._forward_backward(phase=1 if self._split else 0)
         self.graphs = [g1]
         if self._split:
-            # the cooperative BN grids of the SECOND graph leave `nccl_sms` SMs to the collective that runs beside it (a cooperative grid
+            # the cooperative BN grids of the LATER graphs leave `nccl_sms` SMs to the collective that runs beside them (a cooperative grid
             # starts only when all of its blocks fit at once; that collective's communicator is capped: parallel.capped_group)
             sm_limit = _lib.load().acan_bn_set_sm_limit(148 - int(nccl_sms))
             try:
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, pool=g1.pool()):
-                    self._forward_backward(phase=2)
-                self.graphs.append(g2)
+                for phase in range(2, len(self._bound_modules) + 2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=g1.pool()):
+                        self._forward_backward(phase=phase)
+                    self.graphs.append(g)
             finally:
                 _lib.load().acan_bn_set_sm_limit(sm_limit)
-                self._hook.remove()
+                for h in self._hooks:
+                    h.remove()
+                self._hooks = []
         self.library_launches_per_step = int(_lib.load().acan_launch_count() - n0)        # kernels of libacan_b200 in one replay
         if self._flat_sgd and self._never_grad:
             # parameters autograd never reached: torch.optim.SGD skips them (no weight decay, no momentum); the frozen table row does the same
@@ -149,15 +161,17 @@ class GraphedTrainStep:
         self._flat_params = params
         dev = self.static_x.device
         self._flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
-        late = set()
-        for name in ("layer4", "decoder", "interout", "classifier"):
-            m = getattr(self.net, name, None)
-            if m is not None:
-                late.update(id(p) for p in m.parameters())
-        self._views, off, self._n_early = {}, 0, None
+        stage_of = {}
+        for stage, names in enumerate((("layer4", "decoder", "interout", "classifier"), ("layer3",))):
+            for name in names:
+                m = getattr(self.net, name, None)
+                if m is not None:
+                    stage_of.update((id(p), stage) for p in m.parameters())
+        self._stage_of = {id(p): stage_of.get(id(p), 2) for p in params}
+        self._views, off = {}, 0
+        self._stage_start = {}                                  # stage -> element offset of its first parameter
         for p in params:
-            if self._n_early is None and id(p) in late:
-                self._n_early = off
+            self._stage_start.setdefault(self._stage_of[id(p)], off)
             seg = self._flat[off:off + p.numel()]
             off += p.numel()
             if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
@@ -165,11 +179,14 @@ class GraphedTrainStep:
             else:
                 v = seg.view(p.shape)
             self._views[id(p)] = v
-        if self._n_early is None:
-            self._n_early = off
-        self._late_ids = late
+        self._n_early = self._stage_start.get(0, off)            # kept for callers of the two-segment version: start of the late segment
         shadowed = {id(p) for p in self._shadow_params}
         self._plain_params = [p for p in params if id(p) not in shadowed]      # gradients produced by autograd directly (fp32, small)
+
+    def _stages_contiguous(self) -> bool:
+        """the split schedule all-reduces one slice of the flat buffer per stage: parameters must come as [stage 2 | stage 1 | stage 0]"""
+        order = [self._stage_of[id(p)] for p in self._flat_params]
+        return order == sorted(order, reverse=True) and set(order) == {0, 1, 2}
 
     def _layout_view(self, flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
         seg = flat[off:off + p.numel()]
@@ -261,16 +278,14 @@ class GraphedTrainStep:
                                                  self._hyper.data_ptr(), int(first_chunk), int(n_chunks), int(self._flat.numel()), _lib.current_stream()),
                        "acan_sgd_flat")
 
-    def _grab_boundary(self, module, inputs, output):
-        self._boundary = output
-
     # ------------------------------------------------------------------ pieces of one step
     def _forward_backward(self, phase: int = 0):
-        """phase 0: forward + losses + the whole backward.  phase 1: forward + losses + backward down to the output of layer3 (late
-        parameters and the boundary gradient).  phase 2: backward from the boundary gradient through the early layers."""
+        """phase 0: forward + losses + the whole backward.  phase 1: forward + losses + backward down to the first boundary (stage-0
+        parameters and the boundary gradient).  phase k > 1: backward from boundary k - 2 to boundary k - 1 (the last one: to the input)."""
         out = None
-        late_only = lambda ps: [p for p in ps if id(p) in self._late_ids]            # noqa: E731
-        early_only = lambda ps: [p for p in ps if id(p) not in self._late_ids]       # noqa: E731
+        of_stage = lambda st: (lambda ps: [p for p in ps if self._stage_of[id(p)] == st])      # noqa: E731
+        def leaves_of(st):
+            return of_stage(st)(self._plain_params) + [s_ for p, s_ in zip(self._shadow_params, self._shadows) if self._stage_of[id(p)] == st]
         if phase in (0, 1):
             from .functions import deferred_bn_counters
             with deferred_bn_counters(), torch.autocast("cuda", dtype=self.amp_dtype if self.amp_dtype is not None else torch.bfloat16, enabled=self.amp_dtype is not None):
@@ -284,19 +299,24 @@ class GraphedTrainStep:
             if phase == 0:
                 out[3].backward()
             else:
-                b = self._boundary
-                leaves = late_only(self._plain_params) + [s for p, s in zip(self._shadow_params, self._shadows) if id(p) in self._late_ids]
-                self._boundary_grad = None
-                grads = torch.autograd.grad(out[3], [b] + leaves, allow_unused=True)
-                self._boundary_grad = grads[0]
+                leaves = leaves_of(0)
+                grads = torch.autograd.grad(out[3], [self._boundaries[0]] + leaves, allow_unused=True)
+                self._boundary_grads[0] = grads[0]
                 for t, g in zip(leaves, grads[1:]):
                     t.grad = g
         else:
-            torch.autograd.backward(self._boundary, grad_tensors=self._boundary_grad)
-            self._boundary, self._boundary_grad = None, None
+            k = phase - 2                                         # boundary this phase starts from
+            if k + 1 < len(self._bound_modules):
+                leaves = leaves_of(k + 1)
+                grads = torch.autograd.grad(self._boundaries[k], [self._boundaries[k + 1]] + leaves, grad_outputs=self._boundary_grads[k], allow_unused=True)
+                self._boundary_grads[k + 1] = grads[0]
+                for t, g in zip(leaves, grads[1:]):
+                    t.grad = g
+            else:
+                torch.autograd.backward(self._boundaries[k], grad_tensors=self._boundary_grads[k])
+                self._boundaries, self._boundary_grads = {}, {}
         if hasattr(self, "_views"):
-            pick = (lambda ps: ps) if phase == 0 else (late_only if phase == 1 else early_only)
-            self._collect(pick)
+            self._collect((lambda ps: ps) if phase == 0 else of_stage(phase - 1))
         return out
 
     def _collect(self, pick) -> None:
@@ -380,18 +400,21 @@ class GraphedTrainStep:
                 torch._foreach_copy_(self._shadows, self._shadow_params)
 
     def _piece_ranges(self):
-        """[(element range, chunk range)]: the flat buffer cut into `pieces` runs of whole optimizer chunks -- with the split backward
-        the late layers' runs first (their gradients are complete when the first graph ends)."""
-        ch, n, nch = self._sgd_chunk, self._flat.numel(), self._n_sgd_chunks
+        """[[(element range, chunk range), ...] per backward graph]: the flat buffer cut into runs of whole optimizer chunks.  One
+        graph: `pieces` runs (the update of run k hides the all-reduce of run k + 1).  Split backward: one run per stage, in the order
+        the stages complete (a run may start a few elements inside the stage that completed before it: chunk alignment)."""
+        n = self._flat.numel()
+        ch = self._sgd_chunk if self._flat_sgd else 2048
+        nch = (n + ch - 1) // ch
         def cut(c0, c1, k):
             k = max(1, min(k, c1 - c0))
             edges = [c0 + (c1 - c0) * i // k for i in range(k + 1)]
             return [((a * ch, min(b * ch, n)), (a, b - a)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         if self._split:
-            cb = min((self._n_early + ch - 1) // ch, nch)
-            late, early = cut(cb, nch, max(self._pieces - 1, 1)), cut(0, cb, 1)
-            return late, early
-        return cut(0, nch, self._pieces), []
+            c0 = min((self._stage_start[0] + ch - 1) // ch, nch)       # first whole chunk of stage 0 (layer4, decoder, classifier)
+            c1 = min((self._stage_start[1] + ch - 1) // ch, c0)        # ... of stage 1 (layer3)
+            return [cut(c0, nch, 1), cut(c1, c0, 1), cut(0, c1, 1)]
+        return [cut(0, nch, self._pieces)]
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """one training step; returns the total loss (a device scalar; static across steps when graphed)."""
@@ -422,14 +445,14 @@ class GraphedTrainStep:
         if self.world > 1:
             import torch.distributed as dist
             ar = lambda lo, hi, grp=None: dist.all_reduce(self._flat[lo:hi], op=dist.ReduceOp.AVG, group=grp if grp is not None else self.group, async_op=True)   # noqa: E731
-            self.graphs[0].replay()
+            stages = self._piece_ranges()
+            works = []
+            for k, g in enumerate(self.graphs):
+                g.replay()
+                # collectives of all but the last stage run BESIDE the next graph: capped communicator; the last one is exposed: full width
+                grp = self.overlap_group if (self._split and k + 1 < len(self.graphs)) else None
+                works += [(ar(*er, grp), cr) for er, cr in stages[k]]        # queued on the communicator's stream, one after the other
             if self._flat_sgd and self.after_backward is None:
-                first, second = self._piece_ranges()
-                late_grp = self.overlap_group if self._split else None
-                works = [(ar(*er, late_grp), cr) for er, cr in first]      # queued on the NCCL stream, one after the other
-                if self._split:
-                    self.graphs[1].replay()
-                    works += [(ar(*er), cr) for er, cr in second]
                 for w, (c0, nc) in works:
                     w.wait()                                     # the compute stream waits for THIS piece only
                     self._sgd_range(c0, nc)
@@ -437,16 +460,11 @@ class GraphedTrainStep:
                     with torch.no_grad():
                         torch._foreach_copy_(self._shadows, self._shadow_params)
                 return self.losses[3]
-            if self._split:
-                wa = ar(self._n_early, self._flat.numel(), self.overlap_group)        # runs beside the second graph
-                self.graphs[1].replay()
-                wb = ar(0, self._n_early)
-                wa.wait()
-                wb.wait()
-            else:
-                ar(0, self._flat.numel()).wait()
+            for w, _ in works:
+                w.wait()
         else:
-            self.graphs[0].replay()
+            for g in self.graphs:                                # one graph (more only when a test forces the split schedule on one GPU)
+                g.replay()
         if self.opt_graph is not None:
             self.opt_graph.replay()
         else:

@@ -32,40 +32,39 @@ torch.cuda.synchronize(); dist.barrier()
 main = torch.cuda.current_stream(dev)
 comm = torch.cuda.Stream(dev, priority=-1)
 ev = lambda: torch.cuda.Event(enable_timing=True)
-# the two graphs back to back with no collective in between: what the split itself costs
+# the graphs back to back with no collective in between: what the split itself costs
 for _ in range(3):
-    a, b_ = ev(), ev()
-    a.record(main); step.graphs[0].replay(); m_ = ev(); m_.record(main); step.graphs[1].replay(); b_.record(main)
+    evs = [ev() for _ in range(len(step.graphs) + 1)]
+    evs[0].record(main)
+    for k, g in enumerate(step.graphs):
+        g.replay(); evs[k + 1].record(main)
     torch.cuda.synchronize()
     if rank == 0:
-        print(f"no collective: first graph {a.elapsed_time(m_):.3f} ms, second graph {m_.elapsed_time(b_):.3f} ms, both {a.elapsed_time(b_):.3f} ms", flush=True)
+        print("no collective: " + "  ".join(f"graph {k + 1} {evs[k].elapsed_time(evs[k + 1]):.3f} ms" for k in range(len(step.graphs)))
+              + f"  all {evs[0].elapsed_time(evs[-1]):.3f} ms", flush=True)
 dist.barrier()
+stages = step._piece_ranges()
 rows = []
 for it in range(8):
-    e = {k: ev() for k in ("t0", "g1", "ar1s", "ar1e", "g2", "ar2e", "opt")}
-    e["t0"].record(main)
-    step.graphs[0].replay()
-    e["g1"].record(main)
-    comm.wait_stream(main)
-    with torch.cuda.stream(comm):
-        e["ar1s"].record(comm)
-        dist.all_reduce(step._flat[step._n_early:], op=dist.ReduceOp.AVG, group=late_group)
-        e["ar1e"].record(comm)
-    step.graphs[1].replay()
-    e["g2"].record(main)
-    comm.wait_stream(main)
-    with torch.cuda.stream(comm):
-        dist.all_reduce(step._flat[:step._n_early], op=dist.ReduceOp.AVG)
-        e["ar2e"].record(comm)
+    t0 = ev(); t0.record(main)
+    marks = []
+    for k, g in enumerate(step.graphs):
+        g.replay()
+        eg = ev(); eg.record(main)
+        comm.wait_stream(main)
+        grp = late_group if k + 1 < len(step.graphs) else None
+        with torch.cuda.stream(comm):
+            es = ev(); es.record(comm)
+            for (lo, hi), _ in stages[k]:
+                dist.all_reduce(step._flat[lo:hi], op=dist.ReduceOp.AVG, group=grp)
+            ee = ev(); ee.record(comm)
+        marks.append((eg, es, ee))
     main.wait_stream(comm)
     step._sgd_range(0, step._n_sgd_chunks)
-    e["opt"].record(main)
+    eo = ev(); eo.record(main)
     torch.cuda.synchronize()
-    rows.append({k: e["t0"].elapsed_time(v) for k, v in e.items() if k != "t0"})
+    rows.append([(t0.elapsed_time(a), t0.elapsed_time(b), t0.elapsed_time(c)) for a, b, c in marks] + [t0.elapsed_time(eo)])
 if rank == 0:
     for r in rows[2:]:
-        print("ms from step start: " + "  ".join(f"{k} {v:7.3f}" for k, v in r.items()), flush=True)
-    r = rows[-1]
-    print(f"late all-reduce ran {r['ar1s']:.3f} -> {r['ar1e']:.3f} ms; second backward graph ended at {r['g2']:.3f} ms: "
-          + ("OVERLAPPED" if r["ar1e"] < r["g2"] - 0.05 else "NOT overlapped (the collective finished after the graph)"))
+        print("ms from step start: " + "  ".join(f"graph {k + 1} ends {a:7.3f} its all-reduce {b:7.3f} -> {c:7.3f}" for k, (a, b, c) in enumerate(r[:-1])) + f"  sgd ends {r[-1]:7.3f}", flush=True)
 dist.barrier(); dist.destroy_process_group()

@@ -13,7 +13,7 @@ run pipelined 29632
 run split16 29633 --split-backward --nccl-sms 16
 run split8 29634 --split-backward --nccl-sms 8
 run minctas32 29635 --nccl-min-ctas 32
-tail -n 3 ${P}_tests.log; grep -v Warning ${P}_probe16.log | grep "ms\|exit" | tail -n 8
+tail -n 3 ${P}_tests.log; grep -v Warning ${P}_probe16.log | grep "ms\|exit" | tail -n 12
 python - <<PY
 import json
 for f in ("n1","pipelined","split16","split8","minctas32"):

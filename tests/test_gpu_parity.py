@@ -387,6 +387,40 @@ def test_graphed_train_step_matches_eager():
         assert float((final[True][k] - final[False][k]).abs().max()) <= 0.35 * float(upd) + 1e-7, k
 
 
+def test_split_backward_schedule_gives_the_same_step():
+    """The overlapped multi-GPU schedule (three graphs: forward + late backward | layer3 backward | early backward, BN grids of the
+    later graphs sized for the SMs a collective leaves free) forced onto one GPU: same losses and, after three steps, the same weights
+    as the single-graph step (the narrower BN grids change a summation order, nothing else)."""
+    from acan_b200.training import GraphedTrainStep
+    from acan_b200.network import ResNet, OrdinalRegression2d
+    from acan_b200.modules import AttentionLoss2d
+    hh, ww, b = 64, 96, 4
+    xs = [synth.rand(f"spl.x{i}", b, 3, hh, ww).to(DEV).contiguous(memory_format=torch.channels_last) for i in range(3)]
+    ys = [synth.depth_label(f"spl.y{i}", b, hh, ww, 0.5, 10.5).to(DEV) for i in range(3)]
+    out, final = {}, {}
+    for split in (False, True):
+        torch.manual_seed(synth.SEED)
+        net = ResNet(*NYU, "OR", "soft", "attention", hh, ww, alpha=0, beta=1.0, layers=[1, 1, 2, 1]).to(DEV).to(memory_format=torch.channels_last).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.eval()
+        crit = net.LossFunc(*NYU, AppearanceLoss=OrdinalRegression2d(ignore_index=0), AttentionLoss=AttentionLoss2d(scale=1), alpha=0.0, beta=1.0)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=5e-4)
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        step = GraphedTrainStep(net, crit, opt, xs[0], ys[0], amp_dtype=torch.bfloat16, warmup=2, overlap=split, _force_split=split)
+        assert len(step.graphs) == (3 if split else 1)
+        net.load_state_dict(sd0)
+        step.sync_weights()
+        [buf.zero_() for st_ in opt.state.values() for buf in st_.values() if torch.is_tensor(buf)]
+        out[split] = [float(step(x, y)) for x, y in zip(xs, ys)]
+        final[split] = {k: v.detach().float().clone() for k, v in net.named_parameters()}
+    for a, e in zip(out[True], out[False]):
+        assert abs(a - e) <= 1e-3 * abs(e), (out[True], out[False])
+    for k in final[True]:
+        upd = (final[False][k] - sd0[k].float()).abs().max()
+        assert float((final[True][k] - final[False][k]).abs().max()) <= 0.05 * float(upd) + 1e-7, k
+
+
 def test_flat_sgd_kernel_matches_torch_sgd():
     """acan_sgd_flat (one pass over flat parameter / gradient / momentum buffers, per-group hyper-parameters from a device table, bf16 shadow
     written on the way) == torch.optim.SGD with momentum and weight decay over the same tensors in three parameter groups, step after step,
