@@ -69,6 +69,7 @@ SIGNATURES = {
     "acan_sgd_flat_chunk": (c_int, []),
     "acan_sgd_flat": (c_int, [c_void_p] * 7 + [c_int, c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_void_p]),
     "acan_attention_loss_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p]),
+    "acan_cast_to_f32_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 _lib = None

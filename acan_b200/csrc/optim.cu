@@ -70,6 +70,52 @@ __global__ void __launch_bounds__(kSgdThreads) sgd_flat_kernel(float* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------- 16-bit gradients -> their fp32 slices of the flat buffer, one launch
+// Under autocast the weight gradients of the convolutions come out of cuDNN in 16 bit, one tensor per layer; the optimizer (and the
+// all-reduce) want them in fp32 in the flat buffer.  torch._foreach_copy_ with mixed dtypes falls back to one cast kernel per tensor
+// (121 launches, 0.73 ms of a 13 ms ResNet-101 step for 550 MB of traffic).  Here up to kCastBatch (source, destination, count)
+// triples travel in the kernel's parameter space and every block converts one kCastChunk-element piece of one tensor.
+constexpr int kCastBatch = 96, kCastChunk = 4096, kCastThreads = 256;
+struct CastBatch {
+  const void* src[kCastBatch];
+  float* dst[kCastBatch];
+  unsigned first_chunk[kCastBatch + 1];     // prefix sums of ceil(count / kCastChunk)
+  unsigned count[kCastBatch];
+  int n;
+};
+
+template <bool BF16>
+__device__ __forceinline__ float to_f32(unsigned short h) {
+  if (BF16) return __uint_as_float(static_cast<uint32_t>(h) << 16);
+  return __half2float(__ushort_as_half(h));
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kCastThreads) cast_multi_kernel(const __grid_constant__ CastBatch b) {
+  int lo = 0, hi = b.n;                                   // entry e with first_chunk[e] <= blockIdx.x < first_chunk[e + 1]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (b.first_chunk[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+  const unsigned short* src = static_cast<const unsigned short*>(b.src[lo]);
+  float* dst = b.dst[lo];
+  const unsigned n = b.count[lo];
+  const unsigned base = (blockIdx.x - b.first_chunk[lo]) * kCastChunk;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+#pragma unroll
+  for (int r = 0; r < kCastChunk / (kCastThreads * 8); ++r) {
+    const unsigned i = base + (r * kCastThreads + threadIdx.x) * 8;
+    if (vec && i + 7 < n) {
+      const uint4 u = ldg_nc_u4(reinterpret_cast<const uint4*>(src + i));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { f[2 * e] = to_f32<BF16>(static_cast<unsigned short>(w[e] & 0xffffu)); f[2 * e + 1] = to_f32<BF16>(static_cast<unsigned short>(w[e] >> 16)); }
+      *reinterpret_cast<float4*>(dst + i) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      for (unsigned j = i; j < n && j < i + 8; ++j) dst[j] = to_f32<BF16>(src[j]);
+    }
+  }
+}
 }  // namespace
 }  // namespace acan
 
@@ -89,4 +135,31 @@ extern "C" int acan_sgd_flat(float* param, const float* grad, float* momentum_bu
       param, grad, momentum_buf, static_cast<__nv_bfloat16*>(shadow_bf16), chunk_group, seg_end, seg_group, n_seg,
       reinterpret_cast<const float4*>(hyper), first_chunk, n);
   return launch_status("acan_sgd_flat");
+}
+
+extern "C" int acan_cast_to_f32_multi(const void* const* src, float* const* dst, const long long* count, int n_tensors, int src_dtype, void* stream) {
+  ACAN_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || (src && dst && count)), "acan_cast_to_f32_multi: null table");
+  ACAN_CHECK_ARG(src_dtype == ACAN_DT_F16 || src_dtype == ACAN_DT_BF16, "acan_cast_to_f32_multi: src_dtype %d (ACAN_DT_F16 or ACAN_DT_BF16)", src_dtype);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int t0 = 0; t0 < n_tensors; t0 += kCastBatch) {
+    CastBatch b;
+    b.n = 0;
+    unsigned chunks = 0;
+    for (int t = t0; t < n_tensors && b.n < kCastBatch; ++t) {
+      ACAN_CHECK_ARG(count[t] >= 0 && count[t] < (1ll << 32) - kCastChunk, "acan_cast_to_f32_multi: tensor %d has %lld elements", t, count[t]);
+      if (count[t] == 0) continue;
+      ACAN_CHECK_ARG(src[t] && dst[t] && reinterpret_cast<uintptr_t>(src[t]) % 2 == 0 && reinterpret_cast<uintptr_t>(dst[t]) % 4 == 0,
+                     "acan_cast_to_f32_multi: tensor %d: null or misaligned pointer", t);
+      b.src[b.n] = src[t]; b.dst[b.n] = dst[t]; b.count[b.n] = static_cast<unsigned>(count[t]);
+      b.first_chunk[b.n] = chunks;
+      chunks += static_cast<unsigned>((count[t] + kCastChunk - 1) / kCastChunk);
+      ++b.n;
+    }
+    if (b.n == 0) continue;
+    b.first_chunk[b.n] = chunks;
+    if (src_dtype == ACAN_DT_BF16) cast_multi_kernel<true><<<chunks, kCastThreads, 0, st>>>(b);
+    else                           cast_multi_kernel<false><<<chunks, kCastThreads, 0, st>>>(b);
+    if (int e = launch_status("cast_multi_kernel")) return e;
+  }
+  return 0;
 }

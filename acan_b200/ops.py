@@ -550,3 +550,34 @@ def gt_sim_map(dis_label: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(lab.device):
         _lib.check(_lib.load().acan_gt_sim_map(lab.data_ptr(), gt.data_ptr(), ws.data_ptr(), b, hh, ww, _lib.current_stream()), "acan_gt_sim_map")
     return gt
+
+
+def cast_to_f32_multi(dst, src) -> bool:
+    """dst[i] (fp32) <- src[i] (fp16 / bf16), all pairs in ONE launch per 96 tensors (acan_cast_to_f32_multi).  Every pair must be dense
+    and share one memory order (equal strides); returns False -- nothing done -- when a pair does not qualify, so that the caller can
+    fall back to the framework's copies."""
+    import ctypes
+    if not src:
+        return True
+    dt = src[0].dtype
+    if dt not in (torch.float16, torch.bfloat16):
+        return False
+    for d, s_ in zip(dst, src):
+        if not (s_.is_cuda and d.is_cuda and s_.dtype == dt and d.dtype == torch.float32 and s_.shape == d.shape and s_.stride() == d.stride()
+                and s_.device == d.device and _is_dense(s_)):
+            return False
+    n = len(src)
+    sp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in src])
+    dp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in dst])
+    cn = (ctypes.c_longlong * n)(*[t.numel() for t in src])
+    with torch.cuda.device(src[0].device):
+        _lib.check(_lib.load().acan_cast_to_f32_multi(sp, dp, cn, n, _DT[dt], _lib.current_stream()), "acan_cast_to_f32_multi")
+    return True
+
+
+def _is_dense(t: torch.Tensor) -> bool:
+    """every element of the storage span is an element of the tensor (some permutation of a contiguous tensor)"""
+    if t.numel() == 0:
+        return True
+    span = 1 + sum((sz - 1) * st for sz, st in zip(t.shape, t.stride()))
+    return span == t.numel() and all(st > 0 or sz == 1 for sz, st in zip(t.shape, t.stride()))

@@ -329,7 +329,9 @@ class GraphedTrainStep:
                 dst.append(self._views[id(p)])
                 src.append(s_.grad)
         if dst:
-            torch._foreach_copy_(dst, src)
+            from . import ops
+            if not ops.cast_to_f32_multi(dst, src):               # one launch; the framework's mixed-dtype foreach copy is one kernel per tensor
+                torch._foreach_copy_(dst, src)
         for p, s_ in zip(self._shadow_params, self._shadows):
             if id(p) in chosen:
                 s_.grad = None

@@ -328,6 +328,12 @@ int acan_sgd_flat(float* param, const float* grad, float* momentum_buf, void* sh
                   const long long* seg_end, const int* seg_group, int n_seg, const float* hyper,
                   long long first_chunk, long long n_chunks, long long n, void* stream);
 
+/* n_tensors dense 16-bit tensors -> fp32, one launch per 96 tensors: the step that moves the weight gradients autocast leaves in 16 bit
+ * (one tensor per layer) into their slices of the flat fp32 gradient buffer (acan_b200/training.py; replaces one framework cast kernel
+ * per layer).  src / dst / count are HOST arrays of device pointers and element counts (read during the call; the pointers travel in the
+ * kernels' parameter space, so a captured CUDA graph replays with the captured addresses).  src_dtype: ACAN_DT_F16 or ACAN_DT_BF16. */
+int acan_cast_to_f32_multi(const void* const* src, float* const* dst, const long long* count, int n_tensors, int src_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
