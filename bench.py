@@ -320,7 +320,7 @@ def run_train(args, rank, world, device, lib):
             flat = torch.zeros(n_grad, device=device)
         keep = flat.clone()
         ar_ms = ev_time(lambda: dist.all_reduce(flat, op=dist.ReduceOp.AVG), iters=10) * 1e3
-        ne = getattr(step, "_n_early", n_grad)
+        ne = getattr(step, "_stage_start", {}).get(1, getattr(step, "_n_early", n_grad)) if getattr(step, "_split", False) else getattr(step, "_n_early", n_grad)
         ar_early_ms = ev_time(lambda: dist.all_reduce(flat[:ne], op=dist.ReduceOp.AVG), iters=10) * 1e3
         flat.copy_(keep)
     t = torch.tensor([elapsed, e2e_elapsed, elapsed_long], device=device, dtype=torch.float64)
@@ -388,10 +388,14 @@ def run_train(args, rank, world, device, lib):
     t_bn_b = graph_time([lambda k=k: ops.bn_train_backward(xs[k], ys_[k], gs[k], wgt, mean_, invstd_, False) for k in range(n_rot)])
     bn_elems = float(B * bc * bh * bw)
     if world > 1:
-        sched = ("dp%d: batch-sharded replicas; forward + losses + backward graph, then the flat fp32 gradient buffer is averaged in %d pieces on the (high-priority) "
-                 "NCCL stream, the one-pass SGD kernel updating piece k while piece k+1 is in flight" % (world, args.pieces))
         if getattr(step, "_split", False):
-            sched += "; backward split at layer3 into two graphs, the late layers' pieces all-reduced beside the second"
+            sched = ("dp%d: batch-sharded replicas; three graphs (forward + losses + backward of layer4/decoder/classifier | backward of layer3 | backward of "
+                     "layer2..stem); the flat fp32 gradient slice of each stage is averaged by NCCL BESIDE the next graph (communicator capped to %d CTAs, the "
+                     "BN grids of graphs 2-3 sized for the remaining SMs), only the last stage's %.1f MB all-reduce is exposed; then the one-pass SGD kernel per stage"
+                     % (world, args.nccl_sms, step._stage_start.get(1, 0) * 4 / 1e6))
+        else:
+            sched = ("dp%d: batch-sharded replicas; forward + losses + backward graph, then the flat fp32 gradient buffer is averaged in %d pieces on the (high-priority) "
+                     "NCCL stream, the one-pass SGD kernel updating piece k while piece k+1 is in flight" % (world, args.pieces))
     else:
         sched = "dp1"
     return {
@@ -407,7 +411,7 @@ def run_train(args, rank, world, device, lib):
         "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_elapsed / args.steps * 1e3},
         "gpu_launches": int(launches),
-        "allreduce_ms": ar_ms, "allreduce_early_segment_ms": ar_early_ms, "gradient_bytes": n_grad * 4, "replicas_in_sync": in_sync,
+        "allreduce_ms": ar_ms, "allreduce_exposed_segment_ms": ar_early_ms, "gradient_bytes": n_grad * 4, "replicas_in_sync": in_sync,
         "roofline": {"bound": "hbm", "kernel": "bn_bwd_coop_kernel<bf16> (BN + ReLU backward: one cooperative launch, 14 B per element algorithmic: dy, y, x read for the "
                                "statistics, read again -- from L2 -- for dx, dx written), layer3 shape [8,1024,32,44], stand-alone, graph-replayed over 14 rotating operand sets",
                      "achieved": 14.0 * bn_elems / t_bn_b / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": 14.0 * bn_elems / t_bn_b / 1e9 / pk["hbm"],
@@ -549,8 +553,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying their CUDA graphs")
-    ap.add_argument("--split-backward", action="store_true", help="train, N > 1: split the backward at layer3 and all-reduce the late layers beside the second graph (A/B)")
-    ap.add_argument("--nccl-sms", type=int, default=16, help="with --split-backward: CTAs of the NCCL communicator = SMs the BN grids of the step leave free")
+    ap.add_argument("--no-split-backward", dest="split_backward", action="store_false",
+                    help="train, N > 1: one backward graph and a pipelined all-reduce + SGD instead of the default three backward graphs whose "
+                         "stage all-reduces run beside the next graph (A/B)")
+    ap.add_argument("--nccl-sms", type=int, default=16, help="split backward: CTAs of the communicator of the overlapped all-reduces = SMs the BN grids of graphs 2-3 leave free")
     ap.add_argument("--nccl-min-ctas", type=int, default=0, help="N > 1: lower bound on the CTAs of a collective (ncclConfig_t.minCTAs); 0 = NCCL's default")
     ap.add_argument("--pieces", type=int, default=4, help="train, N > 1: pieces of the flat gradient buffer (all-reduce of piece k+1 runs beside the update of piece k)")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[3]/[4] training sub-record")
