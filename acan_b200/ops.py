@@ -563,7 +563,8 @@ def cast_to_f32_multi(dst, src) -> bool:
     if dt not in (torch.float16, torch.bfloat16):
         return False
     for d, s_ in zip(dst, src):
-        if not (s_.is_cuda and d.is_cuda and s_.dtype == dt and d.dtype == torch.float32 and s_.shape == d.shape and s_.stride() == d.stride()
+        same_order = all(a == b_ for a, b_, sz in zip(s_.stride(), d.stride(), s_.shape) if sz > 1)     # strides of size-1 dims are arbitrary
+        if not (s_.is_cuda and d.is_cuda and s_.dtype == dt and d.dtype == torch.float32 and s_.shape == d.shape and same_order
                 and s_.device == d.device and _is_dense(s_)):
             return False
     n = len(src)
