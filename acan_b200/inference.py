@@ -21,6 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .network import Bottleneck, ResNet
+from .training import _capture_mode
 
 
 def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
@@ -265,7 +266,7 @@ class GraphedPredictor:
             g = torch.cuda.CUDAGraph()
             # one memory pool PER graph: with a shared pool the second capture may place its output in memory the first graph uses
             # for temporaries, and replaying slot 0 would then corrupt depth[1] while its download is still in flight
-            with torch.cuda.graph(g), torch.no_grad():
+            with torch.cuda.graph(g, capture_error_mode=_capture_mode()), torch.no_grad():
                 d = net.inference(net(self.x[slot]))
             self.graphs.append(g)
             self.depth.append(d)

@@ -37,6 +37,15 @@ from typing import Callable, Optional
 import torch
 
 
+def _capture_mode() -> str:
+    """cudaStreamCaptureMode of the step's captures.  With a process group alive, NCCL's watchdog thread polls CUDA events every 100 ms;
+    under the default "global" mode such a call from ANOTHER thread invalidates an ongoing capture -- at random, on some ranks only, which
+    then leaves the ranks on different collective schedules.  "thread_local" restricts the check to the capturing thread (what
+    torch._inductor's CUDA-graph trees use); single-process runs keep the default."""
+    import torch.distributed as dist
+    return "thread_local" if (dist.is_available() and dist.is_initialized()) else "global"
+
+
 def _hyper_signature(optimizer) -> tuple:
     sig = []
     for g in optimizer.param_groups:
@@ -57,11 +66,14 @@ class GraphedTrainStep:
     autocast the weight gradients are produced in 16 bit as well.  Parameters, ``state_dict`` and optimizer state stay fp32.
     ``overlap`` (world > 1): split the backward at the output of ``net.layer3`` as described above (False: one backward graph, one
     all-reduce of the whole buffer).  ``after_backward``: called (and captured) in front of the optimizer step, e.g. gradient clipping.
-    Shapes are fixed at construction (the network is shape-specialised anyway)."""
+    Shapes are fixed at construction (the network is shape-specialised anyway).
+    ``fused_grad_cast``: move the 16-bit weight gradients into the flat buffer with acan_cast_to_f32_multi (one launch) instead of the
+    framework's per-tensor casts."""
 
     def __init__(self, net, criterion, optimizer, images: torch.Tensor, labels: torch.Tensor, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  reducer=None, epoch: int = 1, warmup: int = 3, graph: bool = True, after_backward: Optional[Callable[[], None]] = None,
-                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16, overlap_group=None, _force_split: bool = False):
+                 shadow_weights: Optional[bool] = None, overlap: bool = False, pieces: int = 4, nccl_sms: int = 16, overlap_group=None, fused_grad_cast: bool = False,
+                 _force_split: bool = False):
         if not images.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors: acan_b200 has no CPU path")
         self.net, self.criterion, self.optimizer, self.reducer = net, criterion, optimizer, reducer
@@ -90,6 +102,7 @@ class GraphedTrainStep:
         self._flat_sgd = False
         self._never_grad = set()
         self._pieces = max(int(pieces), 1)
+        self._fused_grad_cast = bool(fused_grad_cast)
         self._split = graph and (self.world > 1 or _force_split) and overlap and hasattr(net, "layer3") and hasattr(net, "layer2")
         # stages of the split backward, in the order their gradients complete: 0 = layer4 / decoder / classifier, 1 = layer3, 2 = the rest;
         # the output of _bound_modules[k] is the boundary between stage k and stage k + 1
@@ -122,7 +135,7 @@ class GraphedTrainStep:
         for k, m in enumerate(self._bound_modules):
             self._hooks.append(m.register_forward_hook(lambda mod, inp, out, k=k: self._boundaries.__setitem__(k, out)))
         g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
+        with torch.cuda.graph(g1, capture_error_mode=_capture_mode()):
             self.losses = self._forward_backward(phase=1 if self._split else 0)
         self.graphs = [g1]
         if self._split:
@@ -132,7 +145,7 @@ class GraphedTrainStep:
             try:
                 for phase in range(2, len(self._bound_modules) + 2):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, pool=g1.pool()):
+                    with torch.cuda.graph(g, pool=g1.pool(), capture_error_mode=_capture_mode()):
                         self._forward_backward(phase=phase)
                     self.graphs.append(g)
             finally:
@@ -330,8 +343,8 @@ class GraphedTrainStep:
                 src.append(s_.grad)
         if dst:
             from . import ops
-            if not ops.cast_to_f32_multi(dst, src):               # one launch; the framework's mixed-dtype foreach copy is one kernel per tensor
-                torch._foreach_copy_(dst, src)
+            if not (self._fused_grad_cast and ops.cast_to_f32_multi(dst, src)):     # one launch; the framework's mixed-dtype foreach copy is
+                torch._foreach_copy_(dst, src)                                      # one kernel per tensor
         for p, s_ in zip(self._shadow_params, self._shadows):
             if id(p) in chosen:
                 s_.grad = None
@@ -390,7 +403,7 @@ class GraphedTrainStep:
             self.opt_graph = None
             return
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self.graphs[0].pool()):
+        with torch.cuda.graph(g, pool=self.graphs[0].pool(), capture_error_mode=_capture_mode()):
             self._optimizer_part()
         self.opt_graph = g
 

@@ -53,6 +53,7 @@ WORKLOAD = "configs[1]: full ACAN fwd (ResNet-101 + CAM + OR soft inference), NY
 # benched arithmetic = fp16 activations through 101 folded-BN layers: max-norm relative depth error vs the fp32 reference; the fp32
 # drop-in network holds 1e-3 (tests/test_gpu_fullsize.py), DESIGN.md section 4 explains the split
 PARITY_TOL_MAX, PARITY_TOL_MEAN = 2.5e-1, 4e-2
+TRAIN_DEADLINE_S = 300   # N > 1: wall-clock bound on the training sub-record of the default line (it normally takes 40-90 s)
 REF_SAMPLE_BATCH = 4     # images per step of the CPU reference arm (a bounded sample of the 16-image step: ~1-3 s of host time per step)
 
 
@@ -269,6 +270,15 @@ def run_train(args, rank, world, device, lib):
     except Exception as e:          # same kernels either way: a failed capture must not cost the measurement
         torch.cuda.synchronize()
         graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]})"
+        print(f"[bench rank {rank}] {graph_note}", file=sys.stderr, flush=True)
+        step = None
+    if world > 1:                   # every rank must run the SAME collective schedule: one failed capture sends all of them to the eager path
+        ok = torch.tensor([0 if step is None else 1], device=device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0 and step is not None:
+            graph_note = "eager (CUDA graph capture failed on another rank)"
+            step = None
+    if step is None:
         reducer.enabled = True
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None, graph=False)
 
@@ -766,7 +776,38 @@ def main():
     # ---- configs[3] / [4]: the training step as a sub-record (all ranks take part: it contains the gradient all-reduce)
     train = None
     if not args.no_train:
-        train = run_train(args, rank, world, device, lib)
+        # N > 1: the sub-record contains collectives.  A hang there (a rank that died, a communicator that never formed) must not cost the
+        # headline, which has none: past the deadline rank 0 prints the line it already has and every rank leaves.
+        guard, done = None, threading.Event()
+        if world > 1:
+            def expire():
+                if done.is_set():
+                    return
+                if rank == 0:
+                    out["train"] = {"error": f"the multi-GPU training sub-record did not finish within {TRAIN_DEADLINE_S} s at N = {world}; the headline (no collective in inference) is unaffected"}
+                    out["cpu_baseline"] = None
+                    sys.stdout.write(json.dumps(out) + "\n")
+                    sys.stdout.flush()
+                os._exit(0)
+            guard = threading.Timer(TRAIN_DEADLINE_S, expire)
+            guard.daemon = True
+            guard.start()
+        try:
+            train = run_train(args, rank, world, device, lib)
+        except Exception as e:
+            if world == 1:
+                raise
+            train = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            print(f"[bench rank {rank}] training sub-record failed: {train['error']}", file=sys.stderr, flush=True)
+        done.set()
+        if guard is not None:
+            guard.cancel()
+        if train is not None and "error" in train and world > 1:       # the other ranks may be stuck in a collective: no orderly shutdown
+            if rank == 0:
+                out["train"], out["cpu_baseline"] = train, None
+                sys.stdout.write(json.dumps(out) + "\n")
+                sys.stdout.flush()
+            os._exit(0)
         free_cuda()
     if rank == 0:
         out["train"] = train
