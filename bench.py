@@ -53,6 +53,15 @@ WORKLOAD = "configs[1]: full ACAN fwd (ResNet-101 + CAM + OR soft inference), NY
 # benched arithmetic = fp16 activations through 101 folded-BN layers: max-norm relative depth error vs the fp32 reference; the fp32
 # drop-in network holds 1e-3 (tests/test_gpu_fullsize.py), DESIGN.md section 4 explains the split
 PARITY_TOL_MAX, PARITY_TOL_MEAN = 2.5e-1, 4e-2
+PROGRESS = {"phase": "not started", "t": 0.0}      # last milestone of the training sub-record (reported if its deadline passes)
+
+
+def milestone(name):
+    PROGRESS["phase"], PROGRESS["t"] = name, time.time()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:          # multi-GPU: a hang must be attributable from stderr
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] train: {name}", file=sys.stderr, flush=True)
+
+
 TRAIN_DEADLINE_S = 300   # N > 1: wall-clock bound on the training sub-record of the default line (it normally takes 40-90 s)
 REF_SAMPLE_BATCH = 4     # images per step of the CPU reference arm (a bounded sample of the 16-image step: ~1-3 s of host time per step)
 
@@ -249,6 +258,7 @@ def run_train(args, rank, world, device, lib):
     from acan_b200.parallel import GradAllReducer, capped_group
     from acan_b200.training import GraphedTrainStep
     B = TRAIN_BATCH
+    milestone("building the network")
     torch.manual_seed(2019)
     net = ResNet(DMIN, DMAX, K, "OR", "soft", "attention", H, W, alpha=0, beta=1.0, layers=LAYERS101).to(device)
     net = net.to(memory_format=torch.channels_last).train()
@@ -263,6 +273,7 @@ def run_train(args, rank, world, device, lib):
     dev_y = [t.to(device, non_blocking=True) for t in host_y]
 
     graph_note = None
+    milestone("GraphedTrainStep: eager warm-up steps (per-parameter all-reduces) and CUDA-graph captures")
     try:
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
                                 graph=not args.no_graph, overlap=args.split_backward, pieces=args.pieces, nccl_sms=args.nccl_sms,
@@ -272,6 +283,7 @@ def run_train(args, rank, world, device, lib):
         graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]})"
         print(f"[bench rank {rank}] {graph_note}", file=sys.stderr, flush=True)
         step = None
+    milestone("captures done on this rank (ok)" if step is not None else "capture FAILED on this rank")
     if world > 1:                   # every rank must run the SAME collective schedule: one failed capture sends all of them to the eager path
         ok = torch.tensor([0 if step is None else 1], device=device, dtype=torch.int32)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -287,9 +299,11 @@ def run_train(args, rank, world, device, lib):
             dist.barrier()
         torch.cuda.synchronize()
 
+    milestone("first replayed steps (stage all-reduces + SGD)")
     for i in range(max(args.warmup, 3)):
         step(dev_x[i % n_rot], dev_y[i % n_rot])
     barrier()
+    milestone("timed steps")
     launches0 = lib.acan_launch_count()
     sampler = ClockSampler(device.index)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -784,7 +798,8 @@ def main():
                 if done.is_set():
                     return
                 if rank == 0:
-                    out["train"] = {"error": f"the multi-GPU training sub-record did not finish within {TRAIN_DEADLINE_S} s at N = {world}; the headline (no collective in inference) is unaffected"}
+                    out["train"] = {"error": f"the multi-GPU training sub-record did not finish within {TRAIN_DEADLINE_S} s at N = {world}; the headline (no collective in inference) is unaffected",
+                                    "rank0_last_milestone": PROGRESS["phase"], "seconds_in_it": round(time.time() - PROGRESS["t"], 1)}
                     out["cpu_baseline"] = None
                     sys.stdout.write(json.dumps(out) + "\n")
                     sys.stdout.flush()
