@@ -46,6 +46,26 @@ def _capture_mode() -> str:
     return "thread_local" if (dist.is_available() and dist.is_initialized()) else "global"
 
 
+def piece_ranges(n: int, ch: int, stage_start: Optional[dict], pieces: int) -> list:
+    """[[(element range, chunk range), ...] per backward graph]: a flat buffer of ``n`` elements cut into runs of whole optimizer chunks of
+    ``ch`` elements.  One graph (``stage_start`` None): ``pieces`` runs (the update of run k hides the all-reduce of run k + 1).  Split
+    backward: one run per stage, in the order the stages complete -- stage 0 (layer4 / decoder / classifier: the END of the buffer), stage 1
+    (layer3), stage 2 (the rest: the START); ``stage_start[k]`` is the element offset of stage k's first parameter.  A run may start a few
+    elements inside the stage that completed before it (chunk alignment): those gradients are complete by then.  Every element belongs to
+    exactly one run."""
+    nch = (n + ch - 1) // ch
+
+    def cut(c0, c1, k):
+        k = max(1, min(k, c1 - c0))
+        edges = [c0 + (c1 - c0) * i // k for i in range(k + 1)]
+        return [((a * ch, min(b * ch, n)), (a, b - a)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    if stage_start is not None:
+        c0 = min((stage_start[0] + ch - 1) // ch, nch)       # first whole chunk of stage 0
+        c1 = min((stage_start[1] + ch - 1) // ch, c0)        # ... of stage 1
+        return [cut(c0, nch, 1), cut(c1, c0, 1), cut(0, c1, 1)]
+    return [cut(0, nch, pieces)]
+
+
 def _hyper_signature(optimizer) -> tuple:
     sig = []
     for g in optimizer.param_groups:
@@ -415,21 +435,7 @@ class GraphedTrainStep:
                 torch._foreach_copy_(self._shadows, self._shadow_params)
 
     def _piece_ranges(self):
-        """[[(element range, chunk range), ...] per backward graph]: the flat buffer cut into runs of whole optimizer chunks.  One
-        graph: `pieces` runs (the update of run k hides the all-reduce of run k + 1).  Split backward: one run per stage, in the order
-        the stages complete (a run may start a few elements inside the stage that completed before it: chunk alignment)."""
-        n = self._flat.numel()
-        ch = self._sgd_chunk if self._flat_sgd else 2048
-        nch = (n + ch - 1) // ch
-        def cut(c0, c1, k):
-            k = max(1, min(k, c1 - c0))
-            edges = [c0 + (c1 - c0) * i // k for i in range(k + 1)]
-            return [((a * ch, min(b * ch, n)), (a, b - a)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
-        if self._split:
-            c0 = min((self._stage_start[0] + ch - 1) // ch, nch)       # first whole chunk of stage 0 (layer4, decoder, classifier)
-            c1 = min((self._stage_start[1] + ch - 1) // ch, c0)        # ... of stage 1 (layer3)
-            return [cut(c0, nch, 1), cut(c1, c0, 1), cut(0, c1, 1)]
-        return [cut(0, nch, self._pieces)]
+        return piece_ranges(self._flat.numel(), self._sgd_chunk if self._flat_sgd else 2048, self._stage_start if self._split else None, self._pieces)
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """one training step; returns the total loss (a device scalar; static across steps when graphed)."""

@@ -64,3 +64,38 @@ def test_grad_allreduce_world2_gloo():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert len(out) == 4 * world
     assert all(v < 1e-6 for v in out.values()), dict(out)
+
+
+def _stage_worker(rank, world, port, out):
+    """the stage schedule of the overlapped training step on a flat gradient buffer: one asynchronous all-reduce per run of
+    training.piece_ranges, issued in stage order, waited for in that order, each followed by the (here: CPU) update of its run"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from acan_b200.parallel import init_distributed
+    from acan_b200.training import piece_ranges
+    init_distributed("gloo")
+    n, ch = 2048 * 9 + 77, 2048
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(n, generator=g)
+    want = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + q)) for q in range(world)) / world
+    param = torch.zeros(n)
+    for stage_start, pieces in (({2: 0, 1: 3000, 0: 11000}, 4), (None, 4), (None, 1)):
+        buf, param = flat.clone(), torch.zeros(n)
+        works = []
+        for runs in piece_ranges(n, ch, stage_start, pieces):          # (a graph replay would sit between the stages)
+            works += [(dist.all_reduce(buf[lo:hi], op=dist.ReduceOp.SUM, async_op=True), (lo, hi)) for (lo, hi), _ in runs]
+        for w, (lo, hi) in works:
+            w.wait()
+            param[lo:hi] -= 0.1 * buf[lo:hi] / world                   # the per-run update
+        out[(rank, str(stage_start), pieces)] = float((param + 0.1 * want).abs().max())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stage_allreduce_schedule_world2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_stage_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out) == 3 * world
+    assert all(v < 1e-6 for v in out.values()), dict(out)

@@ -190,3 +190,32 @@ def test_batched_tta_drivers_match_reference_golden(golden):
     with pytest.raises(_lib.AcanLibraryError, match="no CPU path"):
         E.compute_errors(torch.ones(1, 4, 4), torch.ones(1, 4, 4))
     assert _lib.load().acan_depth_metrics(8, 8, 8, 8, 0, 1, None) == 10001
+
+
+def test_piece_ranges_partition_the_flat_gradient_buffer():
+    """host logic of the multi-GPU training step (acan_b200.training.piece_ranges): the runs handed to the all-reduces / the SGD kernel
+    cover every element exactly once, consist of whole optimizer chunks, and in the split schedule come in the order the stages' gradients
+    complete, each run starting at or after its stage's first element (never before: those gradients would not be complete yet)."""
+    from acan_b200.training import piece_ranges
+    for n, ch, pieces in ((92_000_123, 2048, 4), (2048 * 7, 2048, 4), (5000, 2048, 8), (1, 2048, 4), (2048 * 3 + 1, 2048, 1)):
+        (runs,) = piece_ranges(n, ch, None, pieces)
+        assert runs[0][0][0] == 0 and runs[-1][0][1] == n and len(runs) <= pieces
+        for ((lo, hi), (c0, nc)), nxt in zip(runs, runs[1:] + [None]):
+            assert lo == c0 * ch and hi == min((c0 + nc) * ch, n) and hi > lo
+            assert nxt is None or nxt[0][0] == hi
+    n, ch = 92_000_123, 2048
+    for s1, s0 in ((1_500_000, 28_000_000), (2048 * 10, 2048 * 20), (100, 200), (0, 0), (n - 5, n - 5), (4096, n)):
+        stages = piece_ranges(n, ch, {2: 0, 1: s1, 0: s0}, 4)
+        assert len(stages) == 3
+        flat = [r for st in stages for r in st]
+        covered = sorted(r[0] for r in flat)
+        pos = 0
+        for lo, hi in covered:                                   # a partition of [0, n)
+            assert lo == pos and hi > lo
+            pos = hi
+        assert pos == n
+        for (lo, hi), (c0, nc) in flat:
+            assert lo == c0 * ch and hi == min((c0 + nc) * ch, n)
+        for k, start in ((0, s0), (1, s1)):                      # a stage's run never begins inside a stage that completes LATER
+            for (lo, hi), _ in stages[k]:
+                assert lo >= start
