@@ -277,7 +277,7 @@ def run_train(args, rank, world, device, lib):
     try:
         step = GraphedTrainStep(net, crit, opt, dev_x[0], dev_y[0], amp_dtype=torch.bfloat16, reducer=reducer if world > 1 else None,
                                 graph=not args.no_graph, overlap=args.split_backward, pieces=args.pieces, nccl_sms=args.nccl_sms,
-                                overlap_group=capped_group(args.nccl_sms) if (args.split_backward and world > 1) else None)
+                                overlap_group=capped_group(args.nccl_sms) if (args.two_communicators and args.split_backward and world > 1) else None)
     except Exception as e:          # same kernels either way: a failed capture must not cost the measurement
         torch.cuda.synchronize()
         graph_note = f"eager (CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]})"
@@ -435,7 +435,9 @@ def run_train(args, rank, world, device, lib):
         "e2e": {"value": world * B * args.steps / e2e_elapsed, "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_elapsed / args.steps * 1e3},
         "gpu_launches": int(launches),
-        "allreduce_ms": ar_ms, "allreduce_exposed_segment_ms": ar_early_ms, "gradient_bytes": n_grad * 4, "replicas_in_sync": in_sync,
+        "allreduce_ms": ar_ms, "allreduce_exposed_segment_ms": ar_early_ms,
+        "allreduce_note": (f"timed on the step's communicator, capped to {args.nccl_sms} CTAs so that it can run beside the backward graphs (uncapped: 0.70 ms for the whole buffer at 2 GPUs)"
+                           if (world > 1 and args.split_backward and not args.two_communicators) else None), "gradient_bytes": n_grad * 4, "replicas_in_sync": in_sync,
         "roofline": {"bound": "hbm", "kernel": "bn_bwd_coop_kernel<bf16> (BN + ReLU backward: one cooperative launch, 14 B per element algorithmic: dy, y, x read for the "
                                "statistics, read again -- from L2 -- for dx, dx written), layer3 shape [8,1024,32,44], stand-alone, graph-replayed over 14 rotating operand sets",
                      "achieved": 14.0 * bn_elems / t_bn_b / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": 14.0 * bn_elems / t_bn_b / 1e9 / pk["hbm"],
@@ -580,6 +582,9 @@ def main():
     ap.add_argument("--no-split-backward", dest="split_backward", action="store_false",
                     help="train, N > 1: one backward graph and a pipelined all-reduce + SGD instead of the default three backward graphs whose "
                          "stage all-reduces run beside the next graph (A/B)")
+    ap.add_argument("--two-communicators", action="store_true",
+                    help="split backward: overlapped all-reduces on a second, capped communicator and the exposed one on an uncapped default communicator "
+                         "(measured equal at 2 GPUs; the default is one capped communicator: fewer moving parts)")
     ap.add_argument("--nccl-sms", type=int, default=16, help="split backward: CTAs of the communicator of the overlapped all-reduces = SMs the BN grids of graphs 2-3 leave free")
     ap.add_argument("--nccl-min-ctas", type=int, default=0, help="N > 1: lower bound on the CTAs of a collective (ncclConfig_t.minCTAs); 0 = NCCL's default")
     ap.add_argument("--pieces", type=int, default=4, help="train, N > 1: pieces of the flat gradient buffer (all-reduce of piece k+1 runs beside the update of piece k)")
@@ -608,7 +613,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    init_distributed("nccl" if world > 1 else None, min_ctas=args.nccl_min_ctas or None)
+    # split backward (default): ONE communicator capped to --nccl-sms CTAs -- the overlapped stage all-reduces must leave the BN grids their SMs,
+    # and the only exposed collective is the last stage's 5.8 MB, which does not need more
+    init_distributed("nccl" if world > 1 else None, max_ctas=args.nccl_sms if (args.split_backward and not args.two_communicators) else None,
+                     min_ctas=args.nccl_min_ctas or None)
     lib = _lib.load()
     _lib.check(lib.acan_device_check(), "acan_device_check")
     torch.backends.cudnn.benchmark = True                 # as depthest_main.py:65
