@@ -30,6 +30,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import faulthandler
 import gc
 import json
 import math
@@ -805,6 +806,10 @@ def main():
             def expire():
                 if done.is_set():
                     return
+                try:
+                    faulthandler.dump_traceback(file=sys.stderr, all_threads=True)      # where this rank is stuck
+                except Exception:
+                    pass
                 if rank == 0:
                     out["train"] = {"error": f"the multi-GPU training sub-record did not finish within {TRAIN_DEADLINE_S} s at N = {world}; the headline (no collective in inference) is unaffected",
                                     "rank0_last_milestone": PROGRESS["phase"], "seconds_in_it": round(time.time() - PROGRESS["t"], 1)}
@@ -815,6 +820,7 @@ def main():
             guard = threading.Timer(TRAIN_DEADLINE_S, expire)
             guard.daemon = True
             guard.start()
+            faulthandler.dump_traceback_later(TRAIN_DEADLINE_S + 45, exit=True)       # C-level backstop: fires even if a blocked call holds the GIL
         try:
             train = run_train(args, rank, world, device, lib)
         except Exception as e:
@@ -825,6 +831,7 @@ def main():
         done.set()
         if guard is not None:
             guard.cancel()
+            faulthandler.cancel_dump_traceback_later()
         if train is not None and "error" in train and world > 1:       # the other ranks may be stuck in a collective: no orderly shutdown
             if rank == 0:
                 out["train"], out["cpu_baseline"] = train, None
