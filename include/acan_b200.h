@@ -137,8 +137,8 @@ int acan_maxpool3x3s2_nhwc(const void* x, void* y, int dtype, int B, int H, int 
  *   x, y, residual, grad_*: [M, C] (M = B*H*W, channels contiguous), dtype 0 = fp16 / 1 = bf16, C % 8 == 0, 16-byte aligned
  *   y = [relu]( (x - mean) * invstd * weight + bias [+ residual] );   save_mean / save_invstd [C] fp32 are kept for backward
  *   running_mean / running_var: NULL (track_running_stats = False) or [C] fp32, updated in place
- *   ws: acan_bn_ws_floats(C) floats, ZERO-INITIALISED ONCE by the caller (it holds self-resetting arrival counters) and not shared
- *       between streams.
+ *   ws: acan_bn_ws_floats(C) floats, ZERO-INITIALISED ONCE by the caller (it holds self-resetting arrival counters and the generation
+ *       words of the slab barrier, which keep whatever value the last call left) and not shared between streams.
  *   backward: y = the forward output when a ReLU was fused (its sign is the mask), else NULL; grad_residual: NULL, or receives the
  *       masked upstream gradient (what flows into the residual branch); grad_weight / grad_bias [C] fp32. */
 size_t acan_bn_ws_floats(int C);
