@@ -1,12 +1,17 @@
-"""GPU tests (-m gpu) of code that has not run on hardware yet (written after the round's GPU budget was spent).  The file sorts last and
-the tests are xfail(strict=False): a failure here is recorded, it cannot stop `pytest -x` or poison the CUDA context of the validated
-suite in front of it.  Nothing in the default training / inference paths calls this code (GraphedTrainStep(fused_grad_cast=True) opts in)."""
+"""GPU tests (-m gpu) of code that has not run on hardware yet (written after the round's GPU budget was spent).  Nothing in the default
+training / inference paths calls this code (GraphedTrainStep(fused_grad_cast=True) opts in).  The tests run only on request
+(RUN_UNVALIDATED_GPU_TESTS=1 python -m pytest tests/test_zz_gpu_unvalidated.py -m gpu): a kernel that has never executed must not be able
+to poison the CUDA context of, or stop, the validated suite in a `pytest -x` run.  The file sorts last and the tests are xfail(strict=False)
+on top of that."""
+import os
+
 import pytest
 import torch
 
 import synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first run on hardware: acan_cast_to_f32_multi was written after the GPU budget was spent")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("RUN_UNVALIDATED_GPU_TESTS") != "1", reason="opt-in: code that has not run on hardware yet"),
+              pytest.mark.xfail(strict=False, reason="first run on hardware: acan_cast_to_f32_multi was written after the GPU budget was spent")]
 DEV = "cuda"
 
 
